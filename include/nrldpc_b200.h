@@ -1,0 +1,147 @@
+/*
+ * nrldpc_b200.h -- C ABI of the B200-native 3GPP NR LDPC engine (libnrldpc_b200.so).
+ *
+ * This is the drop-in boundary for the reference's LDPC hot path.  Each entry point names the
+ * reference interface it stands in for (file:line relative to robmaunder/ldpc-3gpp-matlab).
+ * Plain C: opaque handle, raw pointers and sizes, integer status codes, no C++/torch types.
+ *
+ * Conventions shared by every call
+ *   - LLR sign: positive => bit 0 (NRLDPCDecoder.m:264 maps known-zero filler bits to +inf).
+ *   - "cw layout": the full lifted codeword of n_cw = cols*Z entries (68Z for BG1, 52Z for BG2),
+ *     i.e. cw_tilde of NRLDPCDecoder.m:262 -- 2Z punctured systematic positions first.
+ *   - bits are one per uint8_t (0/1); batches are row-major [batch][len].
+ *   - mem: NRLDPC_MEM_HOST   buffers are host memory; the call copies in/out (pipelined over
+ *                            internal streams) and returns when the outputs are valid
+ *                            (MATLAB value semantics);
+ *          NRLDPC_MEM_DEVICE buffers are device memory on the handle's GPU; work is enqueued
+ *                            on `stream` (a cudaStream_t passed as void*, NULL = default
+ *                            stream) and the call returns without synchronising.
+ *   - status: 0 or a negative NRLDPC_E*; text via nrldpc_last_error().  Never aborts/throws.
+ *     NRLDPC_EUNSUPPORTED <-> error('ldpc_3gpp_matlab:UnsupportedParameters',...) (callers catch
+ *     and skip: plot_BLER_vs_SNR.m:172-176), NRLDPC_ESHAPE <-> 'ldpc_3gpp_matlab:Error'.
+ *   - a handle is not thread-safe; distinct handles are independent.
+ */
+#ifndef NRLDPC_B200_H
+#define NRLDPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRLDPC_OK            0
+#define NRLDPC_EUNSUPPORTED (-1)
+#define NRLDPC_ESHAPE       (-2)
+#define NRLDPC_ECUDA        (-3)
+#define NRLDPC_ENOMEM       (-4)
+
+#define NRLDPC_MEM_HOST   0
+#define NRLDPC_MEM_DEVICE 1
+
+/* Input LLR magnitudes are clamped to this value on load (NaN and +inf filler -> +LLR_MAX). */
+#define NRLDPC_LLR_MAX 1048576.0f
+
+typedef struct nrldpc_handle nrldpc_t;
+
+/* Replaces the name-value constructor comm.LDPCDecoder('ParityCheckMatrix',H,
+ * 'MaximumIterationCount',iterations,'IterationTerminationCondition','Parity check satisfied')
+ * at NRLDPCDecoder.m:120 and comm.LDPCEncoder('ParityCheckMatrix',H) at NRLDPCEncoder.m:49.
+ * H is implied by (bg, Z): H = get_pcm(get_3gpp_base_graph(bg, i_LS(Z)), Z) (NRLDPC.m:433-440). */
+typedef struct nrldpc_cfg {
+    int32_t bg;         /* 1 or 2 (NRLDPC.m:240-245) */
+    int32_t Z;          /* lifting size, one of the 51 of TS 38.212 Table 5.3.2-1 */
+    int32_t max_iters;  /* MaximumIterationCount, >= 1 (NRLDPCDecoder.m:41: default 50) */
+    int32_t early_term; /* 1 = 'Parity check satisfied' (NRLDPCDecoder.m:120), 0 = 'Maximum iteration count' */
+    float   alpha;      /* min-sum normalisation; <= 0 selects the default 0.75 */
+    int32_t device;     /* CUDA device ordinal, -1 = current device */
+    int32_t reserved[2];
+} nrldpc_cfg;
+
+int  nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg);
+void nrldpc_destroy(nrldpc_t *h);                      /* release(obj) */
+const char *nrldpc_last_error(const nrldpc_t *h);      /* h == NULL: last create() failure */
+int  nrldpc_synchronize(nrldpc_t *h);                  /* waits for all work enqueued through h */
+
+/* Geometry of the handle's code: K = kcols*Z, N = (cols-2)*Z (NRLDPC.m:414-454), n_cw = cols*Z. */
+typedef struct nrldpc_dims {
+    int32_t bg, Z, i_LS, rows, cols, kcols, edges, K, N, n_cw;
+} nrldpc_dims;
+int nrldpc_get_dims(const nrldpc_t *h, nrldpc_dims *out);
+
+/* Table 5.3.2-1 helpers: get_3gpp_set_index.m:1-13 and get_3gpp_lifting_size.m:1-17.
+ * Return NRLDPC_EUNSUPPORTED where the reference raises UnsupportedParameters. */
+int nrldpc_set_index(int32_t Z);
+int nrldpc_lifting_size(int32_t K_b, int32_t K_prime);
+
+/* get_3gpp_base_graph.m:1-534 -- base-graph edges sorted by (row, col) with raw shifts of set
+ * i_LS.  Any output may be NULL.  Returns the edge count (316 / 197) or a negative status. */
+int nrldpc_base_graph(int32_t bg, int32_t i_LS, int32_t *rows, int32_t *cols, int32_t *shifts);
+
+/* ---- decode: replaces step(obj.hLDPCDecoder, cw_tilde) at NRLDPCDecoder.m:265 ----------------
+ * Layered normalized min-sum (float32) over base rows 0..n_rows-1 (n_rows = 0 -> all rows;
+ * 4 <= n_rows).  Rows whose parity bit was not transmitted carry zero LLR and contribute nothing,
+ * so callers may trim them (DESIGN.md "active rows").
+ *   llr       [batch][n_cw] float32, cw layout; +inf / NaN = filler; exact 0 = punctured / unsent
+ *   info_hard [batch][K] uint8, hard decision (app < 0) of the information part (required)
+ *   app_soft  [batch][n_cw] float32 a-posteriori LLRs after the last iteration (nullable)
+ *   iters     [batch] int32 iterations executed (nullable)
+ *   parity_ok [batch] uint8, 1 if every check of the active rows is satisfied (nullable) */
+int nrldpc_decode(nrldpc_t *h, const float *llr, int64_t batch, int32_t n_rows,
+                  uint8_t *info_hard, float *app_soft, int32_t *iters, uint8_t *parity_ok,
+                  int32_t mem, void *stream);
+
+/* ---- encode: replaces step(obj.hLDPCEncoder, c) at NRLDPCEncoder.m:158 ------------------------
+ *   info [batch][K] uint8 (filler positions must already be 0, NRLDPCEncoder.m:153)
+ *   cw   [batch][n_cw] uint8 systematic codeword [info ; parity], H*cw = 0 */
+int nrldpc_encode(nrldpc_t *h, const uint8_t *info, int64_t batch, uint8_t *cw,
+                  int32_t mem, void *stream);
+
+/* Per-code-block rate-matching geometry: the scalars NRLDPCEncoder.bit_selection /
+ * NRLDPCDecoder.bit_selection read from the NRLDPC getters (NRLDPCDecoder.m:201-208). */
+typedef struct nrldpc_rm {
+    int32_t E;        /* E_r  (NRLDPC.m:485-507) */
+    int32_t k_0;      /* NRLDPC.m:510-543 */
+    int32_t N_cb;     /* NRLDPC.m:463-469 */
+    int32_t K_prime;  /* NRLDPC.m:380-382; filler = d positions [max(K'-2Z,0), K-2Z) */
+    int32_t Q_m;      /* 1,2,4,6,8 (NRLDPC.m:278-283); E % Q_m == 0 */
+} nrldpc_rm;
+
+/* ---- rate match: replaces NRLDPCEncoder.bit_selection + bit_interleaving
+ * (NRLDPCEncoder.m:168-225) applied to d = cw(2Z+1:end) with filler skipped (:155,:190).
+ *   cw [batch][n_cw] uint8 -> f [batch][E] uint8 */
+int nrldpc_rate_match(nrldpc_t *h, const uint8_t *cw, int64_t batch, const nrldpc_rm *rm,
+                      uint8_t *f, int32_t mem, void *stream);
+
+/* ---- rate recover: replaces NRLDPCDecoder.bit_interleaving + bit_selection + the cw_tilde
+ * assembly of LDPC_coding (NRLDPCDecoder.m:172-242 and :262-264) in one pass.
+ *   f       [batch][E] float32 demodulator LLRs
+ *   harq    [batch][N] float32 d_tilde_buffer (NRLDPCDecoder.m:236-239), read-modify-written over
+ *           [0, N_cb); nullable (I_HARQ = 0)
+ *   llr_cw  [batch][n_cw] float32 decoder input: 2Z zeros, soft-combined LLRs, +inf at filler */
+int nrldpc_rate_recover(nrldpc_t *h, const float *f, int64_t batch, const nrldpc_rm *rm,
+                        float *harq, float *llr_cw, int32_t mem, void *stream);
+
+/* ---- channel leg of plot_BLER_vs_SNR.m:129-132 on device (QPSK only): Philox information bits
+ * are NOT generated here; this maps f bits to TS 38.211 QPSK (NRModulator.m:75), adds complex
+ * AWGN of total variance `variance` (comm.AWGNChannel, plot_BLER_vs_SNR.m:50,105) from a
+ * counter-based generator keyed by (seed, stream_id, bit pair index), and demaps with the exact
+ * LLR 2*sqrt(2)*y/variance (NRDemodulator.m:78; Variance as plot_BLER_vs_SNR.m:106).
+ *   f_bits [batch][E] uint8 (E even) -> f_llr [batch][E] float32.  Device memory only. */
+int nrldpc_qpsk_awgn_llr(nrldpc_t *h, const uint8_t *f_bits, int64_t batch, int32_t E,
+                         float variance, uint64_t seed, uint64_t stream_id, float *f_llr,
+                         void *stream);
+
+/* Pinned host allocations for callers that want truly asynchronous NRLDPC_MEM_HOST transfers. */
+void *nrldpc_host_alloc(uint64_t bytes);
+void  nrldpc_host_free(void *p);
+
+/* Launch bookkeeping for benchmarks: kernels launched through this handle since creation. */
+int64_t nrldpc_launch_count(const nrldpc_t *h);
+
+const char *nrldpc_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRLDPC_B200_H */

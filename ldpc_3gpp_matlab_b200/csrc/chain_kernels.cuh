@@ -1,0 +1,224 @@
+// chain_kernels.cuh -- companion kernels either side of the decoder: QC encoder, rate matching,
+// rate recovery (+HARQ combine, filler / puncture handling) and the QPSK/AWGN/LLR channel leg.
+// All HBM-bound byte/float streaming: coalesced accesses, one thread per output element, no
+// tensor cores.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace nrldpc {
+
+// ------------------------------------------------------------------------------------------------
+// Encoder: replaces step(obj.hLDPCEncoder, c) (NRLDPCEncoder.m:158).  H = [A B 0; C D I] with B
+// dual-diagonal, so parity is found by back-substitution instead of a generic GF(2) solve:
+//   lambda_r = sum_{systematic cols} P^{s} c      (r = 0..3)
+//   P^{delta} p0 = lambda_0 + lambda_1 + lambda_2 + lambda_3
+//   p1, p2, p3 by substitution down the diagonal; extension parity p_r = row r times [c p0..p3].
+// One CTA per codeword, thread z owns lane z of every circulant; bits as bytes in shared memory.
+// ------------------------------------------------------------------------------------------------
+struct EncArgs {
+    const uint8_t *info;      // [batch][K]
+    uint8_t *cw;              // [batch][ncw]
+    long long batch;
+    int Z, ncols, kcols, n_rows, n_edges;
+    const uint32_t *edesc;    // (col*Z) << 16 | shift
+    const int *row_start;
+    int s0[4];                // shift of column kcols in rows 0..3, -1 if absent
+    int delta;                // surviving rotation of p0 in the sum of the four core rows
+};
+
+__device__ __forceinline__ int wrap_add(int z, int s, int Z) {
+    int p = z + s;
+    return p >= Z ? p - Z : p;
+}
+
+__global__ void __launch_bounds__(384) encode_kernel(const EncArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int Z = a.Z, K = a.kcols * Z, ncw = a.ncols * Z;
+    uint8_t *sys = smem_raw;                                  // [(kcols+4)*Z] info + core parity
+    uint32_t *s_ed = reinterpret_cast<uint32_t *>(smem_raw + (((a.kcols + 4) * Z + 15) & ~15));
+    int *s_rs = reinterpret_cast<int *>(s_ed + a.n_edges);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < a.n_edges; i += blockDim.x) s_ed[i] = a.edesc[i];
+    for (int i = tid; i <= a.n_rows; i += blockDim.x) s_rs[i] = a.row_start[i];
+
+    for (long long b = blockIdx.x; b < a.batch; b += gridDim.x) {
+        __syncthreads();
+        const uint8_t *src = a.info + b * K;
+        uint8_t *dst = a.cw + b * ncw;
+        for (int i = tid; i < K; i += blockDim.x) {
+            const uint8_t v = src[i] & 1;
+            sys[i] = v;
+            dst[i] = v;
+        }
+        __syncthreads();
+        for (int z = tid; z < Z; z += blockDim.x) {  // blockDim >= Z in practice: one pass
+            uint8_t lam[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                uint8_t acc = 0;
+                for (int e = s_rs[r]; e < s_rs[r + 1]; ++e) {
+                    const uint32_t d = s_ed[e];
+                    const int cb = (int)(d >> 16);
+                    if (cb < K) acc ^= sys[cb + wrap_add(z, (int)(d & 0xffffu), Z)];
+                }
+                lam[r] = acc;
+            }
+            sys[K + wrap_add(z, a.delta, Z)] = lam[0] ^ lam[1] ^ lam[2] ^ lam[3];
+            // stash lambda for the substitution after the barrier
+            sys[K + Z + z] = lam[0];
+            sys[K + 2 * Z + z] = lam[1];
+            sys[K + 3 * Z + z] = lam[2];
+        }
+        __syncthreads();
+        for (int z = tid; z < Z; z += blockDim.x) {
+            uint8_t prev = 0;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                uint8_t v = sys[K + (r + 1) * Z + z];  // lambda_r (thread-private slot)
+                if (a.s0[r] >= 0) v ^= sys[K + wrap_add(z, a.s0[r], Z)];
+                if (r > 0) v ^= prev;
+                prev = v;
+                sys[K + (r + 1) * Z + z] = v;          // p_{r+1}[z]
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < 4 * Z; i += blockDim.x) dst[K + i] = sys[K + i];
+        // extension rows: independent of each other
+        for (int z = tid; z < Z; z += blockDim.x) {
+            for (int r = 4; r < a.n_rows; ++r) {
+                uint8_t acc = 0;
+                const int e1 = s_rs[r + 1] - 1;  // last entry of an extension row is its own identity
+                for (int e = s_rs[r]; e < e1; ++e) {
+                    const uint32_t d = s_ed[e];
+                    acc ^= sys[(int)(d >> 16) + wrap_add(z, (int)(d & 0xffffu), Z)];
+                }
+                dst[K + r * Z + z] = acc;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rate matching geometry shared by TX and RX.  The reference walks the circular buffer with a
+// scalar while-loop that skips filler (NRLDPCEncoder.m:187-195, NRLDPCDecoder.m:226-234); here the
+// k-th selected position has a closed form.  In d-coordinates (d = cw without the 2Z punctured
+// columns) the filler interval clipped to the circular buffer is [F0, F1); non-filler positions are
+// ranked 0..Nnf-1 by rank(x) = x - clamp(x - F0, 0, F1 - F0) and unrank(m) = m < F0 ? m : m + (F1-F0).
+// ------------------------------------------------------------------------------------------------
+struct RmGeom {
+    int E, Ncb, F0, F1, Nnf, rank_k0, Qm, EQ;  // EQ = E / Qm
+    int Z2;                                    // 2Z
+    int N, ncw;
+    int F0u, F1u;                              // filler interval before clipping to Ncb
+};
+
+__device__ __forceinline__ int rm_unrank(const RmGeom &g, int m) { return m < g.F0 ? m : m + (g.F1 - g.F0); }
+__device__ __forceinline__ int rm_rank(const RmGeom &g, int x) {
+    int t = x - g.F0;
+    t = t < 0 ? 0 : (t > g.F1 - g.F0 ? g.F1 - g.F0 : t);
+    return x - t;
+}
+
+// TX: f[n] = e[(n % Qm) * E/Qm + n / Qm]  (NRLDPCEncoder.m:219-223), e[k] = d[unrank((rank(k0)+k) % Nnf)]
+__global__ void __launch_bounds__(256) rate_match_kernel(const uint8_t *__restrict__ cw, uint8_t *__restrict__ f,
+                                                         long long batch, RmGeom g) {
+    const long long total = batch * g.E;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / g.E;
+        const int n = (int)(i - b * g.E);
+        const int k = (n % g.Qm) * g.EQ + n / g.Qm;
+        const int m = (int)(((long long)g.rank_k0 + k) % g.Nnf);
+        f[i] = cw[b * g.ncw + g.Z2 + rm_unrank(g, m)];
+    }
+}
+
+// RX: one thread per entry of the decoder's input layout.  Soft-combining of wrapped repetitions
+// is a gather in increasing k, i.e. the same addition order as the reference's serial loop
+// (NRLDPCDecoder.m:230), followed by the HARQ accumulate (:236-239).
+__global__ void __launch_bounds__(256) rate_recover_kernel(const float *__restrict__ f, float *__restrict__ harq,
+                                                           float *__restrict__ out, long long batch, RmGeom g) {
+    const long long total = batch * g.ncw;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long b = i / g.ncw;
+        const int c = (int)(i - b * g.ncw);
+        const int n = c - g.Z2;
+        float v = 0.0f;
+        if (n >= 0) {
+            if (n >= g.F0u && n < g.F1u) {
+                v = __int_as_float(0x7f800000);  // filler: known 0 (NRLDPCDecoder.m:264)
+            } else if (n < g.Ncb) {
+                int first = rm_rank(g, n) - g.rank_k0;
+                if (first < 0) first += g.Nnf;
+                const float *fb = f + b * g.E;
+                float acc = 0.0f;
+                for (int k = first; k < g.E; k += g.Nnf) {
+                    const int q = k / g.EQ;                    // NRLDPCDecoder.m:191-195
+                    acc = __fadd_rn(acc, fb[q + (k - q * g.EQ) * g.Qm]);
+                }
+                if (harq) {
+                    float *hb = harq + b * g.N + n;
+                    acc = __fadd_rn(acc, *hb);
+                    *hb = acc;
+                }
+                v = acc;
+            }
+        }
+        out[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// QPSK + AWGN + exact LLR (plot_BLER_vs_SNR.m:130-132).  Counter-based Philox4x32-10 keyed by
+// (seed, stream_id); counter = global symbol index / 2; Box-Muller turns the four 32-bit outputs
+// into four N(0,1) samples (two complex noise samples = two QPSK symbols).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ void box_muller(uint32_t u0, uint32_t u1, float &n0, float &n1) {
+    const float a = ((float)(u0 >> 8) + 0.5f) * (1.0f / 16777216.0f);  // (0,1)
+    const float b = ((float)(u1 >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float r = sqrtf(-2.0f * __logf(a));
+    float s, c;
+    __sincosf(6.283185307179586f * b, &s, &c);
+    n0 = r * c;
+    n1 = r * s;
+}
+
+__global__ void __launch_bounds__(256) qpsk_awgn_llr_kernel(const uint8_t *__restrict__ bits, float *__restrict__ llr,
+                                                            long long n_quads, float sigma, float gain,
+                                                            uint64_t seed, uint64_t stream_id) {
+    // one thread per 4 bits (2 QPSK symbols); total bit count is a multiple of 4 or handled by the tail launch
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_quads;
+         i += (long long)gridDim.x * blockDim.x) {
+        uint32_t r[4];
+        philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32),
+                      (uint32_t)seed, (uint32_t)(seed >> 32), r);
+        float n[4];
+        box_muller(r[0], r[1], n[0], n[1]);
+        box_muller(r[2], r[3], n[2], n[3]);
+        const uchar4 b = reinterpret_cast<const uchar4 *>(bits)[i];
+        const float amp = 0.70710678118654752440f;
+        float4 o;
+        o.x = gain * ((b.x ? -amp : amp) + sigma * n[0]);
+        o.y = gain * ((b.y ? -amp : amp) + sigma * n[1]);
+        o.z = gain * ((b.z ? -amp : amp) + sigma * n[2]);
+        o.w = gain * ((b.w ? -amp : amp) + sigma * n[3]);
+        reinterpret_cast<float4 *>(llr)[i] = o;
+    }
+}
+
+}  // namespace nrldpc

@@ -1,0 +1,543 @@
+// nrldpc_b200.cu -- host side of the C ABI declared in include/nrldpc_b200.h.
+// Handle lifetime, table lifting, argument validation, launch configuration and the pipelined
+// host<->device path.  No CPU compute fallback exists: every entry point either launches the
+// sm_100a kernels or returns an error.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/nrldpc_b200.h"
+#include "bg_tables.inc"
+#include "chain_kernels.cuh"
+#include "decode_kernel.cuh"
+
+#define NRLDPC_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+constexpr int kNumPipe = 3;  // streams / staging sets for NRLDPC_MEM_HOST calls
+
+thread_local char g_create_error[256] = "";
+
+struct PipeSlot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    float *llr = nullptr;       // device staging
+    uint8_t *hard = nullptr;
+    float *soft = nullptr;
+    int32_t *iters = nullptr;
+    uint8_t *ok = nullptr;
+    uint8_t *bytes_in = nullptr, *bytes_out = nullptr;  // encode / rate-match staging
+    float *f_in = nullptr;
+    size_t cap_cw = 0;          // capacity in codewords of the decode staging
+    size_t cap_bytes = 0;       // capacity of the generic staging buffers
+    float2 *c2v_mins = nullptr; // decode scratch (one set per slot: kernels of different slots may overlap)
+    uint32_t *c2v_meta = nullptr;
+    int *counter = nullptr;
+    size_t scratch_recs = 0;
+};
+
+}  // namespace
+
+struct nrldpc_handle {
+    nrldpc_cfg cfg;
+    nrldpc_dims d;
+    int device = 0;
+    int num_sms = 0;
+    char err[256];
+    int64_t launches = 0;
+    // device tables
+    uint32_t *edesc = nullptr;
+    int *row_start = nullptr;
+    int h_row_start[48];
+    int enc_s0[4];
+    int enc_delta = 0;
+    PipeSlot pipe[kNumPipe];
+    int dec_smem_optin = 0;
+    cudaEvent_t dev_done = nullptr;  // last NRLDPC_MEM_DEVICE launch that used pipe[0]'s scratch
+};
+
+namespace {
+
+int fail(nrldpc_handle *h, int code, const char *fmt, ...) {
+    char *dst = h ? h->err : g_create_error;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 256, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(h, e_ == cudaErrorMemoryAllocation ? NRLDPC_ENOMEM : NRLDPC_ECUDA,        \
+                        "%s: %s", #expr, cudaGetErrorString(e_));                                 \
+    } while (0)
+
+const int kSetA[8] = {2, 3, 5, 7, 9, 11, 13, 15};
+const int kSetN[8] = {8, 8, 7, 6, 6, 6, 5, 5};
+
+struct BgView {
+    int rows, cols, kcols, edges;
+    const unsigned char *row, *col;
+    const unsigned short (*shift)[NRLDPC_BG1_EDGES];
+    const unsigned short (*shift2)[NRLDPC_BG2_EDGES];
+    unsigned short sh(int ils, int e) const { return shift ? shift[ils][e] : shift2[ils][e]; }
+};
+
+BgView bg_view(int bg) {
+    BgView v{};
+    if (bg == 1) {
+        v.rows = 46; v.cols = 68; v.kcols = 22; v.edges = NRLDPC_BG1_EDGES;
+        v.row = nrldpc_bg1_row; v.col = nrldpc_bg1_col; v.shift = nrldpc_bg1_shift; v.shift2 = nullptr;
+    } else {
+        v.rows = 42; v.cols = 52; v.kcols = 10; v.edges = NRLDPC_BG2_EDGES;
+        v.row = nrldpc_bg2_row; v.col = nrldpc_bg2_col; v.shift = nullptr; v.shift2 = nrldpc_bg2_shift;
+    }
+    return v;
+}
+
+int decode_cwpc(int Z) { return std::max(1, nrldpc::kDecThreads / Z); }
+int decode_threads(int Z) { return std::max(32, (decode_cwpc(Z) * Z + 31) / 32 * 32); }
+
+size_t decode_smem_bytes(const nrldpc_handle *h, int n_rows) {
+    const int cwpc = decode_cwpc(h->d.Z);
+    return (size_t)cwpc * h->d.n_cw * 4 + (size_t)h->h_row_start[n_rows] * 4 + (size_t)(n_rows + 1) * 4 +
+           (size_t)cwpc * 4 + 16;
+}
+
+int ensure_scratch(nrldpc_handle *h, PipeSlot &s, size_t recs) {
+    if (!s.counter) CUDA_TRY(h, cudaMalloc(&s.counter, sizeof(int)));
+    if (recs <= s.scratch_recs) return 0;
+    if (s.c2v_mins) cudaFree(s.c2v_mins);
+    if (s.c2v_meta) cudaFree(s.c2v_meta);
+    s.c2v_mins = nullptr; s.c2v_meta = nullptr; s.scratch_recs = 0;
+    CUDA_TRY(h, cudaMalloc(&s.c2v_mins, recs * sizeof(float2)));
+    CUDA_TRY(h, cudaMalloc(&s.c2v_meta, recs * sizeof(uint32_t)));
+    s.scratch_recs = recs;
+    return 0;
+}
+
+// Enqueue one decode launch on `stream` using slot `s`'s scratch.
+int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const float *llr, int64_t batch,
+                  int n_rows, uint8_t *hard, float *soft, int32_t *iters, uint8_t *ok) {
+    const int Z = h->d.Z;
+    const int cwpc = decode_cwpc(Z), threads = decode_threads(Z);
+    const int64_t n_groups = (batch + cwpc - 1) / cwpc;
+    const int grid = (int)std::min<int64_t>(n_groups, (int64_t)h->num_sms * nrldpc::kDecCtasPerSm);
+    const size_t smem = decode_smem_bytes(h, n_rows);
+    if ((int)smem > h->dec_smem_optin) {
+        CUDA_TRY(h, cudaFuncSetAttribute(nrldpc::decode_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->dec_smem_optin = (int)smem;
+    }
+    if (int rc = ensure_scratch(h, s, (size_t)grid * n_rows * threads)) return rc;
+    CUDA_TRY(h, cudaMemsetAsync(s.counter, 0, sizeof(int), stream));
+    nrldpc::DecArgs a{};
+    a.llr = llr; a.hard = hard; a.soft = soft; a.iters = iters; a.ok = ok;
+    a.batch = batch; a.Z = Z; a.ncols = h->d.cols; a.kcols = h->d.kcols; a.n_rows = n_rows;
+    a.n_edges = h->h_row_start[n_rows]; a.max_iters = h->cfg.max_iters; a.early_term = h->cfg.early_term;
+    a.cwpc = cwpc; a.alpha = h->cfg.alpha; a.edesc = h->edesc; a.row_start = h->row_start;
+    a.c2v_mins = s.c2v_mins; a.c2v_meta = s.c2v_meta; a.work_counter = s.counter;
+    nrldpc::decode_nms_kernel<<<grid, threads, smem, stream>>>(a);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+int ensure_pipe(nrldpc_handle *h) {
+    for (auto &s : h->pipe) {
+        if (!s.stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        if (!s.done) CUDA_TRY(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    return 0;
+}
+
+int ensure_decode_staging(nrldpc_handle *h, PipeSlot &s, size_t cw, bool soft) {
+    if (cw > s.cap_cw) {
+        cudaFree(s.llr); cudaFree(s.hard); cudaFree(s.iters); cudaFree(s.ok); cudaFree(s.soft);
+        s.llr = nullptr; s.hard = nullptr; s.iters = nullptr; s.ok = nullptr; s.soft = nullptr; s.cap_cw = 0;
+        CUDA_TRY(h, cudaMalloc(&s.llr, cw * h->d.n_cw * sizeof(float)));
+        CUDA_TRY(h, cudaMalloc(&s.hard, cw * h->d.K));
+        CUDA_TRY(h, cudaMalloc(&s.iters, cw * sizeof(int32_t)));
+        CUDA_TRY(h, cudaMalloc(&s.ok, cw));
+        s.cap_cw = cw;
+    }
+    if (soft && !s.soft) CUDA_TRY(h, cudaMalloc(&s.soft, s.cap_cw * h->d.n_cw * sizeof(float)));
+    return 0;
+}
+
+int ensure_generic_staging(nrldpc_handle *h, PipeSlot &s, size_t bytes) {
+    if (bytes <= s.cap_bytes) return 0;
+    cudaFree(s.bytes_in); cudaFree(s.bytes_out); cudaFree(s.f_in);
+    s.bytes_in = s.bytes_out = nullptr; s.f_in = nullptr; s.cap_bytes = 0;
+    CUDA_TRY(h, cudaMalloc(&s.bytes_in, bytes));
+    CUDA_TRY(h, cudaMalloc(&s.bytes_out, bytes));
+    CUDA_TRY(h, cudaMalloc(&s.f_in, bytes));
+    s.cap_bytes = bytes;
+    return 0;
+}
+
+int make_geom(nrldpc_handle *h, const nrldpc_rm *rm, nrldpc::RmGeom *g) {
+    if (!rm) return fail(h, NRLDPC_ESHAPE, "rate-matching geometry is NULL");
+    const nrldpc_dims &d = h->d;
+    if (!(rm->Q_m == 1 || rm->Q_m == 2 || rm->Q_m == 4 || rm->Q_m == 6 || rm->Q_m == 8))
+        return fail(h, NRLDPC_EUNSUPPORTED, "Valid values of Q_m are 1, 2, 4, 6 and 8.");
+    if (rm->E <= 0 || rm->E % rm->Q_m) return fail(h, NRLDPC_EUNSUPPORTED, "E must be a positive multiple of Q_m.");
+    if (rm->N_cb <= 0 || rm->N_cb > d.N) return fail(h, NRLDPC_EUNSUPPORTED, "N_cb must be in (0, N].");
+    if (rm->k_0 < 0 || rm->k_0 >= rm->N_cb) return fail(h, NRLDPC_EUNSUPPORTED, "k_0 must be in [0, N_cb).");
+    if (rm->K_prime <= 0 || rm->K_prime > d.K) return fail(h, NRLDPC_EUNSUPPORTED, "K_prime must be in (0, K].");
+    g->E = rm->E; g->Ncb = rm->N_cb; g->Qm = rm->Q_m; g->EQ = rm->E / rm->Q_m;
+    g->Z2 = 2 * d.Z; g->N = d.N; g->ncw = d.n_cw;
+    g->F0u = std::max(rm->K_prime - 2 * d.Z, 0);
+    g->F1u = d.K - 2 * d.Z;
+    if (g->F1u < g->F0u) g->F1u = g->F0u;
+    g->F0 = std::min(g->F0u, rm->N_cb);
+    g->F1 = std::min(g->F1u, rm->N_cb);
+    g->Nnf = rm->N_cb - (g->F1 - g->F0);
+    if (g->Nnf <= 0) return fail(h, NRLDPC_EUNSUPPORTED, "circular buffer holds only filler bits.");
+    int t = rm->k_0 - g->F0;
+    t = t < 0 ? 0 : (t > g->F1 - g->F0 ? g->F1 - g->F0 : t);
+    g->rank_k0 = (rm->k_0 - t) % g->Nnf;
+    return 0;
+}
+
+int grid_for(const nrldpc_handle *h, long long work_items, int threads) {
+    long long blocks = (work_items + threads - 1) / threads;
+    return (int)std::max<long long>(1, std::min<long long>(blocks, (long long)h->num_sms * 16));
+}
+
+}  // namespace
+
+// ================================================================================================
+NRLDPC_EXPORT const char *nrldpc_version(void) { return "nrldpc_b200 0.1 (sm_100a)"; }
+
+NRLDPC_EXPORT int nrldpc_set_index(int32_t Z) {
+    for (int s = 0; s < 8; ++s)
+        for (int j = 0; j < kSetN[s]; ++j)
+            if ((kSetA[s] << j) == Z) return s;
+    return NRLDPC_EUNSUPPORTED;
+}
+
+NRLDPC_EXPORT int nrldpc_lifting_size(int32_t K_b, int32_t K_prime) {
+    int best = 0;
+    for (int s = 0; s < 8; ++s)
+        for (int j = 0; j < kSetN[s]; ++j) {
+            const int Z = kSetA[s] << j;
+            if ((long long)K_b * Z >= K_prime && (best == 0 || Z < best)) best = Z;
+        }
+    return best ? best : NRLDPC_EUNSUPPORTED;
+}
+
+NRLDPC_EXPORT int nrldpc_base_graph(int32_t bg, int32_t i_LS, int32_t *rows, int32_t *cols, int32_t *shifts) {
+    if (bg < 1 || bg > 2 || i_LS < 0 || i_LS > 7) return NRLDPC_EUNSUPPORTED;
+    const BgView v = bg_view(bg);
+    for (int e = 0; e < v.edges; ++e) {
+        if (rows) rows[e] = v.row[e];
+        if (cols) cols[e] = v.col[e];
+        if (shifts) shifts[e] = v.sh(i_LS, e);
+    }
+    return v.edges;
+}
+
+NRLDPC_EXPORT const char *nrldpc_last_error(const nrldpc_t *h) { return h ? h->err : g_create_error; }
+
+NRLDPC_EXPORT int64_t nrldpc_launch_count(const nrldpc_t *h) { return h ? h->launches : 0; }
+
+NRLDPC_EXPORT void *nrldpc_host_alloc(uint64_t bytes) {
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+NRLDPC_EXPORT void nrldpc_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
+    if (!out || !cfg) return fail(nullptr, NRLDPC_ESHAPE, "nrldpc_create: NULL argument");
+    *out = nullptr;
+    if (cfg->bg < 1 || cfg->bg > 2) return fail(nullptr, NRLDPC_EUNSUPPORTED, "Valid values of BG are 1 and 2.");
+    const int ils = nrldpc_set_index(cfg->Z);
+    if (ils < 0) return fail(nullptr, NRLDPC_EUNSUPPORTED, "Invalid lifting size.");
+    if (cfg->max_iters < 1) return fail(nullptr, NRLDPC_EUNSUPPORTED, "MaximumIterationCount must be >= 1.");
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(nullptr, NRLDPC_ECUDA, "no CUDA device available (%s); this library has no CPU path",
+                    cudaGetErrorString(ce));
+    nrldpc_handle *h = new (std::nothrow) nrldpc_handle();
+    if (!h) return fail(nullptr, NRLDPC_ENOMEM, "out of host memory");
+    h->err[0] = 0;
+    h->cfg = *cfg;
+    if (!(h->cfg.alpha > 0.0f)) h->cfg.alpha = 0.75f;
+    int dev = cfg->device;
+    if (dev < 0) cudaGetDevice(&dev);
+    if (dev >= ndev) { delete h; return fail(nullptr, NRLDPC_EUNSUPPORTED, "device ordinal %d out of range", dev); }
+    h->device = dev;
+    cudaSetDevice(dev);
+    cudaDeviceProp prop{};
+    ce = cudaGetDeviceProperties(&prop, dev);
+    if (ce != cudaSuccess) { delete h; return fail(nullptr, NRLDPC_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(ce)); }
+    if (prop.major != 10) {
+        delete h;
+        return fail(nullptr, NRLDPC_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
+    }
+    h->num_sms = prop.multiProcessorCount;
+
+    const BgView v = bg_view(cfg->bg);
+    const int Z = cfg->Z;
+    h->d = nrldpc_dims{cfg->bg, Z, ils, v.rows, v.cols, v.kcols, v.edges, v.kcols * Z, (v.cols - 2) * Z, v.cols * Z};
+    std::vector<uint32_t> ed(v.edges);
+    for (int r = 0, e = 0; r <= v.rows; ++r) {
+        while (e < v.edges && v.row[e] < r) ++e;
+        h->h_row_start[r] = e;
+    }
+    for (int e = 0; e < v.edges; ++e)
+        ed[e] = ((uint32_t)(v.col[e] * Z) << 16) | (uint32_t)(v.sh(ils, e) % Z);
+    // encoder structure: shifts of the first core-parity column in rows 0..3
+    int vals[3], nv = 0;
+    for (int r = 0; r < 4; ++r) h->enc_s0[r] = -1;
+    for (int e = 0; e < v.edges; ++e)
+        if (v.col[e] == v.kcols && v.row[e] < 4) {
+            h->enc_s0[v.row[e]] = v.sh(ils, e) % Z;
+            if (nv < 3) vals[nv] = v.sh(ils, e) % Z;
+            ++nv;
+        }
+    if (nv != 3) { delete h; return fail(nullptr, NRLDPC_EUNSUPPORTED, "unexpected core parity structure"); }
+    h->enc_delta = vals[0] == vals[1] ? vals[2] : (vals[0] == vals[2] ? vals[1] : vals[0]);
+
+    int rc = 0;
+    auto up = [&]() -> int {
+        CUDA_TRY(h, cudaMalloc(&h->edesc, ed.size() * sizeof(uint32_t)));
+        CUDA_TRY(h, cudaMalloc(&h->row_start, sizeof(int) * (v.rows + 1)));
+        CUDA_TRY(h, cudaMemcpy(h->edesc, ed.data(), ed.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CUDA_TRY(h, cudaMemcpy(h->row_start, h->h_row_start, sizeof(int) * (v.rows + 1), cudaMemcpyHostToDevice));
+        return 0;
+    };
+    rc = up();
+    if (rc) {
+        snprintf(g_create_error, sizeof(g_create_error), "%s", h->err);
+        nrldpc_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return NRLDPC_OK;
+}
+
+NRLDPC_EXPORT void nrldpc_destroy(nrldpc_t *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (auto &s : h->pipe) {
+        cudaFree(s.llr); cudaFree(s.hard); cudaFree(s.soft); cudaFree(s.iters); cudaFree(s.ok);
+        cudaFree(s.bytes_in); cudaFree(s.bytes_out); cudaFree(s.f_in);
+        cudaFree(s.c2v_mins); cudaFree(s.c2v_meta); cudaFree(s.counter);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    if (h->dev_done) cudaEventDestroy(h->dev_done);
+    cudaFree(h->edesc);
+    cudaFree(h->row_start);
+    delete h;
+}
+
+NRLDPC_EXPORT int nrldpc_synchronize(nrldpc_t *h) {
+    if (!h) return NRLDPC_ESHAPE;
+    cudaSetDevice(h->device);
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    return 0;
+}
+
+NRLDPC_EXPORT int nrldpc_get_dims(const nrldpc_t *h, nrldpc_dims *out) {
+    if (!h || !out) return NRLDPC_ESHAPE;
+    *out = h->d;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+NRLDPC_EXPORT int nrldpc_decode(nrldpc_t *h, const float *llr, int64_t batch, int32_t n_rows, uint8_t *info_hard,
+                                float *app_soft, int32_t *iters, uint8_t *parity_ok, int32_t mem, void *stream) {
+    if (!h) return NRLDPC_ESHAPE;
+    if (batch < 0) return fail(h, NRLDPC_ESHAPE, "batch must be >= 0");
+    if (batch == 0) return 0;
+    if (!llr || !info_hard) return fail(h, NRLDPC_ESHAPE, "llr and info_hard must not be NULL");
+    if (n_rows == 0) n_rows = h->d.rows;
+    if (n_rows < 4 || n_rows > h->d.rows) return fail(h, NRLDPC_EUNSUPPORTED, "n_rows must be 0 or in [4, %d]", h->d.rows);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (mem == NRLDPC_MEM_DEVICE) {
+        if ((reinterpret_cast<uintptr_t>(llr) & 15) || (app_soft && (reinterpret_cast<uintptr_t>(app_soft) & 15)))
+            return fail(h, NRLDPC_ESHAPE, "device llr / app_soft pointers must be 16-byte aligned");
+        if (!h->dev_done) CUDA_TRY(h, cudaEventCreateWithFlags(&h->dev_done, cudaEventDisableTiming));
+        if (int rc = launch_decode(h, h->pipe[0], static_cast<cudaStream_t>(stream), llr, batch, n_rows, info_hard,
+                                   app_soft, iters, parity_ok))
+            return rc;
+        CUDA_TRY(h, cudaEventRecord(h->dev_done, static_cast<cudaStream_t>(stream)));
+        return 0;
+    }
+    if (mem != NRLDPC_MEM_HOST) return fail(h, NRLDPC_ESHAPE, "mem must be NRLDPC_MEM_HOST or NRLDPC_MEM_DEVICE");
+
+    // Host buffers: chunked 3-deep pipeline, H2D / kernel / D2H of different chunks overlap.
+    if (int rc = ensure_pipe(h)) return rc;
+    if (h->dev_done) CUDA_TRY(h, cudaStreamWaitEvent(h->pipe[0].stream, h->dev_done, 0));
+    const int cwpc = decode_cwpc(h->d.Z);
+    const int64_t wave = (int64_t)h->num_sms * nrldpc::kDecCtasPerSm * cwpc;  // codewords per full grid
+    int64_t chunk = wave;
+    while (chunk * 2 * h->d.n_cw * 4 <= (int64_t)96 << 20 && chunk * 2 * kNumPipe <= batch) chunk *= 2;
+    chunk = std::min<int64_t>(chunk, batch);
+    for (auto &s : h->pipe)
+        if (int rc = ensure_decode_staging(h, s, (size_t)chunk, app_soft != nullptr)) return rc;
+    int k = 0;
+    for (int64_t off = 0; off < batch; off += chunk, k = (k + 1) % kNumPipe) {
+        PipeSlot &s = h->pipe[k];
+        const int64_t n = std::min<int64_t>(chunk, batch - off);
+        CUDA_TRY(h, cudaMemcpyAsync(s.llr, llr + off * h->d.n_cw, (size_t)n * h->d.n_cw * sizeof(float),
+                                    cudaMemcpyHostToDevice, s.stream));
+        if (int rc = launch_decode(h, s, s.stream, s.llr, n, n_rows, s.hard, app_soft ? s.soft : nullptr,
+                                   iters ? s.iters : nullptr, parity_ok ? s.ok : nullptr))
+            return rc;
+        CUDA_TRY(h, cudaMemcpyAsync(info_hard + off * h->d.K, s.hard, (size_t)n * h->d.K, cudaMemcpyDeviceToHost, s.stream));
+        if (app_soft)
+            CUDA_TRY(h, cudaMemcpyAsync(app_soft + off * h->d.n_cw, s.soft, (size_t)n * h->d.n_cw * sizeof(float),
+                                        cudaMemcpyDeviceToHost, s.stream));
+        if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters + off, s.iters, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+        if (parity_ok) CUDA_TRY(h, cudaMemcpyAsync(parity_ok + off, s.ok, (size_t)n, cudaMemcpyDeviceToHost, s.stream));
+    }
+    for (auto &s : h->pipe) CUDA_TRY(h, cudaStreamSynchronize(s.stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+namespace {
+int launch_encode(nrldpc_handle *h, cudaStream_t st, const uint8_t *info, int64_t batch, uint8_t *cw) {
+    nrldpc::EncArgs a{};
+    a.info = info; a.cw = cw; a.batch = batch; a.Z = h->d.Z; a.ncols = h->d.cols; a.kcols = h->d.kcols;
+    a.n_rows = h->d.rows; a.n_edges = h->d.edges; a.edesc = h->edesc; a.row_start = h->row_start;
+    for (int r = 0; r < 4; ++r) a.s0[r] = h->enc_s0[r];
+    a.delta = h->enc_delta;
+    const int threads = std::min(384, std::max(32, (h->d.Z + 31) / 32 * 32));
+    const size_t smem = (((size_t)(h->d.kcols + 4) * h->d.Z + 15) & ~(size_t)15) + (size_t)h->d.edges * 4 + (h->d.rows + 1) * 4;
+    const int grid = (int)std::min<int64_t>(batch, (int64_t)h->num_sms * 4);
+    nrldpc::encode_kernel<<<grid, threads, smem, st>>>(a);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+}  // namespace
+
+NRLDPC_EXPORT int nrldpc_encode(nrldpc_t *h, const uint8_t *info, int64_t batch, uint8_t *cw, int32_t mem, void *stream) {
+    if (!h) return NRLDPC_ESHAPE;
+    if (batch < 0) return fail(h, NRLDPC_ESHAPE, "batch must be >= 0");
+    if (batch == 0) return 0;
+    if (!info || !cw) return fail(h, NRLDPC_ESHAPE, "info and cw must not be NULL");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (mem == NRLDPC_MEM_DEVICE) return launch_encode(h, static_cast<cudaStream_t>(stream), info, batch, cw);
+    if (mem != NRLDPC_MEM_HOST) return fail(h, NRLDPC_ESHAPE, "mem must be NRLDPC_MEM_HOST or NRLDPC_MEM_DEVICE");
+    if (int rc = ensure_pipe(h)) return rc;
+    PipeSlot &s = h->pipe[0];
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(batch, ((int64_t)64 << 20) / h->d.n_cw));
+    if (int rc = ensure_generic_staging(h, s, (size_t)chunk * h->d.n_cw)) return rc;
+    for (int64_t off = 0; off < batch; off += chunk) {
+        const int64_t n = std::min<int64_t>(chunk, batch - off);
+        CUDA_TRY(h, cudaMemcpyAsync(s.bytes_in, info + off * h->d.K, (size_t)n * h->d.K, cudaMemcpyHostToDevice, s.stream));
+        if (int rc = launch_encode(h, s.stream, s.bytes_in, n, s.bytes_out)) return rc;
+        CUDA_TRY(h, cudaMemcpyAsync(cw + off * h->d.n_cw, s.bytes_out, (size_t)n * h->d.n_cw, cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(h, cudaStreamSynchronize(s.stream));
+    }
+    return 0;
+}
+
+NRLDPC_EXPORT int nrldpc_rate_match(nrldpc_t *h, const uint8_t *cw, int64_t batch, const nrldpc_rm *rm, uint8_t *f,
+                                    int32_t mem, void *stream) {
+    if (!h) return NRLDPC_ESHAPE;
+    nrldpc::RmGeom g{};
+    if (int rc = make_geom(h, rm, &g)) return rc;
+    if (batch < 0) return fail(h, NRLDPC_ESHAPE, "batch must be >= 0");
+    if (batch == 0) return 0;
+    if (!cw || !f) return fail(h, NRLDPC_ESHAPE, "cw and f must not be NULL");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (mem == NRLDPC_MEM_DEVICE) {
+        nrldpc::rate_match_kernel<<<grid_for(h, batch * g.E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(cw, f, batch, g);
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches += 1;
+        return 0;
+    }
+    if (mem != NRLDPC_MEM_HOST) return fail(h, NRLDPC_ESHAPE, "mem must be NRLDPC_MEM_HOST or NRLDPC_MEM_DEVICE");
+    if (int rc = ensure_pipe(h)) return rc;
+    PipeSlot &s = h->pipe[0];
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(batch, ((int64_t)64 << 20) / h->d.n_cw));
+    if (int rc = ensure_generic_staging(h, s, (size_t)chunk * h->d.n_cw)) return rc;
+    for (int64_t off = 0; off < batch; off += chunk) {
+        const int64_t n = std::min<int64_t>(chunk, batch - off);
+        CUDA_TRY(h, cudaMemcpyAsync(s.bytes_in, cw + off * h->d.n_cw, (size_t)n * h->d.n_cw, cudaMemcpyHostToDevice, s.stream));
+        nrldpc::rate_match_kernel<<<grid_for(h, n * g.E, 256), 256, 0, s.stream>>>(s.bytes_in, s.bytes_out, n, g);
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches += 1;
+        CUDA_TRY(h, cudaMemcpyAsync(f + off * g.E, s.bytes_out, (size_t)n * g.E, cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(h, cudaStreamSynchronize(s.stream));
+    }
+    return 0;
+}
+
+NRLDPC_EXPORT int nrldpc_rate_recover(nrldpc_t *h, const float *f, int64_t batch, const nrldpc_rm *rm, float *harq,
+                                      float *llr_cw, int32_t mem, void *stream) {
+    if (!h) return NRLDPC_ESHAPE;
+    nrldpc::RmGeom g{};
+    if (int rc = make_geom(h, rm, &g)) return rc;
+    if (batch < 0) return fail(h, NRLDPC_ESHAPE, "batch must be >= 0");
+    if (batch == 0) return 0;
+    if (!f || !llr_cw) return fail(h, NRLDPC_ESHAPE, "f and llr_cw must not be NULL");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (mem == NRLDPC_MEM_DEVICE) {
+        nrldpc::rate_recover_kernel<<<grid_for(h, batch * g.ncw, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(f, harq, llr_cw, batch, g);
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches += 1;
+        return 0;
+    }
+    if (mem != NRLDPC_MEM_HOST) return fail(h, NRLDPC_ESHAPE, "mem must be NRLDPC_MEM_HOST or NRLDPC_MEM_DEVICE");
+    if (int rc = ensure_pipe(h)) return rc;
+    PipeSlot &s = h->pipe[0];
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(batch, ((int64_t)16 << 20) / h->d.n_cw));
+    if (int rc = ensure_generic_staging(h, s, (size_t)chunk * h->d.n_cw * sizeof(float))) return rc;
+    float *d_f = s.f_in, *d_out = reinterpret_cast<float *>(s.bytes_out), *d_harq = reinterpret_cast<float *>(s.bytes_in);
+    for (int64_t off = 0; off < batch; off += chunk) {
+        const int64_t n = std::min<int64_t>(chunk, batch - off);
+        CUDA_TRY(h, cudaMemcpyAsync(d_f, f + off * g.E, (size_t)n * g.E * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+        if (harq)
+            CUDA_TRY(h, cudaMemcpyAsync(d_harq, harq + off * g.N, (size_t)n * g.N * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+        nrldpc::rate_recover_kernel<<<grid_for(h, n * g.ncw, 256), 256, 0, s.stream>>>(d_f, harq ? d_harq : nullptr, d_out, n, g);
+        CUDA_TRY(h, cudaGetLastError());
+        h->launches += 1;
+        CUDA_TRY(h, cudaMemcpyAsync(llr_cw + off * g.ncw, d_out, (size_t)n * g.ncw * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+        if (harq)
+            CUDA_TRY(h, cudaMemcpyAsync(harq + off * g.N, d_harq, (size_t)n * g.N * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(h, cudaStreamSynchronize(s.stream));
+    }
+    return 0;
+}
+
+NRLDPC_EXPORT int nrldpc_qpsk_awgn_llr(nrldpc_t *h, const uint8_t *f_bits, int64_t batch, int32_t E, float variance,
+                                       uint64_t seed, uint64_t stream_id, float *f_llr, void *stream) {
+    if (!h) return NRLDPC_ESHAPE;
+    if (batch < 0 || E <= 0) return fail(h, NRLDPC_ESHAPE, "batch must be >= 0 and E > 0");
+    if (!(variance > 0.0f)) return fail(h, NRLDPC_EUNSUPPORTED, "variance must be positive");
+    const long long total = (long long)batch * E;
+    if (total % 4) return fail(h, NRLDPC_EUNSUPPORTED, "batch*E must be a multiple of 4 (two QPSK symbols per thread)");
+    if (total == 0) return 0;
+    if (!f_bits || !f_llr) return fail(h, NRLDPC_ESHAPE, "f_bits and f_llr must not be NULL");
+    if ((reinterpret_cast<uintptr_t>(f_bits) & 3) || (reinterpret_cast<uintptr_t>(f_llr) & 15))
+        return fail(h, NRLDPC_ESHAPE, "f_bits must be 4-byte and f_llr 16-byte aligned");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const long long quads = total / 4;
+    nrldpc::qpsk_awgn_llr_kernel<<<grid_for(h, quads, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        f_bits, f_llr, quads, sqrtf(0.5f * variance), 2.8284271247461900976f / variance, seed, stream_id);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
