@@ -1,0 +1,332 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the NR LDPC decode hot path (BASELINE.json config 2).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+One "step" = one decode of one batch of synthetic codewords: BG1, Z=384, K=8448, rate 1/3
+(E=25272 of N=25344 bits sent, all 46 base rows active), 8 layered normalized-min-sum iterations,
+early termination off, batch 4096 codewords per GPU (weak scaling: every rank decodes its own 4096).
+
+  value   decoded information Gb/s with the LLRs already resident in HBM (CUDA events, max over ranks)
+  e2e     same metric through the C ABI with pinned HOST buffers: H2D of the float32 LLRs, the kernel
+          and D2H of the hard bits all inside the timed region
+  roofline      algorithmic HBM bytes of the decode kernel / its measured launch time vs the measured
+                copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the reference's algorithm (flooding sum-product, float64, parity-check stop: what
+                comm.LDPCDecoder runs at NRLDPCDecoder.m:120,265) restated in C (oracle B), timed on
+                this box's host cores on a bounded sample of the same LLRs
+`--impl reference` times that CPU path alone (the reference itself is MATLAB + a closed toolbox and
+cannot run here).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: bg, Z, E, n_rows, iters, early_term, batch/GPU, Es/N0 dB, filler
+    "bg1_z384_r13_it8_b4096": dict(bg=1, Z=384, E=25272, n_rows=46, iters=8, early_term=0, batch=4096, esn0=-0.3, filler=0),
+    "bg2_z52_r15_it8_b65536": dict(bg=2, Z=52, E=2000, n_rows=33, iters=8, early_term=0, batch=65536, esn0=-2.0, filler=104),
+    "bg1_z384_r89_it20et_b4096": dict(bg=1, Z=384, E=9478, n_rows=5, iters=20, early_term=1, batch=4096, esn0=6.3, filler=0),
+}
+DEFAULT_WORKLOAD = "bg1_z384_r13_it8_b4096"
+METRIC = "decoded info Gb/s @ BG1 Z=384 8-iter"
+CPU_SAMPLE_CW = 256
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = str(gpu_index)
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        rows = [r for r in rows if len(r) >= 9 and r[0] == self.idx]
+        if not rows:
+            return out
+        sm = sorted(float(r[1]) for r in rows)
+        out["sm_mhz"] = sm[len(sm) // 2]
+        out["sm_max_mhz"] = float(rows[0][2])
+        out["power_w_max"] = max(float(r[3]) for r in rows)
+        out["samples"] = len(rows)
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        seen = set()
+        for r in rows:
+            for n, v in zip(names, r[5:9]):
+                if v.strip().lower() == "active":
+                    seen.add(n)
+        out["reasons"] = sorted(seen)
+        return out
+
+
+def make_inputs(h, capi, torch, w, seed, stream):
+    """Synthetic workload generated ON DEVICE through the library's own chain kernels:
+    random info -> encode -> rate match -> QPSK + AWGN + exact LLR -> rate recover (decoder layout)."""
+    B, E = w["batch"], w["E"]
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    info = torch.randint(0, 2, (B, h.K), dtype=torch.uint8, device="cuda", generator=g)
+    if w["filler"]:
+        info[:, h.K - w["filler"]:] = 0
+    cw = torch.empty((B, h.n_cw), dtype=torch.uint8, device="cuda")
+    f = torch.empty((B, E), dtype=torch.uint8, device="cuda")
+    fl = torch.empty((B, E), dtype=torch.float32, device="cuda")
+    llr = torch.empty((B, h.n_cw), dtype=torch.float32, device="cuda")
+    rm = capi.Rm(E, 0, h.N, h.K - w["filler"], 2)
+    h.encode_raw(info, B, cw, mem=capi.MEM_DEVICE, stream=stream)
+    h.rate_match_raw(cw, B, rm, f, mem=capi.MEM_DEVICE, stream=stream)
+    h.qpsk_awgn_llr_raw(f, B, E, 10 ** (-w["esn0"] / 10), seed, 0, fl, stream=stream)
+    h.rate_recover_raw(fl, B, rm, None, llr, mem=capi.MEM_DEVICE, stream=stream)
+    torch.cuda.synchronize()
+    del cw, f, fl
+    return info, llr
+
+
+def cpu_reference_time(w, llr_sample, threads, steps=1, warmup=0):
+    """Oracle B (the reference's algorithm) on `threads` host threads.  Returns (sec/step, info bits/step)."""
+    from oracle import oracle as O
+    O.build()
+    for _ in range(warmup):
+        O.decode_bp(w["bg"], w["Z"], llr_sample, w["iters"], n_threads=threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.decode_bp(w["bg"], w["Z"], llr_sample, w["iters"], n_threads=threads)
+    dt = (time.perf_counter() - t0) / max(1, steps)
+    return dt, llr_sample.shape[0] * O.dims(w["bg"], w["Z"])["K"]
+
+
+def synth_llr_cpu(w, n, seed):
+    """Host-side synthetic LLRs for the reference arm (no GPU involved): oracle encoder + numpy AWGN."""
+    import numpy as np
+    from oracle import oracle as O
+    O.build()
+    rng = np.random.default_rng(seed)
+    d = O.dims(w["bg"], w["Z"])
+    info = rng.integers(0, 2, (n, d["K"]), dtype=np.uint8)
+    if w["filler"]:
+        info[:, d["K"] - w["filler"]:] = 0
+    cw = O.encode(w["bg"], w["Z"], info)
+    s2 = 10 ** (-w["esn0"] / 10)
+    y = (1 - 2.0 * cw) / np.sqrt(2) + rng.normal(0, np.sqrt(s2 / 2), cw.shape)
+    llr = (2 * np.sqrt(2) * y / s2).astype(np.float32)
+    llr[:, :2 * w["Z"]] = 0
+    llr[:, 2 * w["Z"] + w["E"]:] = 0
+    if w["filler"]:
+        llr[:, d["K"] - w["filler"]:d["K"]] = np.inf
+    return llr
+
+
+def run_reference(args, w, wname):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    llr = synth_llr_cpu(w, CPU_SAMPLE_CW, 1234)
+    dt, bits = cpu_reference_time(w, llr, threads, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    val = bits / dt / 1e9
+    cfg_batch = w["batch"]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Gb/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wname, "bg": w["bg"], "Z": w["Z"], "K": 22 * w["Z"] if w["bg"] == 1 else 10 * w["Z"],
+                   "E": w["E"], "iters": w["iters"], "early_term": 1, "batch_per_gpu": cfg_batch,
+                   "algorithm": "flooding sum-product f64, parity-check stop (comm.LDPCDecoder as at NRLDPCDecoder.m:120), "
+                                "C restatement: MATLAB and the toolbox are not runnable here"},
+        "cpu_baseline": {"value": val, "unit": "Gb/s", "cores": threads, "kind": "port",
+                         "sample": f"{CPU_SAMPLE_CW} codewords of the workload per step, OpenMP over codewords"},
+        "e2e": {"value": val, "unit": "Gb/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args, w, args.workload)
+
+    import numpy as np
+    import torch
+    from ldpc_3gpp_matlab_b200 import capi, dist as D
+
+    rank, local_rank, world = D.init()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    h = capi.Handle(w["bg"], w["Z"], w["iters"], bool(w["early_term"]), device=local_rank)
+    B, K = w["batch"], h.K
+    info, llr = make_inputs(h, capi, torch, w, D.rank_seed(0, rank) & 0x7FFFFFFF, stream)
+    hard = torch.empty((B, K), dtype=torch.uint8, device="cuda")
+    iters_t = torch.empty(B, dtype=torch.int32, device="cuda")
+
+    def step():
+        h.decode_raw(llr, B, hard, iters=iters_t if w["early_term"] else None, n_rows=w["n_rows"],
+                     mem=capi.MEM_DEVICE, stream=stream)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    bler = float((hard != info).any(dim=1).float().mean())
+    mean_iters = float(iters_t.float().mean()) if w["early_term"] else float(w["iters"])
+
+    # ---- timed region: K steps, CUDA events on the launching stream, barrier + sync both sides ----
+    sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank])
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    l0 = h.launches
+    D.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    D.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = h.launches - l0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    total_ms = D.max_over_ranks(total_ms)
+    ms_per_step = total_ms / args.steps
+    value = world * B * K / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: pinned host buffers through the synchronous host-memory C-ABI call ----------------
+    e2e = None
+    if not args.no_e2e:
+        llr_h = torch.empty((B, h.n_cw), dtype=torch.float32, pin_memory=True)
+        llr_h.copy_(llr)
+        hard_h = torch.empty((B, K), dtype=torch.uint8, pin_memory=True)
+        torch.cuda.synchronize()
+        for _ in range(2):
+            h.decode_raw(llr_h, B, hard_h, n_rows=w["n_rows"], mem=capi.MEM_HOST)
+        n_e2e = max(3, min(args.steps, 10))
+        D.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            h.decode_raw(llr_h, B, hard_h, n_rows=w["n_rows"], mem=capi.MEM_HOST)
+        torch.cuda.synchronize()
+        dt = D.max_over_ranks((time.perf_counter() - t0) / n_e2e)
+        assert bool((hard_h.cuda() == hard).all()), "host-path result differs from device-path result"
+        e2e = {"value": world * B * K / dt / 1e9, "unit": "Gb/s", "h2d_bytes_per_step": B * h.n_cw * 4,
+               "d2h_bytes_per_step": B * K, "ms_per_step": dt * 1e3, "steps": n_e2e,
+               "timer": "host perf_counter around the synchronous host-memory C-ABI call, max over ranks",
+               "pipeline": "3 streams, chunked H2D / kernel / D2H overlap inside nrldpc_decode"}
+        del llr_h, hard_h
+
+    # ---- roofline of the dominant (only) kernel --------------------------------------------------
+    peak, peak_src = peaks()
+    bytes_per_cw = 4 * h.n_cw + K
+    k_ms = sum(per_launch_ms) / len(per_launch_ms)
+    achieved = B * bytes_per_cw / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get(args.workload)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "decode_nms_kernel", "kernel_ms": k_ms, "bytes_per_codeword": bytes_per_cw,
+                "peak_source": peak_src,
+                "note": "state stays on chip for all iterations; the kernel is issue/shared-memory bound by construction "
+                        "(SURVEY.md 8d), so the HBM fraction is small; see profiles/ for issue-slot utilisation"}
+
+    # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = llr[:CPU_SAMPLE_CW].cpu().numpy()
+        dt, bits = cpu_reference_time(w, sample, threads)
+        cpu = {"value": bits / dt / 1e9, "unit": "Gb/s", "cores": threads, "kind": "port",
+               "sample": f"first {CPU_SAMPLE_CW} codewords of the batch, oracle B = flooding sum-product f64 with parity-check "
+                         f"stop (comm.LDPCDecoder's algorithm), OpenMP over codewords, {dt:.2f} s"}
+        from oracle import oracle as O
+        t0 = time.perf_counter()
+        ref = O.decode_nms(w["bg"], w["Z"], sample, w["iters"], early_term=bool(w["early_term"]), n_rows=w["n_rows"],
+                           want_app=False, n_threads=threads)
+        dta = time.perf_counter() - t0
+        cpu["like_for_like_nms_f32"] = {"value": bits / dta / 1e9, "unit": "Gb/s", "cores": threads,
+                                        "matches_gpu_bits": bool((ref["hard"] == hard[:CPU_SAMPLE_CW].cpu().numpy()).all())}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "Gb/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "bg": w["bg"], "Z": w["Z"], "K": K, "N": h.N, "E": w["E"],
+                       "rate": round(K / w["E"], 4), "n_rows": w["n_rows"], "iters": w["iters"], "early_term": w["early_term"],
+                       "alpha": 0.75, "algorithm": "layered normalized min-sum", "batch_per_gpu": B,
+                       "global_batch": B * world, "parallelism": f"dp{world} (independent codeword shards, no data-path collective)",
+                       "esn0_db": w["esn0"], "bler_at_esn0": bler, "mean_iters": mean_iters,
+                       "l2": f"inputs larger than L2 ({B * h.n_cw * 4 / 2**20:.0f} MiB LLRs per step vs 126 MB L2)"},
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    h.close()
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

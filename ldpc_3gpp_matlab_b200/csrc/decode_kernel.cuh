@@ -18,7 +18,7 @@
 //     writes nothing;
 //   * arithmetic is float32 with every add/mul individually rounded (__fsub_rn/__fmul_rn/__fadd_rn:
 //     no FMA contraction), signs handled as sign BITS, so results are bit-identical to the CPU
-//     oracle (oracle/nrldpc_oracle.c, orc_decode_nms).
+//     oracle (oracle/nrldpc_oracle.c, function orc_decode_nms).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,6 +29,12 @@ constexpr int kDecThreads = 384;     // max threads per decode CTA (= largest li
 constexpr int kDecCtasPerSm = 2;
 constexpr float kLlrMax = 1048576.0f;
 
+constexpr int kMaxEdges = 316;
+constexpr int kMaxRows = 46;
+
+// Edge descriptor, read from the kernel-parameter constant bank with a warp-uniform index:
+//   x = shift*4   (bytes): lane z reads circulant position (z + shift) mod Z
+//   y = col*Z*4   (bytes): start of the block column inside one codeword's APP array
 struct DecArgs {
     const float *llr;        // [batch][ncw]
     uint8_t *hard;           // [batch][K]
@@ -38,11 +44,10 @@ struct DecArgs {
     long long batch;
     int Z, ncols, kcols, n_rows, n_edges, max_iters, early_term, cwpc;
     float alpha;
-    const uint32_t *edesc;   // [edges] (col*Z) << 16 | (shift mod Z)
-    const int *row_start;    // [rows+1]
-    float2 *c2v_mins;        // [grid][n_rows][blockDim]
-    uint32_t *c2v_meta;      // [grid][n_rows][blockDim]  argmin | signbits << 5
+    uint4 *c2v;              // [grid][n_rows][blockDim] {alpha*min1, alpha*min2, argmin | signbits << 5, -}
     int *work_counter;
+    unsigned short row_start[kMaxRows + 2];
+    uint2 ed[kMaxEdges];
 };
 
 __device__ __forceinline__ float clamp_llr(float x) {
@@ -50,30 +55,32 @@ __device__ __forceinline__ float clamp_llr(float x) {
     return fmaxf(fminf(x, kLlrMax), -kLlrMax);
 }
 
-// One check row of degree DEG for check z.  (om1, om2, ometa) is the compressed message record
-// written for this check in the previous iteration (zeros in the first).
+// One check row of degree DEG for check z.  `base` = byte address (shared window) of this thread's
+// codeword's APP array, zoff = z*4; (om1, om2, ometa) is the compressed message record written
+// for this check in the previous iteration (zeros in the first).
+// Sign bits of the messages are kept MSB-first: edge e sits at bit (DEG-1-e) of the sign field.
 template <int DEG>
-__device__ __forceinline__ void process_row(float *__restrict__ app, const uint32_t *__restrict__ ed,
-                                            const int z, const int Z, const float om1, const float om2,
+__device__ __forceinline__ void process_row(const uint32_t base, const uint2 *__restrict__ ed, const uint32_t zoff,
+                                            const uint32_t Z4, const float om1, const float om2,
                                             const uint32_t ometa, const float alpha, float &nm1,
                                             float &nm2, uint32_t &nmeta) {
     float t[DEG];
-    int addr[DEG];
+    uint32_t addr[DEG];
     float m1 = __int_as_float(0x7f800000), m2 = __int_as_float(0x7f800000);
-    uint32_t sx = 0;
+    uint32_t sx = 0, ts = 0;
     int arg = 0;
     const int oarg = (int)(ometa & 31u);
     const uint32_t osg = ometa >> 5;
 #pragma unroll
     for (int e = 0; e < DEG; ++e) {
-        const uint32_t d = ed[e];
-        int p = z + (int)(d & 0xffffu);
-        p = (p >= Z) ? p - Z : p;
-        const int a = (int)(d >> 16) + p;
+        const uint2 d = ed[e];
+        const uint32_t u = zoff + d.x;              // (z + shift)*4, wraps at Z*4:
+        const uint32_t a = base + d.y + min(u, u - Z4);  // u - Z4 underflows to a huge value when u < Z4
         addr[e] = a;
-        const float x = app[a];
+        float x;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(a));
         const float mag = (e == oarg) ? om2 : om1;
-        const float c = __uint_as_float(__float_as_uint(mag) | (((osg >> e) & 1u) << 31));
+        const float c = __uint_as_float(__float_as_uint(mag) | ((osg << (31 - (DEG - 1 - e))) & 0x80000000u));
         const float tt = __fsub_rn(x, c);
         t[e] = tt;
         const float ab = fabsf(tt);
@@ -81,50 +88,49 @@ __device__ __forceinline__ void process_row(float *__restrict__ app, const uint3
         m2 = fminf(m2, fmaxf(ab, m1));
         m1 = fminf(m1, ab);
         sx ^= __float_as_uint(tt);
+        ts = __funnelshift_l(__float_as_uint(tt), ts, 1);  // ts = ts << 1 | signbit(tt)
     }
-    const float m1s = __fmul_rn(alpha, m1), m2s = __fmul_rn(alpha, m2);
     const uint32_t sg = sx & 0x80000000u;
-    uint32_t nsg = 0;
+    // both candidate magnitudes with the row's sign product folded in
+    uint32_t m1ss = __float_as_uint(__fmul_rn(alpha, m1)) | sg;
+    uint32_t m2ss = __float_as_uint(__fmul_rn(alpha, m2)) | sg;
+    asm volatile("" : "+r"(m1ss), "+r"(m2ss));  // keep the sign folded per row, not re-derived per edge
 #pragma unroll
     for (int e = 0; e < DEG; ++e) {
-        const float mag = (e == arg) ? m2s : m1s;
-        const uint32_t cb = (__float_as_uint(t[e]) ^ sg) & 0x80000000u;
-        const float c = __uint_as_float(__float_as_uint(mag) | cb);
-        app[addr[e]] = __fadd_rn(t[e], c);
-        nsg |= (cb >> 31) << e;
+        const uint32_t sel = (e == arg) ? m2ss : m1ss;
+        const float c = __uint_as_float(sel ^ (__float_as_uint(t[e]) & 0x80000000u));
+        const float v = __fadd_rn(t[e], c);
+        asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr[e]), "f"(v) : "memory");
     }
-    nm1 = m1s;
-    nm2 = m2s;
-    nmeta = (uint32_t)arg | (nsg << 5);
+    nm1 = __uint_as_float(m1ss & 0x7fffffffu);
+    nm2 = __uint_as_float(m2ss & 0x7fffffffu);
+    // sign of message e = sg ^ sign(t_e)
+    const uint32_t csg = sg ? (ts ^ ((1u << DEG) - 1u)) : ts;
+    nmeta = (uint32_t)arg | (csg << 5);
 }
 
-__global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(const DecArgs a) {
+__global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(const __grid_constant__ DecArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Z = a.Z;
     const int ncw = a.ncols * Z;
     const int K = a.kcols * Z;
     float *app = reinterpret_cast<float *>(smem_raw);
-    uint32_t *s_ed = reinterpret_cast<uint32_t *>(app + (size_t)a.cwpc * ncw);
-    int *s_rs = reinterpret_cast<int *>(s_ed + a.n_edges);
-    int *s_flag = s_rs + (a.n_rows + 1);
+    int *s_flag = reinterpret_cast<int *>(app + (size_t)a.cwpc * ncw);
     __shared__ int s_group;
 
     const int tid = threadIdx.x;
     const int slot = tid / Z;
     const int z = tid - slot * Z;
     const bool lane_ok = tid < a.cwpc * Z;
-
-    for (int i = tid; i < a.n_edges; i += blockDim.x) s_ed[i] = a.edesc[i];
-    for (int i = tid; i <= a.n_rows; i += blockDim.x) s_rs[i] = a.row_start[i];
+    const uint32_t Z4 = (uint32_t)Z * 4u;
 
     const long long n_groups = (a.batch + a.cwpc - 1) / a.cwpc;
     const size_t rec_stride = blockDim.x;
-    float2 *my_mins = a.c2v_mins + (size_t)blockIdx.x * a.n_rows * rec_stride + tid;
-    uint32_t *my_meta = a.c2v_meta + (size_t)blockIdx.x * a.n_rows * rec_stride + tid;
+    uint4 *my_rec = a.c2v + (size_t)blockIdx.x * a.n_rows * rec_stride + tid;
     const bool want_ok = a.ok != nullptr;
 
     while (true) {
-        __syncthreads();  // previous group's outputs are out of smem; tables are loaded
+        __syncthreads();  // previous group's outputs are out of smem
         if (tid == 0) s_group = atomicAdd(a.work_counter, 1);
         __syncthreads();
         const long long group = s_group;
@@ -142,20 +148,18 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
                 v.x = clamp_llr(v.x); v.y = clamp_llr(v.y); v.z = clamp_llr(v.z); v.w = clamp_llr(v.w);
                 dst[i] = v;
             }
-            const int tail = (n_here * ncw) & 3;  // only if ncw is odd-sized (never for valid Z); kept for safety
-            for (int i = (n4 << 2) + tid; i < (n4 << 2) + tail; i += blockDim.x)
-                app[i] = clamp_llr(a.llr[cw0 * ncw + i]);
         }
         if (tid < a.cwpc) s_flag[tid] = 0;
         __syncthreads();
 
         const bool active = lane_ok && slot < n_here;
         float *my_app = app + (size_t)slot * ncw;
+        const uint32_t base = (uint32_t)__cvta_generic_to_shared(my_app);
+        const uint32_t zoff = (uint32_t)z * 4u;
         bool done = !active;
         int my_iters = 0;
         int my_ok = 0;
-        float2 cm = make_float2(0.f, 0.f);
-        uint32_t cmeta = 0;
+        uint4 cur = make_uint4(0u, 0u, 0u, 0u);
 
         for (int it = 0; it < a.max_iters; ++it) {
             const bool store_rec = it + 1 < a.max_iters;
@@ -163,33 +167,26 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
                 // software prefetch of the next layer's record (it wraps into the next iteration)
                 int rn = r + 1, itn = it;
                 if (rn == a.n_rows) { rn = 0; itn = it + 1; }
-                float2 pm = make_float2(0.f, 0.f);
-                uint32_t pmeta = 0;
-                if (!done && itn > 0 && itn < a.max_iters) {
-                    pm = __ldcg(my_mins + (size_t)rn * rec_stride);
-                    pmeta = __ldcg(my_meta + (size_t)rn * rec_stride);
-                }
+                uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+                if (!done && itn > 0 && itn < a.max_iters) nxt = __ldcg(my_rec + (size_t)rn * rec_stride);
                 if (!done) {
-                    const int e0 = s_rs[r];
-                    const int deg = s_rs[r + 1] - e0;
-                    const uint32_t *ed = s_ed + e0;
+                    const int e0 = a.row_start[r];
+                    const int deg = a.row_start[r + 1] - e0;
+                    const uint2 *ed = a.ed + e0;
                     float n1, n2;
                     uint32_t nmeta;
                     switch (deg) {
-#define NRLDPC_ROW_CASE(D) case D: process_row<D>(my_app, ed, z, Z, cm.x, cm.y, cmeta, a.alpha, n1, n2, nmeta); break;
+#define NRLDPC_ROW_CASE(D) case D: process_row<D>(base, ed, zoff, Z4, __uint_as_float(cur.x), __uint_as_float(cur.y), cur.z, a.alpha, n1, n2, nmeta); break;
                         NRLDPC_ROW_CASE(3) NRLDPC_ROW_CASE(4) NRLDPC_ROW_CASE(5) NRLDPC_ROW_CASE(6)
                         NRLDPC_ROW_CASE(7) NRLDPC_ROW_CASE(8) NRLDPC_ROW_CASE(9) NRLDPC_ROW_CASE(10)
                         NRLDPC_ROW_CASE(19)
 #undef NRLDPC_ROW_CASE
                         default: n1 = 0.f; n2 = 0.f; nmeta = 0; break;
                     }
-                    if (store_rec) {
-                        __stcg(my_mins + (size_t)r * rec_stride, make_float2(n1, n2));
-                        __stcg(my_meta + (size_t)r * rec_stride, nmeta);
-                    }
+                    if (store_rec)
+                        __stcg(my_rec + (size_t)r * rec_stride, make_uint4(__float_as_uint(n1), __float_as_uint(n2), nmeta, 0u));
                 }
-                cm = pm;
-                cmeta = pmeta;
+                cur = nxt;
                 __syncthreads();
             }
             if (!done) my_iters = it + 1;
@@ -201,11 +198,13 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
                     int fail = 0;
                     for (int r = 0; r < a.n_rows; ++r) {
                         int par = 0;
-                        for (int e = s_rs[r]; e < s_rs[r + 1]; ++e) {
-                            const uint32_t d = s_ed[e];
-                            int p = z + (int)(d & 0xffffu);
-                            p = (p >= Z) ? p - Z : p;
-                            par ^= (my_app[(d >> 16) + p] < 0.0f) ? 1 : 0;
+                        for (int e = a.row_start[r]; e < a.row_start[r + 1]; ++e) {
+                            const uint2 d = a.ed[e];
+                            const uint32_t u = zoff + d.x;
+                            const uint32_t ad = base + d.y + min(u, u - Z4);
+                            float x;
+                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(ad));
+                            par ^= (x < 0.0f) ? 1 : 0;
                         }
                         fail |= par;
                     }

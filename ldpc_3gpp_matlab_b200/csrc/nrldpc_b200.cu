@@ -37,8 +37,7 @@ struct PipeSlot {
     float *f_in = nullptr;
     size_t cap_cw = 0;          // capacity in codewords of the decode staging
     size_t cap_bytes = 0;       // capacity of the generic staging buffers
-    float2 *c2v_mins = nullptr; // decode scratch (one set per slot: kernels of different slots may overlap)
-    uint32_t *c2v_meta = nullptr;
+    uint4 *c2v = nullptr;       // decode scratch (one set per slot: kernels of different slots may overlap)
     int *counter = nullptr;
     size_t scratch_recs = 0;
 };
@@ -60,6 +59,7 @@ struct nrldpc_handle {
     int enc_delta = 0;
     PipeSlot pipe[kNumPipe];
     int dec_smem_optin = 0;
+    nrldpc::DecArgs dec_args;
     cudaEvent_t dev_done = nullptr;  // last NRLDPC_MEM_DEVICE launch that used pipe[0]'s scratch
 };
 
@@ -110,18 +110,16 @@ int decode_threads(int Z) { return std::max(32, (decode_cwpc(Z) * Z + 31) / 32 *
 
 size_t decode_smem_bytes(const nrldpc_handle *h, int n_rows) {
     const int cwpc = decode_cwpc(h->d.Z);
-    return (size_t)cwpc * h->d.n_cw * 4 + (size_t)h->h_row_start[n_rows] * 4 + (size_t)(n_rows + 1) * 4 +
-           (size_t)cwpc * 4 + 16;
+    (void)n_rows;
+    return (size_t)cwpc * h->d.n_cw * 4 + (size_t)cwpc * 4 + 16;
 }
 
 int ensure_scratch(nrldpc_handle *h, PipeSlot &s, size_t recs) {
     if (!s.counter) CUDA_TRY(h, cudaMalloc(&s.counter, sizeof(int)));
     if (recs <= s.scratch_recs) return 0;
-    if (s.c2v_mins) cudaFree(s.c2v_mins);
-    if (s.c2v_meta) cudaFree(s.c2v_meta);
-    s.c2v_mins = nullptr; s.c2v_meta = nullptr; s.scratch_recs = 0;
-    CUDA_TRY(h, cudaMalloc(&s.c2v_mins, recs * sizeof(float2)));
-    CUDA_TRY(h, cudaMalloc(&s.c2v_meta, recs * sizeof(uint32_t)));
+    if (s.c2v) cudaFree(s.c2v);
+    s.c2v = nullptr; s.scratch_recs = 0;
+    CUDA_TRY(h, cudaMalloc(&s.c2v, recs * sizeof(uint4)));
     s.scratch_recs = recs;
     return 0;
 }
@@ -140,12 +138,12 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
     }
     if (int rc = ensure_scratch(h, s, (size_t)grid * n_rows * threads)) return rc;
     CUDA_TRY(h, cudaMemsetAsync(s.counter, 0, sizeof(int), stream));
-    nrldpc::DecArgs a{};
+    nrldpc::DecArgs &a = h->dec_args;  // tables were filled at create()
     a.llr = llr; a.hard = hard; a.soft = soft; a.iters = iters; a.ok = ok;
     a.batch = batch; a.Z = Z; a.ncols = h->d.cols; a.kcols = h->d.kcols; a.n_rows = n_rows;
     a.n_edges = h->h_row_start[n_rows]; a.max_iters = h->cfg.max_iters; a.early_term = h->cfg.early_term;
-    a.cwpc = cwpc; a.alpha = h->cfg.alpha; a.edesc = h->edesc; a.row_start = h->row_start;
-    a.c2v_mins = s.c2v_mins; a.c2v_meta = s.c2v_meta; a.work_counter = s.counter;
+    a.cwpc = cwpc; a.alpha = h->cfg.alpha;
+    a.c2v = s.c2v; a.work_counter = s.counter;
     nrldpc::decode_nms_kernel<<<grid, threads, smem, stream>>>(a);
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
@@ -299,8 +297,13 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
         while (e < v.edges && v.row[e] < r) ++e;
         h->h_row_start[r] = e;
     }
-    for (int e = 0; e < v.edges; ++e)
-        ed[e] = ((uint32_t)(v.col[e] * Z) << 16) | (uint32_t)(v.sh(ils, e) % Z);
+    memset(&h->dec_args, 0, sizeof(h->dec_args));
+    for (int r = 0; r <= v.rows; ++r) h->dec_args.row_start[r] = (unsigned short)h->h_row_start[r];
+    for (int e = 0; e < v.edges; ++e) {
+        const int sft = v.sh(ils, e) % Z;
+        ed[e] = ((uint32_t)(v.col[e] * Z) << 16) | (uint32_t)sft;
+        h->dec_args.ed[e] = make_uint2((uint32_t)sft * 4u, (uint32_t)(v.col[e] * Z) * 4u);
+    }
     // encoder structure: shifts of the first core-parity column in rows 0..3
     int vals[3], nv = 0;
     for (int r = 0; r < 4; ++r) h->enc_s0[r] = -1;
@@ -338,7 +341,7 @@ NRLDPC_EXPORT void nrldpc_destroy(nrldpc_t *h) {
     for (auto &s : h->pipe) {
         cudaFree(s.llr); cudaFree(s.hard); cudaFree(s.soft); cudaFree(s.iters); cudaFree(s.ok);
         cudaFree(s.bytes_in); cudaFree(s.bytes_out); cudaFree(s.f_in);
-        cudaFree(s.c2v_mins); cudaFree(s.c2v_meta); cudaFree(s.counter);
+        cudaFree(s.c2v); cudaFree(s.counter);
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -471,8 +474,9 @@ NRLDPC_EXPORT int nrldpc_rate_match(nrldpc_t *h, const uint8_t *cw, int64_t batc
     if (mem != NRLDPC_MEM_HOST) return fail(h, NRLDPC_ESHAPE, "mem must be NRLDPC_MEM_HOST or NRLDPC_MEM_DEVICE");
     if (int rc = ensure_pipe(h)) return rc;
     PipeSlot &s = h->pipe[0];
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(batch, ((int64_t)64 << 20) / h->d.n_cw));
-    if (int rc = ensure_generic_staging(h, s, (size_t)chunk * h->d.n_cw)) return rc;
+    const int64_t per_cw = std::max<int64_t>(h->d.n_cw, g.E);
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(batch, ((int64_t)64 << 20) / per_cw));
+    if (int rc = ensure_generic_staging(h, s, (size_t)chunk * per_cw)) return rc;
     for (int64_t off = 0; off < batch; off += chunk) {
         const int64_t n = std::min<int64_t>(chunk, batch - off);
         CUDA_TRY(h, cudaMemcpyAsync(s.bytes_in, cw + off * h->d.n_cw, (size_t)n * h->d.n_cw, cudaMemcpyHostToDevice, s.stream));
@@ -503,8 +507,9 @@ NRLDPC_EXPORT int nrldpc_rate_recover(nrldpc_t *h, const float *f, int64_t batch
     if (mem != NRLDPC_MEM_HOST) return fail(h, NRLDPC_ESHAPE, "mem must be NRLDPC_MEM_HOST or NRLDPC_MEM_DEVICE");
     if (int rc = ensure_pipe(h)) return rc;
     PipeSlot &s = h->pipe[0];
-    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(batch, ((int64_t)16 << 20) / h->d.n_cw));
-    if (int rc = ensure_generic_staging(h, s, (size_t)chunk * h->d.n_cw * sizeof(float))) return rc;
+    const int64_t per_cw = std::max<int64_t>(h->d.n_cw, g.E);
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(batch, ((int64_t)16 << 20) / per_cw));
+    if (int rc = ensure_generic_staging(h, s, (size_t)chunk * per_cw * sizeof(float))) return rc;
     float *d_f = s.f_in, *d_out = reinterpret_cast<float *>(s.bytes_out), *d_harq = reinterpret_cast<float *>(s.bytes_in);
     for (int64_t off = 0; off < batch; off += chunk) {
         const int64_t n = std::min<int64_t>(chunk, batch - off);

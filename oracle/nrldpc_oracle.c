@@ -282,12 +282,21 @@ ORC_API long orc_syndrome_weight(int bg, int Z, int n_rows, const uint8_t *cw) {
 static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
-static int decode_nms_one(int bg, int Z, int ils, int n_rows, int max_iters, int early_term, float alpha,
-                          const float *llr, uint8_t *hard_info, float *app_out, uint8_t *parity_ok) {
+/* vidx[e*Z + z] = variable index touched by check z of base-graph edge e (get_pcm.m:8) */
+static int *build_vidx(int bg, int Z, int ils) {
     int R, C, Kc, E;
     bg_dims(bg, &R, &C, &Kc, &E);
-    const unsigned char *er = bg_row(bg), *ec = bg_col(bg);
-    const unsigned short *es = bg_shift(bg, ils);
+    int *v = (int *)malloc(sizeof(int) * (size_t)E * Z);
+    for (int e = 0; e < E; ++e)
+        for (int z = 0; z < Z; ++z) v[(size_t)e * Z + z] = bg_col(bg)[e] * Z + (z + bg_shift(bg, ils)[e] % Z) % Z;
+    return v;
+}
+
+static int decode_nms_one(int bg, int Z, int ils, int n_rows, int max_iters, int early_term, float alpha,
+                          const int *vidx, const float *llr, uint8_t *hard_info, float *app_out, uint8_t *parity_ok) {
+    int R, C, Kc, E;
+    bg_dims(bg, &R, &C, &Kc, &E);
+    const unsigned char *er = bg_row(bg);
     int row_start[47];
     for (int r = 0, e = 0; r <= R; ++r) { while (e < E && er[e] < r) ++e; row_start[r] = e; }
     const int nV = C * Z;
@@ -306,7 +315,7 @@ static int decode_nms_one(int bg, int Z, int ils, int n_rows, int max_iters, int
                 float m1 = INFINITY, m2 = INFINITY; int arg = 0; uint32_t sgn = 0;
                 for (int k = 0; k < deg; ++k) {
                     int e = e0 + k;
-                    v[k] = ec[e] * Z + (z + es[e] % Z) % Z;
+                    v[k] = vidx[(size_t)e * Z + z];
                     t[k] = app[v[k]] - c2v[(size_t)e * Z + z];
                     float a = fabsf(t[k]);
                     if (a < m1) { m2 = m1; m1 = a; arg = k; } else if (a < m2) { m2 = a; }
@@ -328,7 +337,7 @@ static int decode_nms_one(int bg, int Z, int ils, int n_rows, int max_iters, int
                 for (int z = 0; z < Z; ++z) {
                     int par = 0;
                     for (int e = row_start[r]; e < row_start[r + 1]; ++e)
-                        par ^= app[ec[e] * Z + (z + es[e] % Z) % Z] < 0.0f;
+                        par ^= app[vidx[(size_t)e * Z + z]] < 0.0f;
                     if (par) { ok = 0; break; }
                 }
             if (early_term && ok) break;
@@ -351,13 +360,15 @@ ORC_API int orc_decode_nms(int bg, int Z, int n_rows, int max_iters, int early_t
     if (n_rows < 4) return -1;
     if (n_threads < 1) n_threads = 1;
     const long nV = (long)C * Z, K = (long)Kc * Z;
+    int *vidx = build_vidx(bg, Z, ils);
 #pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
     for (long b = 0; b < batch; ++b) {
-        int it = decode_nms_one(bg, Z, ils, n_rows, max_iters, early_term, alpha, llr + b * nV,
+        int it = decode_nms_one(bg, Z, ils, n_rows, max_iters, early_term, alpha, vidx, llr + b * nV,
                                 hard_info + b * K, app_out ? app_out + b * nV : NULL,
                                 parity_ok ? parity_ok + b : NULL);
         if (iters_out) iters_out[b] = it;
     }
+    free(vidx);
     return 0;
 }
 
@@ -371,20 +382,19 @@ ORC_API int orc_decode_nms(int bg, int Z, int n_rows, int max_iters, int early_t
  * argument is clipped to +-(1 - 2^-53) so that +inf filler LLRs cannot produce inf - inf.
  * Uses the whole H (the reference always passes the full matrix), n_rows <= 0 => all rows.
  * ---------------------------------------------------------------------------------------- */
-static int decode_bp_one(int bg, int Z, int ils, int n_rows, int max_iters, const double *llr,
+static int decode_bp_one(int bg, int Z, int ils, int n_rows, int max_iters, const int *vidx, const double *llr,
                          uint8_t *hard_info, uint8_t *parity_ok) {
     int R, C, Kc, E;
     bg_dims(bg, &R, &C, &Kc, &E);
-    const unsigned char *er = bg_row(bg), *ec = bg_col(bg);
-    const unsigned short *es = bg_shift(bg, ils);
+    const unsigned char *er = bg_row(bg);
     int row_start[47];
     for (int r = 0, e = 0; r <= R; ++r) { while (e < E && er[e] < r) ++e; row_start[r] = e; }
     const int nV = C * Z, Eact = row_start[n_rows];
     double *q = (double *)malloc(sizeof(double) * (size_t)Eact * Z);   /* v2c, [edge][check z] */
     double *rm = (double *)malloc(sizeof(double) * (size_t)Eact * Z);  /* c2v */
     double *Q = (double *)malloc(sizeof(double) * nV);
-    for (int e = 0; e < Eact; ++e)
-        for (int z = 0; z < Z; ++z) q[(size_t)e * Z + z] = llr[ec[e] * Z + (z + es[e] % Z) % Z];
+    const size_t nE = (size_t)Eact * Z;
+    for (size_t i = 0; i < nE; ++i) q[i] = llr[vidx[i]];
     const double lim = 1.0 - ldexp(1.0, -53);
     int it = 0, ok = 0;
     while (it < max_iters) {
@@ -403,18 +413,15 @@ static int decode_bp_one(int bg, int Z, int ils, int n_rows, int max_iters, cons
             }
         }
         for (int i = 0; i < nV; ++i) Q[i] = llr[i];
-        for (int e = 0; e < Eact; ++e)
-            for (int z = 0; z < Z; ++z) Q[ec[e] * Z + (z + es[e] % Z) % Z] += rm[(size_t)e * Z + z];
-        for (int e = 0; e < Eact; ++e)
-            for (int z = 0; z < Z; ++z)
-                q[(size_t)e * Z + z] = Q[ec[e] * Z + (z + es[e] % Z) % Z] - rm[(size_t)e * Z + z];
+        for (size_t i = 0; i < nE; ++i) Q[vidx[i]] += rm[i];
+        for (size_t i = 0; i < nE; ++i) q[i] = Q[vidx[i]] - rm[i];
         ++it;
         ok = 1;
         for (int r = 0; r < n_rows && ok; ++r)
             for (int z = 0; z < Z; ++z) {
                 int par = 0;
                 for (int e = row_start[r]; e < row_start[r + 1]; ++e)
-                    par ^= Q[ec[e] * Z + (z + es[e] % Z) % Z] < 0.0;
+                    par ^= Q[vidx[(size_t)e * Z + z]] < 0.0;
                 if (par) { ok = 0; break; }
             }
         if (ok) break;
@@ -434,12 +441,14 @@ ORC_API int orc_decode_bp(int bg, int Z, int n_rows, int max_iters, const double
     if (n_rows <= 0 || n_rows > R) n_rows = R;
     if (n_threads < 1) n_threads = 1;
     const long nV = (long)C * Z, K = (long)Kc * Z;
+    int *vidx = build_vidx(bg, Z, ils);
 #pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
     for (long b = 0; b < batch; ++b) {
-        int it = decode_bp_one(bg, Z, ils, n_rows, max_iters, llr + b * nV, hard_info + b * K,
+        int it = decode_bp_one(bg, Z, ils, n_rows, max_iters, vidx, llr + b * nV, hard_info + b * K,
                                parity_ok ? parity_ok + b : NULL);
         if (iters_out) iters_out[b] = it;
     }
+    free(vidx);
     return 0;
 }
 
@@ -452,15 +461,17 @@ ORC_API int orc_decode_bp_f32(int bg, int Z, int n_rows, int max_iters, const fl
     if (n_rows <= 0 || n_rows > R) n_rows = R;
     if (n_threads < 1) n_threads = 1;
     const long nV = (long)C * Z, K = (long)Kc * Z;
+    int *vidx = build_vidx(bg, Z, ils);
 #pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
     for (long b = 0; b < batch; ++b) {
         double *d = (double *)malloc(sizeof(double) * nV);
         for (long i = 0; i < nV; ++i) d[i] = llr[b * nV + i];
-        int it = decode_bp_one(bg, Z, ils, n_rows, max_iters, d, hard_info + b * K,
+        int it = decode_bp_one(bg, Z, ils, n_rows, max_iters, vidx, d, hard_info + b * K,
                                parity_ok ? parity_ok + b : NULL);
         if (iters_out) iters_out[b] = it;
         free(d);
     }
+    free(vidx);
     return 0;
 }
 

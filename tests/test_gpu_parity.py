@@ -1,0 +1,286 @@
+"""Parity tests proper: the sm_100a kernels, called through the C ABI, against the CPU oracle on the
+same seeded inputs (bit-exact: hard bits, iteration counts, parity flags AND float32 APP bit patterns),
+against the committed golden vectors, and through size-independent properties at BASELINE sizes."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import ALL_Z, make_llr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from ldpc_3gpp_matlab_b200 import capi
+    capi.load()
+    return capi
+
+
+def _same_bits(a, b):
+    return bool((a.view(np.uint32) == b.view(np.uint32)).all())
+
+
+def test_decode_golden_vectors_on_gpu(capi, golden_decode):
+    names = sorted({k.split("__")[0] for k in golden_decode.files})
+    for n in names:
+        bg, Z, iters, et, rows = golden_decode[n + "__cfg"].tolist()
+        h = capi.Handle(bg, Z, iters, bool(et))
+        out = h.decode(golden_decode[n + "__llr"], n_rows=rows, want_soft=True)
+        assert (np.packbits(out["hard"], axis=1) == golden_decode[n + "__hard"]).all(), n
+        assert (out["iters"] == golden_decode[n + "__iters"]).all(), n
+        assert (out["parity_ok"] == golden_decode[n + "__ok"]).all(), n
+        u = out["app"].view(np.uint32)
+        assert (np.bitwise_xor.reduce(u, axis=1) == golden_decode[n + "__app_xor"]).all(), n
+        assert (u.astype(np.uint64).sum(axis=1) == golden_decode[n + "__app_sum"]).all(), n
+        h.close()
+
+
+@pytest.mark.parametrize("bg", [1, 2])
+def test_decode_bit_exact_all_51_lifting_sizes(capi, O, bg):
+    """Every (BG, Z): ragged batch (not a multiple of codewords-per-CTA), fixed iterations and early stop."""
+    rng = np.random.default_rng(100 + bg)
+    for Z in ALL_Z:
+        d = O.dims(bg, Z)
+        B = max(3, min(40, 1500 // Z)) + 1
+        E = int(d["N"] * rng.uniform(0.35, 1.0)) // 2 * 2
+        info, llr = make_llr(O, bg, Z, B, E, rng.uniform(-1.0, 3.0), rng)
+        for et in (False, True):
+            ref = O.decode_nms(bg, Z, llr, 6, early_term=et)
+            h = capi.Handle(bg, Z, 6, et)
+            out = h.decode(llr, want_soft=True)
+            h.close()
+            assert (out["hard"] == ref["hard"]).all(), (bg, Z, et)
+            assert _same_bits(out["app"], ref["app"]), (bg, Z, et)
+            assert (out["iters"] == ref["iters"]).all() and (out["parity_ok"] == ref["parity_ok"]).all(), (bg, Z, et)
+
+
+@pytest.mark.parametrize("bg,Z,rows", [(1, 384, 46), (1, 384, 5), (1, 384, 13), (2, 52, 33), (2, 6, 13), (2, 384, 42),
+                                       (1, 30, 4), (2, 208, 20)])
+def test_decode_special_values_and_row_trimming(capi, O, bg, Z, rows):
+    """+inf / NaN filler, exact zeros, huge and denormal magnitudes, -0.0; active-row trimming."""
+    rng = np.random.default_rng(Z + rows)
+    d = O.dims(bg, Z)
+    B = 5
+    llr = (rng.normal(0, 4, (B, d["ncw"]))).astype(np.float32)
+    llr[:, :2 * Z] = 0
+    llr[:, (d["kcols"] + rows) * Z:] = 0
+    llr[0, 3 * Z:3 * Z + 17] = np.inf
+    llr[1, 3 * Z:3 * Z + 17] = np.nan
+    llr[2, 5 * Z:5 * Z + 9] = -np.inf
+    llr[3, ::7] = 0.0
+    llr[3, 1::11] = -0.0
+    llr[4, 2 * Z::5] *= 1e30
+    llr[4, 2 * Z + 1::9] *= 1e-42
+    for et in (False, True):
+        ref = O.decode_nms(bg, Z, llr, 7, early_term=et, n_rows=rows)
+        h = capi.Handle(bg, Z, 7, et)
+        out = h.decode(llr, n_rows=rows, want_soft=True)
+        h.close()
+        assert np.isfinite(out["app"]).all()
+        assert (out["hard"] == ref["hard"]).all() and _same_bits(out["app"], ref["app"])
+        assert (out["iters"] == ref["iters"]).all() and (out["parity_ok"] == ref["parity_ok"]).all()
+
+
+def test_decode_alpha_and_iteration_sweep(capi, O):
+    rng = np.random.default_rng(9)
+    info, llr = make_llr(O, 2, 104, 6, 4000, -1.5, rng)
+    for alpha, iters in ((0.75, 1), (0.8125, 3), (1.0, 5), (0.7, 12)):
+        ref = O.decode_nms(2, 104, llr, iters, alpha=alpha)
+        h = capi.Handle(2, 104, iters, False, alpha=alpha)
+        out = h.decode(llr, want_soft=True)
+        h.close()
+        assert (out["hard"] == ref["hard"]).all() and _same_bits(out["app"], ref["app"]), (alpha, iters)
+
+
+def test_decode_empty_batch_and_shape_errors(capi):
+    h = capi.Handle(1, 8, 4)
+    out = h.decode(np.zeros((0, h.n_cw), np.float32))
+    assert out["hard"].shape == (0, h.K)
+    with pytest.raises(capi.NRLDPCError):
+        h.decode(np.zeros((2, h.n_cw - 1), np.float32))
+    with pytest.raises(capi.UnsupportedParameters):
+        h.decode(np.zeros((2, h.n_cw), np.float32), n_rows=3)
+    with pytest.raises(capi.UnsupportedParameters):
+        h.decode(np.zeros((2, h.n_cw), np.float32), n_rows=47)
+    h.close()
+
+
+def test_decode_device_pointers_match_host_path(capi, O):
+    import torch
+    rng = np.random.default_rng(4)
+    info, llr = make_llr(O, 1, 96, 37, 5000, 0.0, rng)
+    h = capi.Handle(1, 96, 8, True)
+    host = h.decode(llr, want_soft=True)
+    t = torch.from_numpy(llr).cuda()
+    hard = torch.zeros((37, h.K), dtype=torch.uint8, device="cuda")
+    soft = torch.zeros((37, h.n_cw), dtype=torch.float32, device="cuda")
+    iters = torch.zeros(37, dtype=torch.int32, device="cuda")
+    ok = torch.zeros(37, dtype=torch.uint8, device="cuda")
+    h.decode_raw(t, 37, hard, soft, iters, ok, mem=capi.MEM_DEVICE, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert (hard.cpu().numpy() == host["hard"]).all() and _same_bits(soft.cpu().numpy(), host["app"])
+    assert (iters.cpu().numpy() == host["iters"]).all() and (ok.cpu().numpy() == host["parity_ok"]).all()
+    h.close()
+
+
+@pytest.mark.parametrize("bg", [1, 2])
+def test_encode_all_102_against_oracle(capi, O, bg):
+    rng = np.random.default_rng(200 + bg)
+    for Z in ALL_Z:
+        d = O.dims(bg, Z)
+        info = rng.integers(0, 2, (5, d["K"]), dtype=np.uint8)
+        h = capi.Handle(bg, Z, 1)
+        cw = h.encode(info)
+        h.close()
+        assert (cw == O.encode(bg, Z, info)).all(), (bg, Z)
+        assert all(O.syndrome_weight(bg, Z, c) == 0 for c in cw)
+
+
+def test_encode_linearity_and_zero(capi):
+    """Size-independent properties at the headline size: enc(0)=0, enc(a^b)=enc(a)^enc(b)."""
+    rng = np.random.default_rng(11)
+    h = capi.Handle(1, 384, 1)
+    a = rng.integers(0, 2, (64, h.K), dtype=np.uint8)
+    b = rng.integers(0, 2, (64, h.K), dtype=np.uint8)
+    assert not h.encode(np.zeros((2, h.K), np.uint8)).any()
+    assert (h.encode(a ^ b) == (h.encode(a) ^ h.encode(b))).all()
+    h.close()
+
+
+@pytest.mark.parametrize("A,BG,R,Qm,rv,lbrm", [(20, 2, 0.2, 2, 0, 0), (400, 2, 0.2, 4, 1, 0), (1000, 1, 1 / 3, 6, 2, 0),
+                                               (3842, 2, 1 / 3, 2, 3, 0), (8000, 1, 0.5, 8, 0, 0), (500, 1, 0.12, 1, 3, 0),
+                                               (8424, 1, 1 / 3, 2, 2, 1), (8424, 1, 8 / 9, 2, 0, 0), (60, 2, 0.05, 2, 1, 0)])
+def test_rate_match_and_recover_against_reference_loops(capi, O, A, BG, R, Qm, rv, lbrm):
+    """GPU closed-form index maps vs the oracle's literal restatement of the reference's while-loops
+    (NRLDPCEncoder.m:168-225, NRLDPCDecoder.m:172-242,262-264), including wrap-around soft combining,
+    filler skipping, all rv_id, LBRM and a HARQ retransmission."""
+    G = int(math.floor(A / R / Qm + 0.5)) * Qm
+    p = O.params(BG, A, G, Q_m=Qm, rv_id=rv, I_LBRM=lbrm, TBS_LBRM=A)
+    assert p is not None
+    Z, K, Kp, N, E = p.Z_c, p.K, p.K_prime, p.N, p.E_r[0]
+    rng = np.random.default_rng(A + rv)
+    B = 3
+    info = rng.integers(0, 2, (B, K), dtype=np.uint8)
+    info[:, Kp:] = 0
+    h = capi.Handle(BG, Z, 1)
+    cw = h.encode(info)
+    f = h.rate_match(cw, E, p.k_0, p.N_cb, Kp, Qm)
+    harq_gpu = np.zeros((B, N), np.float32)
+    harq_ref = [np.zeros(p.N_cb, np.float32) for _ in range(B)]
+    for tx in range(2):
+        llr_f = ((1 - 2.0 * f) * rng.uniform(0.5, 4.0, f.shape)).astype(np.float32)
+        got = h.rate_recover(llr_f, E, p.k_0, p.N_cb, Kp, Qm, harq=harq_gpu)
+        for b in range(B):
+            d = O.cw_to_d(Z, K, Kp, N, cw[b])
+            if tx == 0:
+                assert (f[b] == O.interleave_tx(O.bit_selection_tx(d, p.N_cb, p.k_0, E), Qm)).all()
+            d_t = O.bit_selection_rx(O.deinterleave_rx(llr_f[b], Qm), N, p.N_cb, p.k_0, Z, K, Kp, harq_buf=harq_ref[b])
+            want = O.d_to_cw_llr(d_t, Z)
+            assert (got[b].view(np.uint32) == want.view(np.uint32)).all(), (tx, b)
+    h.close()
+
+
+def test_full_chain_system_objects(capi, O):
+    """encode -> QPSK -> AWGN -> exact LLR -> decode through the NRLDPCEncoder/NRLDPCDecoder mirrors
+    (plot_BLER_vs_SNR.m:118-146 for one frame per configuration), incl. C=2 segmentation and a_hat=[]."""
+    from ldpc_3gpp_matlab_b200.nrldpc import NRLDPCDecoder, NRLDPCEncoder, matlab_round
+    rng = np.random.default_rng(21)
+    for A, BG, R, esn0 in ((20, 2, 0.2, 6.0), (3842, 2, 1 / 3, 3.0), (8424, 1, 1 / 3, 1.5), (8424, 1, 8 / 9, 9.0),
+                           (12000, 1, 0.5, 4.0)):
+        G = matlab_round(A / R / 2) * 2
+        enc = NRLDPCEncoder(A=A, BG=BG, G=G, Q_m=2)
+        dec = NRLDPCDecoder(A=A, BG=BG, G=G, Q_m=2, I_HARQ=1, iterations=8)
+        a = rng.integers(0, 2, A).astype(np.float64)
+        g = enc.step(a)
+        assert g.shape == (G,) and set(np.unique(g)) <= {0.0, 1.0}
+        var = 10 ** (-esn0 / 10)
+        re, im = O.qpsk_mod(g.astype(np.uint8))
+        re = re + rng.normal(0, math.sqrt(var / 2), re.shape).astype(np.float32)
+        im = im + rng.normal(0, math.sqrt(var / 2), im.shape).astype(np.float32)
+        dec.reset()
+        a_hat = dec.step(O.qpsk_demod(re, im, var))
+        assert a_hat.shape == (A,) and (a_hat == a).all(), (A, BG)
+        # garbage in -> CRC failure -> empty output (NRLDPCDecoder.m:337-339)
+        dec.reset()
+        assert dec.step(rng.normal(0, 1, G)).size == 0
+        with pytest.raises(capi.NRLDPCError):
+            dec.step(np.zeros(G + 1))
+        enc.release(); dec.release()
+
+
+def test_harq_retransmissions_combine(capi, O):
+    """rv_id sequence [0,2,3,1] at an SNR where one transmission fails but the combination succeeds."""
+    from ldpc_3gpp_matlab_b200.nrldpc import NRLDPCDecoder, NRLDPCEncoder
+    rng = np.random.default_rng(33)
+    A, BG, G = 4000, 1, 4800
+    enc = NRLDPCEncoder(A=A, BG=BG, G=G, Q_m=2)
+    dec = NRLDPCDecoder(A=A, BG=BG, G=G, Q_m=2, I_HARQ=1, iterations=12)
+    a = rng.integers(0, 2, A).astype(np.float64)
+    var = 10 ** (-(-1.0) / 10)
+    dec.reset()
+    results = []
+    for rv in (0, 2, 3, 1):
+        enc.rv_id = rv; dec.rv_id = rv
+        g = enc.step(a)
+        re, im = O.qpsk_mod(g.astype(np.uint8))
+        re = re + rng.normal(0, math.sqrt(var / 2), re.shape).astype(np.float32)
+        im = im + rng.normal(0, math.sqrt(var / 2), im.shape).astype(np.float32)
+        a_hat = dec.step(O.qpsk_demod(re, im, var))
+        results.append(a_hat.size > 0 and bool((a_hat == a).all()))
+    assert results[0] is False and results[-1] is True
+
+
+def test_headline_size_round_trip_properties(capi):
+    """BASELINE config 2 at full size (BG1 Z=384 K=8448 rate 1/3, batch 4096, 8 iterations): on-device
+    encode -> rate match -> QPSK/AWGN/LLR -> rate recover -> decode; every block must come back at
+    2 dB, and the all-zero LLR input must decode to all-zero bits."""
+    import torch
+    B, E = 4096, 25272
+    h = capi.Handle(1, 384, 8, False)
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cuda").manual_seed(5)
+    info = torch.randint(0, 2, (B, h.K), dtype=torch.uint8, device="cuda", generator=g)
+    cw = torch.empty((B, h.n_cw), dtype=torch.uint8, device="cuda")
+    f = torch.empty((B, E), dtype=torch.uint8, device="cuda")
+    fl = torch.empty((B, E), dtype=torch.float32, device="cuda")
+    llr = torch.empty((B, h.n_cw), dtype=torch.float32, device="cuda")
+    hard = torch.empty((B, h.K), dtype=torch.uint8, device="cuda")
+    ok = torch.empty(B, dtype=torch.uint8, device="cuda")
+    rm = capi.Rm(E, 0, h.N, h.K, 2)
+    h.encode_raw(info, B, cw, mem=capi.MEM_DEVICE, stream=st)
+    h.rate_match_raw(cw, B, rm, f, mem=capi.MEM_DEVICE, stream=st)
+    h.qpsk_awgn_llr_raw(f, B, E, 10 ** (-0.2), 7, 0, fl, stream=st)
+    h.rate_recover_raw(fl, B, rm, None, llr, mem=capi.MEM_DEVICE, stream=st)
+    h.decode_raw(llr, B, hard, ok=ok, mem=capi.MEM_DEVICE, stream=st)
+    torch.cuda.synchronize()
+    assert torch.equal(cw[:, :h.K], info)
+    assert torch.equal(hard, info) and bool(ok.all())
+    # noise statistics of the channel leg: LLR = 2*sqrt(2)*(x+n)/var, so var(LLR | bit) = 4/var
+    var = 10 ** (-0.2)
+    s = (fl * (1 - 2.0 * f.float()))
+    assert abs(float(s.mean()) - 2.0 / var) < 0.01 * 2.0 / var
+    assert abs(float(s.var()) - 4.0 / var) < 0.01 * 4.0 / var
+    llr.zero_()
+    h.decode_raw(llr, B, hard, mem=capi.MEM_DEVICE, stream=st)
+    torch.cuda.synchronize()
+    assert not bool(hard.any())
+    h.close()
+
+
+def test_small_z_high_batch_config3(capi, O):
+    """BASELINE config 3 (BG2 Z=52, 104 filler, E=2000, 33 active rows, batch 65536): GPU batch equals the
+    oracle on a strided sample and is idempotent (decoding twice gives the same bytes)."""
+    import torch
+    rng = np.random.default_rng(52)
+    info, llr = make_llr(O, 2, 52, 512, 2000, -1.0, rng, filler=104)
+    big = np.tile(llr, (128, 1))
+    h = capi.Handle(2, 52, 8, False)
+    out1 = h.decode(big, n_rows=33)
+    out2 = h.decode(big, n_rows=33)
+    assert (out1["hard"] == out2["hard"]).all()
+    ref = O.decode_nms(2, 52, llr, 8, n_rows=33)
+    for rep in (0, 57, 127):
+        assert (out1["hard"][rep * 512:(rep + 1) * 512] == ref["hard"]).all()
+    h.close()

@@ -1,0 +1,118 @@
+"""Oracle known-answer and property tests -- CPU only."""
+import numpy as np
+import pytest
+
+from conftest import make_llr
+
+
+def _bits(s):
+    return np.unpackbits(np.frombuffer(s, dtype=np.uint8))
+
+
+def test_crc_check_values(O, golden_tables):
+    """CRC catalogue check values for '123456789' (CRC-16/XMODEM, CRC-24/LTE-A, CRC-24/LTE-B)."""
+    for kind, want in golden_tables["crc_check_123456789"].items():
+        par = O.crc(kind, _bits(b"123456789"))
+        got = int("".join(str(int(b)) for b in par), 2)
+        assert got == want, kind
+
+
+def test_decode_golden_vectors(O, golden_decode):
+    names = sorted({k.split("__")[0] for k in golden_decode.files})
+    assert len(names) >= 6
+    for n in names:
+        bg, Z, iters, et, rows = golden_decode[n + "__cfg"].tolist()
+        out = O.decode_nms(bg, Z, golden_decode[n + "__llr"], iters, early_term=bool(et), n_rows=rows)
+        assert (np.packbits(out["hard"], axis=1) == golden_decode[n + "__hard"]).all(), n
+        assert (out["iters"] == golden_decode[n + "__iters"]).all(), n
+        assert (out["parity_ok"] == golden_decode[n + "__ok"]).all(), n
+        u = out["app"].view(np.uint32)
+        assert (np.bitwise_xor.reduce(u, axis=1) == golden_decode[n + "__app_xor"]).all(), n
+        assert (u.astype(np.uint64).sum(axis=1) == golden_decode[n + "__app_sum"]).all(), n
+
+
+@pytest.mark.parametrize("bg,Z", [(1, 2), (1, 15), (2, 3), (2, 52), (1, 96), (2, 240)])
+def test_noiseless_round_trip_both_decoders(O, bg, Z):
+    rng = np.random.default_rng(Z)
+    d = O.dims(bg, Z)
+    info = rng.integers(0, 2, (3, d["K"]), dtype=np.uint8)
+    cw = O.encode(bg, Z, info)
+    llr = (4.0 * (1 - 2.0 * cw)).astype(np.float32)
+    llr[:, :2 * Z] = 0  # punctured columns must be recovered
+    a = O.decode_nms(bg, Z, llr, 10, early_term=True)
+    b = O.decode_bp(bg, Z, llr, 10)
+    assert (a["hard"] == info).all() and a["parity_ok"].all() and (a["iters"] <= 3).all()
+    assert (b["hard"] == info).all() and b["parity_ok"].all()
+
+
+def test_filler_and_row_trimming_equivalence(O):
+    """Rows whose parity bit was not sent carry a zero degree-1 LLR: trimming them changes nothing."""
+    rng = np.random.default_rng(7)
+    bg, Z, E, fill = 2, 52, 2000, 104
+    info, llr = make_llr(O, bg, Z, 6, E, -2.0, rng, filler=fill)
+    full = O.decode_nms(bg, Z, llr, 8, n_rows=0)
+    trim = O.decode_nms(bg, Z, llr, 8, n_rows=33)
+    assert (full["hard"] == trim["hard"]).all()
+    np.testing.assert_array_equal(np.abs(full["app"][:, :35 * Z]), np.abs(trim["app"][:, :35 * Z]))
+
+
+def test_nms_beats_bp_is_reported_not_assumed(O):
+    """Both decoders clear a comfortable SNR; the dB delta between them is a DESIGN.md number."""
+    rng = np.random.default_rng(3)
+    info, llr = make_llr(O, 2, 6, 200, 100, 6.0, rng, filler=24)
+    a = O.decode_nms(2, 6, llr, 8, early_term=True, n_rows=13)
+    b = O.decode_bp(2, 6, llr, 8)
+    assert (a["hard"][:, :36] != info[:, :36]).any(1).mean() < 0.05
+    assert (b["hard"][:, :36] != info[:, :36]).any(1).mean() < 0.05
+
+
+def test_inf_nan_and_clamp(O):
+    rng = np.random.default_rng(5)
+    info, llr = make_llr(O, 1, 48, 4, 3000, 0.5, rng, filler=40)
+    llr2 = llr.copy()
+    llr2[np.isinf(llr2)] = np.nan            # NaN marks filler upstream (NRLDPCDecoder.m:224)
+    a, b = O.decode_nms(1, 48, llr), O.decode_nms(1, 48, llr2)
+    assert (a["hard"] == b["hard"]).all() and np.isfinite(a["app"]).all()
+    assert (a["app"].view(np.uint32) == b["app"].view(np.uint32)).all()
+
+
+@pytest.mark.parametrize("A,BG,R,Qm,rv", [(20, 2, 0.2, 2, 0), (400, 2, 0.2, 4, 1), (1000, 1, 1 / 3, 6, 2),
+                                          (3842, 2, 1 / 3, 2, 3), (8000, 1, 0.5, 8, 0), (500, 1, 0.12, 1, 3)])
+def test_rate_match_recover_round_trip(O, A, BG, R, Qm, rv):
+    """TX bit_selection/interleave followed by RX deinterleave/bit_selection returns every sent bit to its
+    own position; wrapped repetitions add (NRLDPCDecoder.m:230)."""
+    import math
+    G = int(math.floor(A / R / Qm + 0.5)) * Qm
+    p = O.params(BG, A, G, Q_m=Qm, rv_id=rv)
+    if p is None:
+        pytest.skip("UnsupportedParameters")
+    rng = np.random.default_rng(A)
+    Z, K, Kp, N = p.Z_c, p.K, p.K_prime, p.N
+    info = rng.integers(0, 2, K, dtype=np.uint8)
+    info[Kp:] = 0
+    cw = O.encode(BG, Z, info)
+    d = O.cw_to_d(Z, K, Kp, N, cw)
+    E = p.E_r[0]
+    e = O.bit_selection_tx(d, p.N_cb, p.k_0, E)
+    f = O.interleave_tx(e, Qm)
+    assert set(np.unique(f)) <= {0, 1}
+    llr_f = (1.0 - 2.0 * f).astype(np.float32)
+    e_t = O.deinterleave_rx(llr_f, Qm)
+    assert (e_t == 1.0 - 2.0 * e).all()
+    d_t = O.bit_selection_rx(e_t, N, p.N_cb, p.k_0, Z, K, Kp)
+    filler = np.isnan(d_t)
+    assert filler.sum() == K - max(Kp, 2 * Z) if K > max(Kp, 2 * Z) else filler.sum() == 0
+    sent = (d_t != 0) & ~filler
+    assert (np.sign(d_t[sent]) == 1 - 2.0 * d[sent]).all()
+    assert np.abs(d_t[~filler]).sum() == E       # every transmitted LLR landed somewhere, repeats added
+    cwl = O.d_to_cw_llr(d_t, Z)
+    assert (cwl[:2 * Z] == 0).all() and np.isinf(cwl[2 * Z:][filler]).all()
+
+
+def test_qpsk_map_and_llr(O):
+    bits = np.array([0, 0, 0, 1, 1, 0, 1, 1], np.uint8)
+    re, im = O.qpsk_mod(bits)
+    a = np.float32(1 / np.sqrt(2))
+    np.testing.assert_allclose(re, [a, a, -a, -a]); np.testing.assert_allclose(im, [a, -a, a, -a])
+    llr = O.qpsk_demod(re, im, 0.5)
+    np.testing.assert_allclose(llr, (1 - 2.0 * bits) * 2 * np.sqrt(2) * a / 0.5, rtol=1e-6)
