@@ -12,10 +12,13 @@
 //   * the a-posteriori LLRs (cols*Z floats per codeword, 104 KB at BG1/Z=384) live in shared
 //     memory for all iterations; two CTAs fit per SM so one CTA's barriers/loads hide under the
 //     other's arithmetic;
-//   * check-to-variable messages are kept compressed (alpha*min1, alpha*min2, argmin, sign bits =
-//     12 B per check) in a per-CTA global scratch that stays L2-resident (<= 63 MB for the whole
-//     grid), software-prefetched one layer ahead; the first iteration reads nothing and the last
-//     writes nothing;
+//   * check-to-variable messages are kept compressed (alpha*min1, alpha*min2, argmin, sign bits)
+//     as one 16-byte record per check in a per-CTA global scratch that stays L2-resident,
+//     software-prefetched one layer ahead; the first iteration reads nothing and the last writes
+//     nothing;
+//   * the base graph's shape (row degrees, edge order) is a compile-time constant per base graph:
+//     the layer loop is fully unrolled, and the per-edge shift / column offsets are read straight
+//     from the kernel-parameter constant bank as instruction operands (no descriptor loads);
 //   * arithmetic is float32 with every add/mul individually rounded (__fsub_rn/__fmul_rn/__fadd_rn:
 //     no FMA contraction), signs handled as sign BITS, so results are bit-identical to the CPU
 //     oracle (oracle/nrldpc_oracle.c, function orc_decode_nms).
@@ -28,11 +31,10 @@ namespace nrldpc {
 constexpr int kDecThreads = 384;     // max threads per decode CTA (= largest lifting size)
 constexpr int kDecCtasPerSm = 2;
 constexpr float kLlrMax = 1048576.0f;
-
 constexpr int kMaxEdges = 316;
 constexpr int kMaxRows = 46;
 
-// Edge descriptor, read from the kernel-parameter constant bank with a warp-uniform index:
+// Edge descriptor, read from the kernel-parameter constant bank:
 //   x = shift*4   (bytes): lane z reads circulant position (z + shift) mod Z
 //   y = col*Z*4   (bytes): start of the block column inside one codeword's APP array
 struct DecArgs {
@@ -44,15 +46,36 @@ struct DecArgs {
     long long batch;
     int Z, ncols, kcols, n_rows, n_edges, max_iters, early_term, cwpc;
     float alpha;
-    uint4 *c2v;              // [grid][n_rows][blockDim] {alpha*min1, alpha*min2, argmin | signbits << 5, -}
+    uint4 *c2v;              // [grid][n_rows+1][blockDim] {alpha*min1, alpha*min2, argmin | signbits << 5, -}
     int *work_counter;
     unsigned short row_start[kMaxRows + 2];
     uint2 ed[kMaxEdges];
 };
 
+template <int BG> struct BgShape;
+template <> struct BgShape<1> {
+    static constexpr int kRows = NRLDPC_BG1_ROWS;
+    static __host__ __device__ constexpr int deg(int r) { return nrldpc_bg1_deg[r]; }
+    static __host__ __device__ constexpr int start(int r) { return nrldpc_bg1_start[r]; }
+};
+template <> struct BgShape<2> {
+    static constexpr int kRows = NRLDPC_BG2_ROWS;
+    static __host__ __device__ constexpr int deg(int r) { return nrldpc_bg2_deg[r]; }
+    static __host__ __device__ constexpr int start(int r) { return nrldpc_bg2_start[r]; }
+};
+
 __device__ __forceinline__ float clamp_llr(float x) {
     // NaN marks filler upstream (NRLDPCDecoder.m:224,264): fminf(NaN, M) = M.
     return fmaxf(fminf(x, kLlrMax), -kLlrMax);
+}
+
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float x;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(addr));
+    return x;
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
 // One check row of degree DEG for check z.  `base` = byte address (shared window) of this thread's
@@ -74,11 +97,10 @@ __device__ __forceinline__ void process_row(const uint32_t base, const uint2 *__
 #pragma unroll
     for (int e = 0; e < DEG; ++e) {
         const uint2 d = ed[e];
-        const uint32_t u = zoff + d.x;              // (z + shift)*4, wraps at Z*4:
+        const uint32_t u = zoff + d.x;                   // (z + shift)*4, wraps at Z*4:
         const uint32_t a = base + d.y + min(u, u - Z4);  // u - Z4 underflows to a huge value when u < Z4
         addr[e] = a;
-        float x;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(a));
+        const float x = lds_f32(a);
         const float mag = (e == oarg) ? om2 : om1;
         const float c = __uint_as_float(__float_as_uint(mag) | ((osg << (31 - (DEG - 1 - e))) & 0x80000000u));
         const float tt = __fsub_rn(x, c);
@@ -99,8 +121,7 @@ __device__ __forceinline__ void process_row(const uint32_t base, const uint2 *__
     for (int e = 0; e < DEG; ++e) {
         const uint32_t sel = (e == arg) ? m2ss : m1ss;
         const float c = __uint_as_float(sel ^ (__float_as_uint(t[e]) & 0x80000000u));
-        const float v = __fadd_rn(t[e], c);
-        asm volatile("st.shared.f32 [%0], %1;" :: "r"(addr[e]), "f"(v) : "memory");
+        sts_f32(addr[e], __fadd_rn(t[e], c));
     }
     nm1 = __uint_as_float(m1ss & 0x7fffffffu);
     nm2 = __uint_as_float(m2ss & 0x7fffffffu);
@@ -109,6 +130,123 @@ __device__ __forceinline__ void process_row(const uint32_t base, const uint2 *__
     nmeta = (uint32_t)arg | (csg << 5);
 }
 
+// ---- pieces shared by both kernel variants -------------------------------------------------------
+struct DecCtx {
+    uint32_t base, zoff, Z4;
+    uint4 *my_rec;   // slot 0 of this thread's record column
+    uint4 *rec0;     // slot n_rows: where layer 0's record lives
+    uint32_t rec_stride;
+    uint4 cur;
+    bool done;
+};
+
+__device__ __forceinline__ void load_group(const DecArgs &a, float *app, long long cw0, int n_here, int ncw) {
+    // the group's codewords are contiguous in HBM; ncw*4 bytes is a multiple of 16 for every (BG,Z)
+    const float4 *src = reinterpret_cast<const float4 *>(a.llr + cw0 * ncw);
+    float4 *dst = reinterpret_cast<float4 *>(app);
+    const int n4 = (n_here * ncw) >> 2;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+        float4 v = __ldcs(src + i);
+        v.x = clamp_llr(v.x); v.y = clamp_llr(v.y); v.z = clamp_llr(v.z); v.w = clamp_llr(v.w);
+        dst[i] = v;
+    }
+}
+
+// exact syndrome of hard = (app < 0) over the active rows ('Parity check satisfied', NRLDPCDecoder.m:120)
+__device__ __forceinline__ int syndrome_fail(const DecArgs &a, const DecCtx &c) {
+    int fail = 0;
+    for (int r = 0; r < a.n_rows; ++r) {
+        int par = 0;
+        for (int e = a.row_start[r]; e < a.row_start[r + 1]; ++e) {
+            const uint2 d = a.ed[e];
+            const uint32_t u = c.zoff + d.x;
+            par ^= (lds_f32(c.base + d.y + min(u, u - c.Z4)) < 0.0f) ? 1 : 0;
+        }
+        fail |= par;
+    }
+    return fail;
+}
+
+__device__ __forceinline__ void store_outputs(const DecArgs &a, const float *app, long long cw0, int n_here, int ncw, int K) {
+    for (int s = 0; s < n_here; ++s) {
+        const float *src = app + (size_t)s * ncw;
+        uint8_t *dst = a.hard + (cw0 + s) * K;
+        for (int k = threadIdx.x; k < K; k += blockDim.x) dst[k] = src[k] < 0.0f ? 1 : 0;
+    }
+    if (a.soft) {
+        float4 *dst = reinterpret_cast<float4 *>(a.soft + cw0 * ncw);
+        const float4 *src = reinterpret_cast<const float4 *>(app);
+        const int n4 = (n_here * ncw) >> 2;
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) __stcs(dst + i, src[i]);
+    }
+}
+
+// ---- one full iteration over the layers: looped (generic) --------------------------------------
+__device__ __forceinline__ void iteration_looped(const DecArgs &a, DecCtx &c, const int it) {
+    const bool store_rec = it + 1 < a.max_iters;
+    // Record slots: layer r >= 1 lives in slot r; layer 0 lives in slot n_rows, so that "the next
+    // layer's record" is always the next slot, also across the iteration boundary.
+    uint4 *rp = c.my_rec;
+    for (int r = 0; r < a.n_rows; ++r) {
+        // software prefetch of the next layer's record
+        uint4 *np = rp + c.rec_stride;
+        const bool ld = (r + 1 == a.n_rows) ? store_rec : (it > 0);
+        uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+        if (ld && !c.done) nxt = __ldcg(np);
+        if (!c.done) {
+            const int e0 = a.row_start[r];
+            const int deg = a.row_start[r + 1] - e0;
+            const uint2 *ed = a.ed + e0;
+            float n1, n2;
+            uint32_t nmeta;
+            switch (deg) {
+#define NRLDPC_ROW_CASE(D) case D: process_row<D>(c.base, ed, c.zoff, c.Z4, __uint_as_float(c.cur.x), __uint_as_float(c.cur.y), c.cur.z, a.alpha, n1, n2, nmeta); break;
+                NRLDPC_ROW_CASE(3) NRLDPC_ROW_CASE(4) NRLDPC_ROW_CASE(5) NRLDPC_ROW_CASE(6)
+                NRLDPC_ROW_CASE(7) NRLDPC_ROW_CASE(8) NRLDPC_ROW_CASE(9) NRLDPC_ROW_CASE(10)
+                NRLDPC_ROW_CASE(19)
+#undef NRLDPC_ROW_CASE
+                default: n1 = 0.f; n2 = 0.f; nmeta = 0; break;
+            }
+            if (store_rec) __stcg(r == 0 ? c.rec0 : rp, make_uint4(__float_as_uint(n1), __float_as_uint(n2), nmeta, 0u));
+        }
+        c.cur = nxt;
+        rp = np;
+        __syncthreads();
+    }
+}
+
+// ---- one full iteration over the layers: fully unrolled for base graph BG -----------------------
+template <int BG, int R>
+struct UnrolledRows {
+    static __device__ __forceinline__ void run(const DecArgs &a, DecCtx &c, const bool first, const bool store_rec) {
+        if (R >= a.n_rows) return;
+        constexpr int DEG = BgShape<BG>::deg(R);
+        constexpr int E0 = BgShape<BG>::start(R);
+        // slot R+1 (slot n_rows holds layer 0: see iteration_looped)
+        const bool ld = (R + 1 == a.n_rows) ? store_rec : !first;
+        uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+        if (ld && !c.done) nxt = __ldcg(c.my_rec + (size_t)(R + 1) * c.rec_stride);
+        if (!c.done) {
+            float n1, n2;
+            uint32_t nmeta;
+            process_row<DEG>(c.base, a.ed + E0, c.zoff, c.Z4, __uint_as_float(c.cur.x), __uint_as_float(c.cur.y),
+                             c.cur.z, a.alpha, n1, n2, nmeta);
+            if (store_rec)
+                __stcg(c.my_rec + (size_t)(R == 0 ? a.n_rows : R) * c.rec_stride,
+                       make_uint4(__float_as_uint(n1), __float_as_uint(n2), nmeta, 0u));
+        }
+        c.cur = nxt;
+        __syncthreads();
+        UnrolledRows<BG, R + 1>::run(a, c, first, store_rec);
+    }
+};
+template <int BG>
+struct UnrolledRows<BG, BgShape<BG>::kRows> {
+    static __device__ __forceinline__ void run(const DecArgs &, DecCtx &, bool, bool) {}
+};
+
+// BG = 0: generic looped variant; BG = 1 / 2: layer loop unrolled for that base graph.
+template <int BG>
 __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(const __grid_constant__ DecArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Z = a.Z;
@@ -122,12 +260,16 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
     const int slot = tid / Z;
     const int z = tid - slot * Z;
     const bool lane_ok = tid < a.cwpc * Z;
-    const uint32_t Z4 = (uint32_t)Z * 4u;
-
     const long long n_groups = (a.batch + a.cwpc - 1) / a.cwpc;
-    const size_t rec_stride = blockDim.x;
-    uint4 *my_rec = a.c2v + (size_t)blockIdx.x * a.n_rows * rec_stride + tid;
     const bool want_ok = a.ok != nullptr;
+
+    DecCtx c;
+    c.Z4 = (uint32_t)Z * 4u;
+    c.zoff = (uint32_t)z * 4u;
+    c.base = (uint32_t)__cvta_generic_to_shared(app + (size_t)slot * ncw);
+    c.rec_stride = blockDim.x;
+    c.my_rec = a.c2v + (size_t)blockIdx.x * (a.n_rows + 1) * c.rec_stride + tid;
+    c.rec0 = c.my_rec + (size_t)a.n_rows * c.rec_stride;
 
     while (true) {
         __syncthreads();  // previous group's outputs are out of smem
@@ -138,102 +280,37 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
         const long long cw0 = group * a.cwpc;
         const int n_here = (int)min((long long)a.cwpc, a.batch - cw0);
 
-        // ---- load + clamp: the group's codewords are contiguous in HBM -----------------------
-        {
-            const float4 *src = reinterpret_cast<const float4 *>(a.llr + cw0 * ncw);
-            float4 *dst = reinterpret_cast<float4 *>(app);
-            const int n4 = (n_here * ncw) >> 2;  // ncw*4 bytes is a multiple of 16 for every (BG,Z)
-            for (int i = tid; i < n4; i += blockDim.x) {
-                float4 v = __ldcs(src + i);
-                v.x = clamp_llr(v.x); v.y = clamp_llr(v.y); v.z = clamp_llr(v.z); v.w = clamp_llr(v.w);
-                dst[i] = v;
-            }
-        }
+        load_group(a, app, cw0, n_here, ncw);
         if (tid < a.cwpc) s_flag[tid] = 0;
         __syncthreads();
 
         const bool active = lane_ok && slot < n_here;
-        float *my_app = app + (size_t)slot * ncw;
-        const uint32_t base = (uint32_t)__cvta_generic_to_shared(my_app);
-        const uint32_t zoff = (uint32_t)z * 4u;
-        bool done = !active;
+        c.done = !active;
+        c.cur = make_uint4(0u, 0u, 0u, 0u);
         int my_iters = 0;
         int my_ok = 0;
-        uint4 cur = make_uint4(0u, 0u, 0u, 0u);
 
         for (int it = 0; it < a.max_iters; ++it) {
-            const bool store_rec = it + 1 < a.max_iters;
-            for (int r = 0; r < a.n_rows; ++r) {
-                // software prefetch of the next layer's record (it wraps into the next iteration)
-                int rn = r + 1, itn = it;
-                if (rn == a.n_rows) { rn = 0; itn = it + 1; }
-                uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
-                if (!done && itn > 0 && itn < a.max_iters) nxt = __ldcg(my_rec + (size_t)rn * rec_stride);
-                if (!done) {
-                    const int e0 = a.row_start[r];
-                    const int deg = a.row_start[r + 1] - e0;
-                    const uint2 *ed = a.ed + e0;
-                    float n1, n2;
-                    uint32_t nmeta;
-                    switch (deg) {
-#define NRLDPC_ROW_CASE(D) case D: process_row<D>(base, ed, zoff, Z4, __uint_as_float(cur.x), __uint_as_float(cur.y), cur.z, a.alpha, n1, n2, nmeta); break;
-                        NRLDPC_ROW_CASE(3) NRLDPC_ROW_CASE(4) NRLDPC_ROW_CASE(5) NRLDPC_ROW_CASE(6)
-                        NRLDPC_ROW_CASE(7) NRLDPC_ROW_CASE(8) NRLDPC_ROW_CASE(9) NRLDPC_ROW_CASE(10)
-                        NRLDPC_ROW_CASE(19)
-#undef NRLDPC_ROW_CASE
-                        default: n1 = 0.f; n2 = 0.f; nmeta = 0; break;
-                    }
-                    if (store_rec)
-                        __stcg(my_rec + (size_t)r * rec_stride, make_uint4(__float_as_uint(n1), __float_as_uint(n2), nmeta, 0u));
-                }
-                cur = nxt;
-                __syncthreads();
-            }
-            if (!done) my_iters = it + 1;
+            if (BG == 0) iteration_looped(a, c, it);
+            else UnrolledRows<(BG == 0 ? 1 : BG), 0>::run(a, c, it == 0, it + 1 < a.max_iters);
+
+            if (!c.done) my_iters = it + 1;
             const bool last = it + 1 == a.max_iters;
             if (a.early_term || (want_ok && last)) {
-                // exact syndrome of hard = (app < 0) over the active rows ('Parity check satisfied',
-                // NRLDPCDecoder.m:120)
-                if (!done) {
-                    int fail = 0;
-                    for (int r = 0; r < a.n_rows; ++r) {
-                        int par = 0;
-                        for (int e = a.row_start[r]; e < a.row_start[r + 1]; ++e) {
-                            const uint2 d = a.ed[e];
-                            const uint32_t u = zoff + d.x;
-                            const uint32_t ad = base + d.y + min(u, u - Z4);
-                            float x;
-                            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(ad));
-                            par ^= (x < 0.0f) ? 1 : 0;
-                        }
-                        fail |= par;
-                    }
-                    if (fail) s_flag[slot] = 1;
-                }
+                if (!c.done && syndrome_fail(a, c)) s_flag[slot] = 1;
                 __syncthreads();
-                if (!done) {
+                if (!c.done) {
                     my_ok = s_flag[slot] ? 0 : 1;
-                    if (my_ok && a.early_term) done = true;
+                    if (my_ok && a.early_term) c.done = true;
                 }
-                const int all_done = __syncthreads_and(done ? 1 : 0);  // also orders the flag reset below
+                const int all_done = __syncthreads_and(c.done ? 1 : 0);  // also orders the flag reset below
                 if (tid < a.cwpc) s_flag[tid] = 0;
                 if (a.early_term && all_done) break;
             }
         }
         __syncthreads();
 
-        // ---- outputs --------------------------------------------------------------------------
-        for (int s = 0; s < n_here; ++s) {
-            const float *src = app + (size_t)s * ncw;
-            uint8_t *dst = a.hard + (cw0 + s) * K;
-            for (int k = tid; k < K; k += blockDim.x) dst[k] = src[k] < 0.0f ? 1 : 0;
-        }
-        if (a.soft) {
-            float4 *dst = reinterpret_cast<float4 *>(a.soft + cw0 * ncw);
-            const float4 *src = reinterpret_cast<const float4 *>(app);
-            const int n4 = (n_here * ncw) >> 2;
-            for (int i = tid; i < n4; i += blockDim.x) __stcs(dst + i, src[i]);
-        }
+        store_outputs(a, app, cw0, n_here, ncw, K);
         if (active && z == 0) {
             if (a.iters) a.iters[cw0 + slot] = my_iters;
             if (a.ok) a.ok[cw0 + slot] = (uint8_t)my_ok;

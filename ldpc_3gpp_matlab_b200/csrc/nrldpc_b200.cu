@@ -59,6 +59,7 @@ struct nrldpc_handle {
     int enc_delta = 0;
     PipeSlot pipe[kNumPipe];
     int dec_smem_optin = 0;
+    int dec_variant = 1;             // NRLDPC_DECODE_VARIANT=loop selects the generic looped kernel
     nrldpc::DecArgs dec_args;
     cudaEvent_t dev_done = nullptr;  // last NRLDPC_MEM_DEVICE launch that used pipe[0]'s scratch
 };
@@ -132,11 +133,15 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
     const int64_t n_groups = (batch + cwpc - 1) / cwpc;
     const int grid = (int)std::min<int64_t>(n_groups, (int64_t)h->num_sms * nrldpc::kDecCtasPerSm);
     const size_t smem = decode_smem_bytes(h, n_rows);
+    // variant 0: generic looped layers; 1/2: layer loop unrolled for that base graph (default)
+    using Kern = void (*)(const nrldpc::DecArgs);
+    const Kern kern = h->dec_variant == 0 ? (Kern)nrldpc::decode_nms_kernel<0>
+                      : (h->d.bg == 1 ? (Kern)nrldpc::decode_nms_kernel<1> : (Kern)nrldpc::decode_nms_kernel<2>);
     if ((int)smem > h->dec_smem_optin) {
-        CUDA_TRY(h, cudaFuncSetAttribute(nrldpc::decode_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         h->dec_smem_optin = (int)smem;
     }
-    if (int rc = ensure_scratch(h, s, (size_t)grid * n_rows * threads)) return rc;
+    if (int rc = ensure_scratch(h, s, (size_t)grid * (n_rows + 1) * threads)) return rc;
     CUDA_TRY(h, cudaMemsetAsync(s.counter, 0, sizeof(int), stream));
     nrldpc::DecArgs &a = h->dec_args;  // tables were filled at create()
     a.llr = llr; a.hard = hard; a.soft = soft; a.iters = iters; a.ok = ok;
@@ -144,7 +149,7 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
     a.n_edges = h->h_row_start[n_rows]; a.max_iters = h->cfg.max_iters; a.early_term = h->cfg.early_term;
     a.cwpc = cwpc; a.alpha = h->cfg.alpha;
     a.c2v = s.c2v; a.work_counter = s.counter;
-    nrldpc::decode_nms_kernel<<<grid, threads, smem, stream>>>(a);
+    kern<<<grid, threads, smem, stream>>>(a);
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
     return 0;
@@ -288,6 +293,7 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
         return fail(nullptr, NRLDPC_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
     }
     h->num_sms = prop.multiProcessorCount;
+    if (const char *v = getenv("NRLDPC_DECODE_VARIANT")) h->dec_variant = strcmp(v, "loop") == 0 ? 0 : 1;
 
     const BgView v = bg_view(cfg->bg);
     const int Z = cfg->Z;
