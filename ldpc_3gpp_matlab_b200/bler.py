@@ -1,0 +1,189 @@
+"""Device-resident BLER-vs-SNR Monte-Carlo loop: the protocol of plot_BLER_vs_SNR.m:104-171 with the
+frame loop (:116) turned into batches that never leave the GPU.
+
+Per batch: random information blocks -> LDPC encode -> rate match (bit selection + interleave) ->
+QPSK + AWGN + exact LLR -> rate recover (+HARQ combine over the rv_id sequence, :124-137) -> decode
+-> block-error count, every stage a C-ABI call on device pointers.  Batches shard across ranks
+(one process per GPU, independent random streams per rank as the reference asks at :23-27); the only
+collective is a sum of four counters per SNR point.
+
+Block-error criterion.  The reference counts ~isequal(a, a_hat) with a_hat = [] whenever the TB CRC
+or a CB CRC fails (NRLDPCDecoder.m:337-339, plot_BLER_vs_SNR.m:146).  Any wrong bit among the K'
+payload+CRC bits of any code block makes a CRC fail or the payload differ, and no wrong bit means
+both pass, so "block error <=> some code block has an error in its first K' decoded bits" is the same
+event; it is evaluated on device without materialising the CRCs.  The K' bits are drawn uniformly
+(the code is linear and the channel symmetric, so BLER does not depend on the transmitted word);
+the host-side NRLDPCEncoder/NRLDPCDecoder mirrors do attach and check the real CRCs.
+
+Results are written in the reference's file format ("%f\\t%e\\n" per SNR point, :165) so curves can be
+overlaid file for file.
+"""
+from __future__ import annotations
+
+import argparse
+import math
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+
+from . import capi, dist as D
+from .nrldpc import NRLDPC, matlab_round
+
+
+def active_rows(p: NRLDPC, E_max: int, rv_ids) -> int:
+    """Base rows that can carry information for this rate-matching configuration (see nrldpc.NRLDPCDecoder)."""
+    Z, kcols, rows_all = p.Z_c, (22 if p.BG == 1 else 10), (46 if p.BG == 1 else 42)
+    nfill = max(0, p.K - max(p.K_prime, 2 * Z))
+    hi = 0
+    for rv in rv_ids:
+        p.rv_id = rv
+        span = p.k_0 + E_max + nfill
+        hi = max(hi, p.N_cb if span >= p.N_cb else span)
+    return int(min(rows_all, max(4, -(-(hi + 2 * Z) // Z) - kcols)))
+
+
+class BlerSimulator:
+    def __init__(self, A, R, BG, Q_m=2, rv_id_sequence=(0,), iterations=8, early_termination=True, alpha=0.75,
+                 batch=4096, seed=0, device=0, rank=0, world=1):
+        import torch
+        if Q_m != 2:
+            raise capi.UnsupportedParameters("the on-device channel leg implements QPSK only (Q_m = 2)")
+        self.torch = torch
+        self.p = NRLDPC(A=A, BG=BG, G=matlab_round(A / R / Q_m) * Q_m, Q_m=Q_m)  # plot_BLER_vs_SNR.m:94
+        self.p.validate_properties()
+        p = self.p
+        self.rvs = tuple(int(r) for r in rv_id_sequence)
+        self.C, self.K, self.Kp, self.Z, self.N = p.C, p.K, p.K_prime, p.Z_c, p.N
+        self.E_r = [int(e) for e in p.E_r]
+        self.n_rows = active_rows(p, max(self.E_r), self.rvs)
+        p.rv_id = 0
+        self.h = capi.Handle(BG, self.Z, iterations, early_termination, alpha, device=device)
+        self.B = int(batch)
+        self.rank, self.world, self.seed = rank, world, seed
+        self.gen = torch.Generator(device="cuda").manual_seed(D.rank_seed(seed, rank) & 0x7FFFFFFFFFFF)
+        self.stream_id = 0
+        dev = "cuda"
+        n = self.B * self.C
+        self.info = torch.zeros((n, self.K), dtype=torch.uint8, device=dev)
+        self.cw = torch.empty((n, self.h.n_cw), dtype=torch.uint8, device=dev)
+        self.llr = torch.empty((n, self.h.n_cw), dtype=torch.float32, device=dev)
+        self.hard = torch.empty((n, self.K), dtype=torch.uint8, device=dev)
+        self.iters = torch.empty(n, dtype=torch.int32, device=dev)
+        self.harq = torch.zeros((n, self.N), dtype=torch.float32, device=dev) if len(self.rvs) > 1 else None
+        Emax = max(self.E_r)
+        self.f = torch.empty((self.B, Emax), dtype=torch.uint8, device=dev)
+        self.fl = torch.empty((self.B, Emax), dtype=torch.float32, device=dev)
+
+    def close(self):
+        self.h.close()
+
+    def run_batch(self, esn0_db: float):
+        """One batch of B transport blocks at Es/N0.  Returns [blocks, block_errors, bit_errors, iterations]."""
+        torch, h, B, C = self.torch, self.h, self.B, self.C
+        st = torch.cuda.current_stream().cuda_stream
+        var = 10 ** (-esn0_db / 10)                      # plot_BLER_vs_SNR.m:105-106
+        self.info[:, :self.Kp] = torch.randint(0, 2, (B * C, self.Kp), dtype=torch.uint8, device="cuda", generator=self.gen)
+        h.encode_raw(self.info, B * C, self.cw, mem=capi.MEM_DEVICE, stream=st)
+        if self.harq is not None:
+            self.harq.zero_()                            # reset(hDec), plot_BLER_vs_SNR.m:122
+        ok_latched = torch.zeros(B, dtype=torch.bool, device="cuda")
+        iters_total = 0
+        # code blocks are interleaved frame-major: block r of frame b sits at row b*C + r
+        cw3 = self.cw.view(B, C, -1)
+        llr3 = self.llr.view(B, C, -1)
+        harq3 = self.harq.view(B, C, -1) if self.harq is not None else None
+        for rv in self.rvs:                              # HARQ loop, :124-137
+            self.p.rv_id = rv
+            for r in range(C):
+                E = self.E_r[r]
+                rm = capi.Rm(E, int(self.p.k_0), int(self.p.N_cb), int(self.Kp), 2)
+                cw_r = cw3[:, r].contiguous() if C > 1 else self.cw
+                f, fl = self.f[:, :E], self.fl[:, :E]
+                if E != self.f.shape[1]:
+                    f, fl = f.contiguous(), fl.contiguous()
+                h.rate_match_raw(cw_r, B, rm, f, mem=capi.MEM_DEVICE, stream=st)
+                self.stream_id += 1
+                h.qpsk_awgn_llr_raw(f, B, E, var, D.rank_seed(self.seed, self.rank), self.stream_id, fl, stream=st)
+                if C > 1:
+                    llr_r = torch.empty((B, h.n_cw), dtype=torch.float32, device="cuda")
+                    hq = harq3[:, r].contiguous() if harq3 is not None else None
+                    h.rate_recover_raw(fl, B, rm, hq, llr_r, mem=capi.MEM_DEVICE, stream=st)
+                    llr3[:, r] = llr_r
+                    if hq is not None:
+                        harq3[:, r] = hq
+                else:
+                    h.rate_recover_raw(fl, B, rm, self.harq, self.llr, mem=capi.MEM_DEVICE, stream=st)
+            h.decode_raw(self.llr, B * C, self.hard, iters=self.iters, n_rows=self.n_rows, mem=capi.MEM_DEVICE, stream=st)
+            cb_ok = (self.hard[:, :self.Kp] == self.info[:, :self.Kp]).all(dim=1).view(B, C).all(dim=1)
+            iters_total += int(self.iters.sum())
+            ok_latched |= cb_ok
+            if bool(ok_latched.all()):
+                break
+        bit_err = int(((self.hard[:, :self.Kp] != self.info[:, :self.Kp]).view(B, C, -1).sum(dim=(1, 2)) * (~ok_latched)).sum())
+        return np.array([B, int((~ok_latched).sum()), bit_err, iters_total], dtype=np.int64), bool(ok_latched.any())
+
+    def run_point(self, esn0_db, target_block_errors, max_blocks=None, found_start=True):
+        """Batches until `target_block_errors` errors were seen across all ranks (plot_BLER_vs_SNR.m:116)."""
+        tot = np.zeros(4, dtype=np.int64)
+        while True:
+            c, any_ok = self.run_batch(esn0_db)
+            c = D.sum_counters(c).numpy()
+            tot += c
+            if not found_start:
+                any_ok_all = bool(D.sum_counters([int(any_ok)])[0] > 0)
+                if not any_ok_all:          # start detection, :139-144: nothing decodes yet at this SNR
+                    return tot, False
+                found_start = True
+            if tot[1] >= target_block_errors or (max_blocks and tot[0] >= max_blocks):
+                return tot, True
+
+
+def sweep(A, R, BG, iterations=8, target_block_errors=100, target_BLER=1e-3, EsN0_start=0.0, EsN0_delta=0.5, seed=0,
+          rv_id_sequence=(0,), batch=4096, max_blocks=None, early_termination=True, out_dir="results", log=print):
+    """plot_BLER_vs_SNR.m:53-171 for one (A, R, BG): returns [(EsN0, BLER, blocks, errors, mean_iters)]."""
+    rank, local_rank, world = D.init()
+    import torch
+    torch.cuda.set_device(local_rank)
+    sim = BlerSimulator(A, R, BG, 2, rv_id_sequence, iterations, early_termination, 0.75, batch, seed, local_rank, rank, world)
+    rows, esn0, bler, found = [], float(EsN0_start), 1.0, False
+    fid = None
+    if rank == 0 and out_dir:
+        Path(out_dir).mkdir(parents=True, exist_ok=True)
+        name = f"BLER_vs_SNR_{A}_{R:g}_{BG}_QPSK_{iterations}_{target_block_errors}_{EsN0_start:g}_{seed}.txt"  # :79
+        fid = open(Path(out_dir) / name, "w")
+    while bler > target_BLER:
+        tot, found = sim.run_point(esn0, target_block_errors, max_blocks, found)
+        bler = tot[1] / tot[0] if found else 1.0
+        if found and bler < 1 and rank == 0:
+            if fid:
+                fid.write("%f\t%e\n" % (esn0, bler))                                                  # :165
+                fid.flush()
+            rows.append((esn0, bler, int(tot[0]), int(tot[1]), tot[3] / max(1, tot[0] * sim.C)))
+            log(f"EsN0 {esn0:6.2f} dB  BLER {bler:.3e}  blocks {tot[0]}  errors {tot[1]}  mean iters {rows[-1][4]:.2f}")
+        if max_blocks and found and tot[1] == 0:
+            break
+        esn0 += EsN0_delta                                                                           # :169
+    if fid:
+        fid.close()
+    sim.close()
+    return rows
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description="BLER vs SNR on device (protocol of plot_BLER_vs_SNR.m)")
+    ap.add_argument("--A", type=int, default=3842); ap.add_argument("--R", type=float, default=1 / 3)
+    ap.add_argument("--BG", type=int, default=2); ap.add_argument("--iterations", type=int, default=8)
+    ap.add_argument("--target-block-errors", type=int, default=100); ap.add_argument("--target-BLER", type=float, default=1e-3)
+    ap.add_argument("--EsN0-start", type=float, default=0.0); ap.add_argument("--EsN0-delta", type=float, default=0.5)
+    ap.add_argument("--seed", type=int, default=0); ap.add_argument("--rv", type=int, nargs="+", default=[0])
+    ap.add_argument("--batch", type=int, default=4096); ap.add_argument("--max-blocks", type=int, default=None)
+    ap.add_argument("--out-dir", default="results")
+    a = ap.parse_args(argv)
+    sweep(a.A, a.R, a.BG, a.iterations, a.target_block_errors, a.target_BLER, a.EsN0_start, a.EsN0_delta, a.seed, a.rv,
+          a.batch, a.max_blocks, True, a.out_dir)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,96 @@
+// nrldpc_mex.cpp -- thin MEX gateway over the C ABI (include/nrldpc_b200.h).
+//
+// UNVERIFIED: this image has no MATLAB and no mex.h, so this file is shipped as source only and has
+// never been compiled.  It is deliberately trivial: every behaviour lives behind the C ABI, which is
+// what the test-suite exercises.  Build (on a machine with MATLAB + CUDA):
+//     mex -I../include nrldpc_mex.cpp -L../ldpc_3gpp_matlab_b200 -lnrldpc_b200
+//
+// Usage from MATLAB (see B200LDPCDecoder.m / B200LDPCEncoder.m):
+//     h     = nrldpc_mex('create', BG, Z, max_iters, early_term, alpha);
+//     c_hat = nrldpc_mex('decode', h, cw_tilde, n_rows);   % cw_tilde: (68Z or 52Z) x batch double, +inf = filler
+//     cw    = nrldpc_mex('encode', h, c);                  % c: K x batch, values 0/1
+//     nrldpc_mex('destroy', h);
+// Error codes are mapped onto the reference's identifiers: NRLDPC_EUNSUPPORTED ->
+// 'ldpc_3gpp_matlab:UnsupportedParameters' (callers catch and skip, plot_BLER_vs_SNR.m:172-176),
+// everything else -> 'ldpc_3gpp_matlab:Error'.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mex.h"
+#include "nrldpc_b200.h"
+
+static void check(int rc, const nrldpc_t *h) {
+    if (rc == NRLDPC_OK) return;
+    const char *msg = nrldpc_last_error(h);
+    if (rc == NRLDPC_EUNSUPPORTED) mexErrMsgIdAndTxt("ldpc_3gpp_matlab:UnsupportedParameters", "%s", msg);
+    mexErrMsgIdAndTxt("ldpc_3gpp_matlab:Error", "%s (nrldpc rc=%d)", msg, rc);
+}
+
+static nrldpc_t *handle_of(const mxArray *a) {
+    if (!mxIsUint64(a) || mxGetNumberOfElements(a) != 1) mexErrMsgIdAndTxt("ldpc_3gpp_matlab:Error", "bad handle");
+    return reinterpret_cast<nrldpc_t *>(*static_cast<uint64_t *>(mxGetData(a)));
+}
+
+void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
+    if (nrhs < 1 || !mxIsChar(prhs[0])) mexErrMsgIdAndTxt("ldpc_3gpp_matlab:Error", "first argument must be a command string");
+    char cmd[32];
+    mxGetString(prhs[0], cmd, sizeof(cmd));
+
+    if (!strcmp(cmd, "create")) {
+        nrldpc_cfg cfg{};
+        cfg.bg = (int32_t)mxGetScalar(prhs[1]);
+        cfg.Z = (int32_t)mxGetScalar(prhs[2]);
+        cfg.max_iters = (int32_t)mxGetScalar(prhs[3]);
+        cfg.early_term = (int32_t)mxGetScalar(prhs[4]);
+        cfg.alpha = nrhs > 5 ? (float)mxGetScalar(prhs[5]) : 0.75f;
+        cfg.device = -1;
+        nrldpc_t *h = nullptr;
+        check(nrldpc_create(&h, &cfg), nullptr);
+        plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
+        *static_cast<uint64_t *>(mxGetData(plhs[0])) = reinterpret_cast<uint64_t>(h);
+        return;
+    }
+    if (!strcmp(cmd, "destroy")) {
+        nrldpc_destroy(handle_of(prhs[1]));
+        return;
+    }
+    nrldpc_t *h = handle_of(prhs[1]);
+    nrldpc_dims d;
+    nrldpc_get_dims(h, &d);
+
+    if (!strcmp(cmd, "decode")) {
+        // MATLAB passes a column-major (n_cw x batch) double matrix: each column is one cw_tilde
+        // (NRLDPCDecoder.m:262-264), i.e. exactly the row-major [batch][n_cw] layout of the C ABI.
+        const mxArray *in = prhs[2];
+        if (!mxIsDouble(in) || (int)mxGetM(in) != d.n_cw)
+            mexErrMsgIdAndTxt("ldpc_3gpp_matlab:Error", "cw_tilde should have %d rows.", d.n_cw);
+        const int64_t batch = (int64_t)mxGetN(in);
+        const int n_rows = nrhs > 3 ? (int)mxGetScalar(prhs[3]) : 0;
+        const double *x = mxGetPr(in);
+        std::vector<float> llr((size_t)batch * d.n_cw);
+        for (size_t i = 0; i < llr.size(); ++i) llr[i] = (float)x[i];  // +inf stays +inf; NaN = filler too
+        std::vector<uint8_t> hard((size_t)batch * d.K);
+        check(nrldpc_decode(h, llr.data(), batch, n_rows, hard.data(), nullptr, nullptr, nullptr, NRLDPC_MEM_HOST, nullptr), h);
+        plhs[0] = mxCreateLogicalMatrix(d.K, batch);  // comm.LDPCDecoder returns logical K x 1 (NRLDPCDecoder.m:265)
+        mxLogical *o = mxGetLogicals(plhs[0]);
+        for (size_t i = 0; i < hard.size(); ++i) o[i] = hard[i] != 0;
+        return;
+    }
+    if (!strcmp(cmd, "encode")) {
+        const mxArray *in = prhs[2];
+        if ((int)mxGetM(in) != d.K) mexErrMsgIdAndTxt("ldpc_3gpp_matlab:Error", "c should have K=%d rows.", d.K);
+        const int64_t batch = (int64_t)mxGetN(in);
+        std::vector<uint8_t> info((size_t)batch * d.K), cw((size_t)batch * d.n_cw);
+        if (mxIsDouble(in)) { const double *x = mxGetPr(in); for (size_t i = 0; i < info.size(); ++i) info[i] = x[i] != 0.0; }
+        else if (mxIsLogical(in)) { const mxLogical *x = mxGetLogicals(in); for (size_t i = 0; i < info.size(); ++i) info[i] = x[i]; }
+        else mexErrMsgIdAndTxt("ldpc_3gpp_matlab:Error", "c must be double or logical.");
+        check(nrldpc_encode(h, info.data(), batch, cw.data(), NRLDPC_MEM_HOST, nullptr), h);
+        plhs[0] = mxCreateDoubleMatrix(d.n_cw, batch, mxREAL);  // comm.LDPCEncoder keeps the input type (NRLDPCEncoder.m:158)
+        double *o = mxGetPr(plhs[0]);
+        for (size_t i = 0; i < cw.size(); ++i) o[i] = cw[i];
+        return;
+    }
+    mexErrMsgIdAndTxt("ldpc_3gpp_matlab:Error", "unknown command '%s'", cmd);
+}

@@ -1,0 +1,53 @@
+#!/usr/bin/env python3
+"""BLER-vs-SNR overlay on identical noise: CUDA engine vs oracle A (same algorithm: must be IDENTICAL counts)
+vs oracle B (the reference's flooding sum-product f64: reported as a dB delta).  GPU box only.
+Writes gpurun_out/bler_overlay.txt (copied to profiles/ by hand)."""
+import sys, json, time
+sys.path.insert(0, '.')
+import numpy as np
+from ldpc_3gpp_matlab_b200.bler import BlerSimulator
+from oracle import oracle as O
+
+def interp_db(rows, target, col):
+    xs = [r[0] for r in rows]; ys = [max(r[col], 1e-9) for r in rows]
+    for (x0, y0), (x1, y1) in zip(zip(xs, ys), zip(xs[1:], ys[1:])):
+        if y0 >= target >= y1 and y0 != y1:
+            return x0 + (x1 - x0) * (np.log10(y0) - np.log10(target)) / (np.log10(y0) - np.log10(y1))
+    return None
+
+out = []
+for name, A, R, BG, snrs, nbatch, B in (("cfgP_bg2_A20_r15", 20, 0.2, 2, np.arange(0.0, 4.01, 0.5), 12, 8192),
+                                       ("cfgS_bg2_A400_r15", 400, 0.2, 2, np.arange(-3.5, -1.49, 0.25), 2, 4096)):
+    sim = BlerSimulator(A, R, BG, iterations=8, early_termination=True, batch=B, seed=1)
+    rows = []
+    for s in snrs:
+        e_gpu = e_a = e_b = n = 0
+        for _ in range(nbatch):
+            sim.run_batch(float(s))
+            llr = sim.llr.cpu().numpy(); info = sim.info.cpu().numpy(); hard = sim.hard.cpu().numpy()
+            Kp = sim.Kp
+            e_gpu += int((hard[:, :Kp] != info[:, :Kp]).any(1).sum())
+            ra = O.decode_nms(BG, sim.Z, llr, 8, early_term=True, n_rows=sim.n_rows, want_app=False)
+            e_a += int((ra["hard"][:, :Kp] != info[:, :Kp]).any(1).sum())
+            assert (ra["hard"] == hard).all(), "CUDA and oracle A differ on identical LLRs"
+            rb = O.decode_bp(BG, sim.Z, llr, 8)
+            e_b += int((rb["hard"][:, :Kp] != info[:, :Kp]).any(1).sum())
+            n += B
+        rows.append((float(s), e_gpu / n, e_a / n, e_b / n, n))
+        print(name, rows[-1], flush=True)
+    d = {"config": name, "rows": rows}
+    for tgt in (1e-1, 1e-2):
+        g, b = interp_db(rows, tgt, 1), interp_db(rows, tgt, 3)
+        d[f"esn0_at_bler_{tgt:g}"] = {"cuda_layered_nms": g, "oracleB_flooding_bp": b, "delta_db": (b - g) if g is not None and b is not None else None}
+    out.append(d)
+    sim.close()
+txt = ["# BLER on identical noise, 8 iterations, early termination: columns EsN0_dB, BLER(CUDA), BLER(oracle A), BLER(oracle B), blocks"]
+for d in out:
+    txt.append(f"## {d['config']}")
+    for r in d["rows"]:
+        txt.append("%6.2f\t%.4e\t%.4e\t%.4e\t%d" % r)
+    for k, v in d.items():
+        if k.startswith("esn0_at"):
+            txt.append(f"{k}: {json.dumps(v)}")
+open("gpurun_out/bler_overlay.txt", "w").write("\n".join(txt) + "\n")
+print("\n".join(txt))
