@@ -13,15 +13,22 @@
 //     memory for all iterations; two CTAs fit per SM so one CTA's barriers/loads hide under the
 //     other's arithmetic;
 //   * check-to-variable messages are kept compressed (alpha*min1, alpha*min2, argmin, sign bits)
-//     as one 16-byte record per check in a per-CTA global scratch that stays L2-resident,
-//     software-prefetched one layer ahead; the first iteration reads nothing and the last writes
-//     nothing;
-//   * the base graph's shape (row degrees, edge order) is a compile-time constant per base graph:
-//     the layer loop is fully unrolled, and the per-edge shift / column offsets are read straight
-//     from the kernel-parameter constant bank as instruction operands (no descriptor loads);
+//     as one 16-byte record per check in a per-CTA global scratch that is pinned in L2
+//     (evict_last cache policy), software-prefetched one layer ahead; the first iteration reads
+//     nothing and the last writes nothing;
+//   * the base graph's shape (row degrees, edge order, identity extension columns) is a
+//     compile-time constant per base graph: the layer loop is fully unrolled, and the per-edge
+//     offsets / wrap thresholds are read straight from the kernel-parameter constant bank as
+//     instruction operands (no descriptor loads);
 //   * arithmetic is float32 with every add/mul individually rounded (__fsub_rn/__fmul_rn/__fadd_rn:
 //     no FMA contraction), signs handled as sign BITS, so results are bit-identical to the CPU
 //     oracle (oracle/nrldpc_oracle.c, function orc_decode_nms).
+//
+// The kernel is bound by the SM's ALU pipe (integer / logic / min-max / select instructions), not
+// by HBM, so the row update is written to minimise ALU-pipe instructions:
+// address arithmetic is issued as IMAD (FMA pipe) around one unsigned min for the circulant wrap,
+// the arg-min index is not tracked while scanning (the second pass finds it by value), sign bits
+// are gathered with funnel shifts.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -33,10 +40,13 @@ constexpr int kDecCtasPerSm = 2;
 constexpr float kLlrMax = 1048576.0f;
 constexpr int kMaxEdges = 316;
 constexpr int kMaxRows = 46;
+constexpr int kRecStride = kDecThreads;  // records per layer slot in the c2v scratch (fixed: immediate offsets)
 
 // Edge descriptor, read from the kernel-parameter constant bank:
-//   x = shift*4   (bytes): lane z reads circulant position (z + shift) mod Z
-//   y = col*Z*4   (bytes): start of the block column inside one codeword's APP array
+//   x = shift*4               (bytes): lane z reads circulant position (z + shift) mod Z
+//   y = smem_base + col*Z*4   (bytes): shared-window address of the block column inside the CTA's first
+//                                      APP array (smem_base = shared address of the dynamic shared memory,
+//                                      probed once per handle; the kernel traps if it ever differs)
 struct DecArgs {
     const float *llr;        // [batch][ncw]
     uint8_t *hard;           // [batch][K]
@@ -46,7 +56,10 @@ struct DecArgs {
     long long batch;
     int Z, ncols, kcols, n_rows, n_edges, max_iters, early_term, cwpc;
     float alpha;
-    uint4 *c2v;              // [grid][n_rows+1][blockDim] {alpha*min1, alpha*min2, argmin | signbits << 5, -}
+    int l2_pin;              // 1: c2v scratch accesses carry an L2 evict_last policy
+    int one;                 // = 1 (see mad_u32)
+    uint32_t smem_base;      // shared-window address of the kernel's dynamic shared memory
+    uint4 *c2v;              // [grid][n_rows+1][kRecStride] {alpha*min1|sgn, alpha*min2|sgn, argmin | signbits << 5, -}
     int *work_counter;
     unsigned short row_start[kMaxRows + 2];
     uint2 ed[kMaxEdges];
@@ -78,37 +91,101 @@ __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
 
-// One check row of degree DEG for check z.  `base` = byte address (shared window) of this thread's
-// codeword's APP array, zoff = z*4; (om1, om2, ometa) is the compressed message record written
-// for this check in the previous iteration (zeros in the first).
-// Sign bits of the messages are kept MSB-first: edge e sits at bit (DEG-1-e) of the sign field.
-template <int DEG>
-__device__ __forceinline__ void process_row(const uint32_t base, const uint2 *__restrict__ ed, const uint32_t zoff,
-                                            const uint32_t Z4, const float om1, const float om2,
-                                            const uint32_t ometa, const float alpha, float &nm1,
-                                            float &nm2, uint32_t &nmeta) {
+// c2v scratch accesses: L1-bypassing, with an L2 cache policy (evict_last pins the scratch in L2 so
+// that the streamed LLR input cannot push dirty records out to HBM).
+__device__ __forceinline__ uint64_t make_l2_policy(int pin) {
+    uint64_t p;
+    if (pin) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint4 ld_rec(const uint4 *p, uint64_t pol) {
+    uint4 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_rec(uint4 *p, uint4 v, uint64_t pol) {
+    asm volatile("st.global.cg.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
+                 ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+
+// Integer multiply-add whose multiplier is the kernel parameter `one` (always 1): the compiler
+// cannot fold it, so it is emitted as IMAD, which issues on the FMA pipe -- address arithmetic
+// stays off the saturated ALU pipe.
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t one, uint32_t b) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(one), "r"(b));
+    return d;
+}
+
+// (a & ~m) | (b & m) in one LOP3
+__device__ __forceinline__ uint32_t bitselect(uint32_t a, uint32_t b, uint32_t m) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+    return d;
+}
+
+// Per-thread addressing state.
+//   zoff  = z*4                        lane position inside a circulant, bytes
+//   nZ4   = -(Z*4)                     (two's complement)
+//   slot_off = byte offset of this thread's codeword's APP array inside the CTA's APP storage (0 when FULL)
+//   one   = 1, from the parameter bank
+struct Lane {
+    uint32_t zoff, nZ4, slot_off, one;
+};
+
+// Shared-memory address of the variable edge `d` connects to check z.
+//   u = (z + shift)*4 wraps at Z*4: min(u, u - Z*4) as unsigned (u - Z*4 underflows when u < Z*4)
+// ONE_CW: one codeword per CTA (slot_off = 0): the uniform d.y folds into the LDS/STS address operand.
+template <bool ONE_CW>
+__device__ __forceinline__ uint32_t edge_addr(const Lane &l, const uint2 d, const bool ident = false) {
+    uint32_t m = l.zoff;
+    if (!ident) {
+        const uint32_t u = mad_u32(l.zoff, l.one, d.x);
+        const uint32_t w = mad_u32(u, l.one, l.nZ4);
+        m = min(u, w);
+    }
+    if (!ONE_CW) m = mad_u32(m, l.one, l.slot_off);
+    return m + d.y;
+}
+
+// One check row of degree DEG for check z.  (om1, om2, ometa) is the compressed message record
+// written for this check in the previous iteration: om1/om2 = alpha*min1, alpha*min2 (their sign
+// bits are ignored), ometa = arg-min index in bits 0..4 and the messages' sign bits MSB-first above
+// it (edge e at bit 5 + DEG-1-e).
+// In the first iteration the record is all zeros (previous messages +0: x - (+0) = x exactly).
+// IDENT_LAST: the row's last edge is an identity circulant (extension parity column, shift 0 for
+// every lifting-size set: TS 38.212 tables) -> no wrap.
+template <int DEG, bool IDENT_LAST, bool ONE_CW>
+__device__ __forceinline__ uint4 process_row(const Lane &l, const uint2 *__restrict__ ed, const uint32_t om1,
+                                             const uint32_t om2, const uint32_t ometa, const float alpha) {
     float t[DEG];
     uint32_t addr[DEG];
-    float m1 = __int_as_float(0x7f800000), m2 = __int_as_float(0x7f800000);
+    float m1 = 0.f, m2 = 0.f;
     uint32_t sx = 0, ts = 0;
-    int arg = 0;
-    const int oarg = (int)(ometa & 31u);
-    const uint32_t osg = ometa >> 5;
+    const uint32_t oarg = ometa & 31u;
 #pragma unroll
     for (int e = 0; e < DEG; ++e) {
         const uint2 d = ed[e];
-        const uint32_t u = zoff + d.x;                   // (z + shift)*4, wraps at Z*4:
-        const uint32_t a = base + d.y + min(u, u - Z4);  // u - Z4 underflows to a huge value when u < Z4
+        const uint32_t a = edge_addr<ONE_CW>(l, d, IDENT_LAST && e == DEG - 1);
         addr[e] = a;
         const float x = lds_f32(a);
-        const float mag = (e == oarg) ? om2 : om1;
-        const float c = __uint_as_float(__float_as_uint(mag) | ((osg << (31 - (DEG - 1 - e))) & 0x80000000u));
-        const float tt = __fsub_rn(x, c);
+        const uint32_t mag = (oarg == (uint32_t)e) ? om2 : om1;
+        // magnitude bits of the stored minimum, sign bit of edge e (meta bit 5 + DEG-1-e -> bit 31)
+        const uint32_t c = bitselect(mag, ometa << (26 - (DEG - 1 - e)), 0x80000000u);
+        const float tt = __fsub_rn(x, __uint_as_float(c));
         t[e] = tt;
         const float ab = fabsf(tt);
-        arg = (ab < m1) ? e : arg;
-        m2 = fminf(m2, fmaxf(ab, m1));
-        m1 = fminf(m1, ab);
+        if (e == 0) {
+            m1 = ab;
+        } else if (e == 1) {
+            m2 = fmaxf(m1, ab);
+            m1 = fminf(m1, ab);
+        } else {
+            m2 = fminf(m2, fmaxf(ab, m1));
+            m1 = fminf(m1, ab);
+        }
         sx ^= __float_as_uint(tt);
         ts = __funnelshift_l(__float_as_uint(tt), ts, 1);  // ts = ts << 1 | signbit(tt)
     }
@@ -117,27 +194,28 @@ __device__ __forceinline__ void process_row(const uint32_t base, const uint2 *__
     uint32_t m1ss = __float_as_uint(__fmul_rn(alpha, m1)) | sg;
     uint32_t m2ss = __float_as_uint(__fmul_rn(alpha, m2)) | sg;
     asm volatile("" : "+r"(m1ss), "+r"(m2ss));  // keep the sign folded per row, not re-derived per edge
+    uint32_t arg = 0;
 #pragma unroll
     for (int e = 0; e < DEG; ++e) {
-        const uint32_t sel = (e == arg) ? m2ss : m1ss;
+        // the arg-min edge is found by value: on a tie min2 == min1, so every tied edge gets the same message
+        const bool is_min = fabsf(t[e]) == m1;
+        const uint32_t sel = is_min ? m2ss : m1ss;
+        arg = is_min ? (uint32_t)e : arg;
         const float c = __uint_as_float(sel ^ (__float_as_uint(t[e]) & 0x80000000u));
         sts_f32(addr[e], __fadd_rn(t[e], c));
     }
-    nm1 = __uint_as_float(m1ss & 0x7fffffffu);
-    nm2 = __uint_as_float(m2ss & 0x7fffffffu);
     // sign of message e = sg ^ sign(t_e)
     const uint32_t csg = sg ? (ts ^ ((1u << DEG) - 1u)) : ts;
-    nmeta = (uint32_t)arg | (csg << 5);
+    return make_uint4(m1ss, m2ss, arg | (csg << 5), 0u);
 }
 
-// ---- pieces shared by both kernel variants -------------------------------------------------------
+// ---- pieces shared by all kernel variants --------------------------------------------------------
 struct DecCtx {
-    uint32_t base, zoff, Z4;
+    Lane l;
     uint4 *my_rec;   // slot 0 of this thread's record column
-    uint4 *rec0;     // slot n_rows: where layer 0's record lives
-    uint32_t rec_stride;
+    uint64_t pol;
     uint4 cur;
-    bool done;
+    bool done;       // this thread does no row work (inactive lane, or its codeword has converged)
 };
 
 __device__ __forceinline__ void load_group(const DecArgs &a, float *app, long long cw0, int n_here, int ncw) {
@@ -154,24 +232,37 @@ __device__ __forceinline__ void load_group(const DecArgs &a, float *app, long lo
 
 // exact syndrome of hard = (app < 0) over the active rows ('Parity check satisfied', NRLDPCDecoder.m:120)
 __device__ __forceinline__ int syndrome_fail(const DecArgs &a, const DecCtx &c) {
-    int fail = 0;
+    uint32_t fail = 0;
     for (int r = 0; r < a.n_rows; ++r) {
-        int par = 0;
+        uint32_t par = 0;
         for (int e = a.row_start[r]; e < a.row_start[r + 1]; ++e) {
             const uint2 d = a.ed[e];
-            const uint32_t u = c.zoff + d.x;
-            par ^= (lds_f32(c.base + d.y + min(u, u - c.Z4)) < 0.0f) ? 1 : 0;
+            par ^= __float_as_uint(lds_f32(edge_addr<false>(c.l, d)));
         }
         fail |= par;
     }
-    return fail;
+    return (int)(fail >> 31);
 }
 
 __device__ __forceinline__ void store_outputs(const DecArgs &a, const float *app, long long cw0, int n_here, int ncw, int K) {
-    for (int s = 0; s < n_here; ++s) {
-        const float *src = app + (size_t)s * ncw;
-        uint8_t *dst = a.hard + (cw0 + s) * K;
-        for (int k = threadIdx.x; k < K; k += blockDim.x) dst[k] = src[k] < 0.0f ? 1 : 0;
+    // hard decisions, four per 32-bit store (K = kcols*Z is a multiple of 4 for every even Z; odd Z stores bytes)
+    if ((K & 3) == 0) {
+        const int K4 = K >> 2;
+        for (int s = 0; s < n_here; ++s) {
+            const float4 *src = reinterpret_cast<const float4 *>(app + (size_t)s * ncw);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(a.hard + (cw0 + s) * K);
+            for (int k = threadIdx.x; k < K4; k += blockDim.x) {
+                const float4 v = src[k];
+                dst[k] = (__float_as_uint(v.x) >> 31) | ((__float_as_uint(v.y) >> 31) << 8) |
+                         ((__float_as_uint(v.z) >> 31) << 16) | ((__float_as_uint(v.w) >> 31) << 24);
+            }
+        }
+    } else {
+        for (int s = 0; s < n_here; ++s) {
+            const float *src = app + (size_t)s * ncw;
+            uint8_t *dst = a.hard + (cw0 + s) * K;
+            for (int k = threadIdx.x; k < K; k += blockDim.x) dst[k] = src[k] < 0.0f ? 1 : 0;
+        }
     }
     if (a.soft) {
         float4 *dst = reinterpret_cast<float4 *>(a.soft + cw0 * ncw);
@@ -181,33 +272,33 @@ __device__ __forceinline__ void store_outputs(const DecArgs &a, const float *app
     }
 }
 
+// Record slots: layer r >= 1 lives in slot r; layer 0 lives in slot n_rows, so that "the next
+// layer's record" is always the next slot, also across the iteration boundary.
+
 // ---- one full iteration over the layers: looped (generic) --------------------------------------
 __device__ __forceinline__ void iteration_looped(const DecArgs &a, DecCtx &c, const int it) {
     const bool store_rec = it + 1 < a.max_iters;
-    // Record slots: layer r >= 1 lives in slot r; layer 0 lives in slot n_rows, so that "the next
-    // layer's record" is always the next slot, also across the iteration boundary.
     uint4 *rp = c.my_rec;
     for (int r = 0; r < a.n_rows; ++r) {
         // software prefetch of the next layer's record
-        uint4 *np = rp + c.rec_stride;
+        uint4 *np = rp + kRecStride;
         const bool ld = (r + 1 == a.n_rows) ? store_rec : (it > 0);
         uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
-        if (ld && !c.done) nxt = __ldcg(np);
+        if (ld && !c.done) nxt = ld_rec(np, c.pol);
         if (!c.done) {
             const int e0 = a.row_start[r];
             const int deg = a.row_start[r + 1] - e0;
             const uint2 *ed = a.ed + e0;
-            float n1, n2;
-            uint32_t nmeta;
+            uint4 rec = make_uint4(0u, 0u, 0u, 0u);
             switch (deg) {
-#define NRLDPC_ROW_CASE(D) case D: process_row<D>(c.base, ed, c.zoff, c.Z4, __uint_as_float(c.cur.x), __uint_as_float(c.cur.y), c.cur.z, a.alpha, n1, n2, nmeta); break;
+#define NRLDPC_ROW_CASE(D) case D: rec = process_row<D, false, false>(c.l, ed, c.cur.x, c.cur.y, c.cur.z, a.alpha); break;
                 NRLDPC_ROW_CASE(3) NRLDPC_ROW_CASE(4) NRLDPC_ROW_CASE(5) NRLDPC_ROW_CASE(6)
                 NRLDPC_ROW_CASE(7) NRLDPC_ROW_CASE(8) NRLDPC_ROW_CASE(9) NRLDPC_ROW_CASE(10)
                 NRLDPC_ROW_CASE(19)
 #undef NRLDPC_ROW_CASE
-                default: n1 = 0.f; n2 = 0.f; nmeta = 0; break;
+                default: break;
             }
-            if (store_rec) __stcg(r == 0 ? c.rec0 : rp, make_uint4(__float_as_uint(n1), __float_as_uint(n2), nmeta, 0u));
+            if (store_rec) st_rec(r == 0 ? c.my_rec + (size_t)a.n_rows * kRecStride : rp, rec, c.pol);
         }
         c.cur = nxt;
         rp = np;
@@ -216,45 +307,53 @@ __device__ __forceinline__ void iteration_looped(const DecArgs &a, DecCtx &c, co
 }
 
 // ---- one full iteration over the layers: fully unrolled for base graph BG -----------------------
-template <int BG, int R>
+// One instantiation serves every iteration: the unrolled layer code of BG1 is ~100 KB of SASS and
+// has to stay resident in the SM's instruction cache (per-iteration specialisations were measured
+// to thrash it).  ld_from / ld_to: the next layer's record is prefetched while processing layer R
+// iff ld_from <= R < ld_to (first iteration: only across the iteration boundary; last: never across).
+// FULL: every thread of the CTA owns a check for the whole decode (one codeword per CTA, Z a
+// multiple of 32): no per-thread activity test.
+template <int BG, int R, bool FULL>
 struct UnrolledRows {
-    static __device__ __forceinline__ void run(const DecArgs &a, DecCtx &c, const bool first, const bool store_rec) {
+    static __device__ __forceinline__ void run(const DecArgs &a, DecCtx &c, const int ld_from, const int ld_to, const bool store_rec) {
         if (R >= a.n_rows) return;
         constexpr int DEG = BgShape<BG>::deg(R);
         constexpr int E0 = BgShape<BG>::start(R);
-        // slot R+1 (slot n_rows holds layer 0: see iteration_looped)
-        const bool ld = (R + 1 == a.n_rows) ? store_rec : !first;
-        uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
-        if (ld && !c.done) nxt = __ldcg(c.my_rec + (size_t)(R + 1) * c.rec_stride);
-        if (!c.done) {
-            float n1, n2;
-            uint32_t nmeta;
-            process_row<DEG>(c.base, a.ed + E0, c.zoff, c.Z4, __uint_as_float(c.cur.x), __uint_as_float(c.cur.y),
-                             c.cur.z, a.alpha, n1, n2, nmeta);
-            if (store_rec)
-                __stcg(c.my_rec + (size_t)(R == 0 ? a.n_rows : R) * c.rec_stride,
-                       make_uint4(__float_as_uint(n1), __float_as_uint(n2), nmeta, 0u));
+        if (FULL || !c.done) {
+            // slot R+1; slot n_rows holds layer 0
+            uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+            if (R >= ld_from && R < ld_to) nxt = ld_rec(c.my_rec + (R + 1) * kRecStride, c.pol);
+            const uint4 rec = process_row<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur.x, c.cur.y, c.cur.z, a.alpha);
+            if (store_rec) st_rec(R == 0 ? c.my_rec + (size_t)a.n_rows * kRecStride : c.my_rec + R * kRecStride, rec, c.pol);
+            c.cur = nxt;
         }
-        c.cur = nxt;
         __syncthreads();
-        UnrolledRows<BG, R + 1>::run(a, c, first, store_rec);
+        UnrolledRows<BG, R + 1, FULL>::run(a, c, ld_from, ld_to, store_rec);
     }
 };
-template <int BG>
-struct UnrolledRows<BG, BgShape<BG>::kRows> {
-    static __device__ __forceinline__ void run(const DecArgs &, DecCtx &, bool, bool) {}
+template <int BG, bool FULL>
+struct UnrolledRows<BG, BgShape<BG>::kRows, FULL> {
+    static __device__ __forceinline__ void run(const DecArgs &, DecCtx &, int, int, bool) {}
 };
 
+template <int BG, bool FULL>
+__device__ __forceinline__ void iteration_unrolled(const DecArgs &a, DecCtx &c, const int it) {
+    const bool first = it == 0, last = it + 1 == a.max_iters;
+    UnrolledRows<BG, 0, FULL>::run(a, c, first ? a.n_rows - 1 : 0, last ? a.n_rows - 1 : a.n_rows, !last);
+}
+
 // BG = 0: generic looped variant; BG = 1 / 2: layer loop unrolled for that base graph.
-template <int BG>
+template <int BG, bool FULL>
 __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(const __grid_constant__ DecArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Z = a.Z;
     const int ncw = a.ncols * Z;
     const int K = a.kcols * Z;
     float *app = reinterpret_cast<float *>(smem_raw);
-    int *s_flag = reinterpret_cast<int *>(app + (size_t)a.cwpc * ncw);
-    __shared__ int s_group;
+    int *s_flag = reinterpret_cast<int *>(app + (size_t)a.cwpc * ncw);  // [cwpc] + work-group slot
+    int &s_group = s_flag[a.cwpc];
+    // the edge descriptors carry absolute shared addresses (DecArgs::ed): fail loudly if the window moved
+    if ((uint32_t)__cvta_generic_to_shared(smem_raw) != a.smem_base) __trap();
 
     const int tid = threadIdx.x;
     const int slot = tid / Z;
@@ -264,12 +363,12 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
     const bool want_ok = a.ok != nullptr;
 
     DecCtx c;
-    c.Z4 = (uint32_t)Z * 4u;
-    c.zoff = (uint32_t)z * 4u;
-    c.base = (uint32_t)__cvta_generic_to_shared(app + (size_t)slot * ncw);
-    c.rec_stride = blockDim.x;
-    c.my_rec = a.c2v + (size_t)blockIdx.x * (a.n_rows + 1) * c.rec_stride + tid;
-    c.rec0 = c.my_rec + (size_t)a.n_rows * c.rec_stride;
+    c.l.zoff = (uint32_t)z * 4u;
+    c.l.nZ4 = 0u - (uint32_t)Z * 4u;
+    c.l.slot_off = FULL ? 0u : (uint32_t)(slot * ncw) * 4u;
+    c.l.one = (uint32_t)a.one;
+    c.my_rec = a.c2v + (size_t)blockIdx.x * (a.n_rows + 1) * kRecStride + tid;
+    c.pol = make_l2_policy(a.l2_pin);
 
     while (true) {
         __syncthreads();  // previous group's outputs are out of smem
@@ -292,7 +391,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
 
         for (int it = 0; it < a.max_iters; ++it) {
             if (BG == 0) iteration_looped(a, c, it);
-            else UnrolledRows<(BG == 0 ? 1 : BG), 0>::run(a, c, it == 0, it + 1 < a.max_iters);
+            else iteration_unrolled<(BG == 0 ? 1 : BG), FULL>(a, c, it);
 
             if (!c.done) my_iters = it + 1;
             const bool last = it + 1 == a.max_iters;

@@ -19,6 +19,14 @@
 
 #define NRLDPC_EXPORT extern "C" __attribute__((visibility("default")))
 
+namespace nrldpc {
+// Shared-window address at which a kernel without static shared memory sees its dynamic shared memory.
+__global__ void smem_base_probe(uint32_t *out) {
+    extern __shared__ __align__(16) unsigned char probe_smem[];
+    *out = (uint32_t)__cvta_generic_to_shared(probe_smem);
+}
+}  // namespace nrldpc
+
 namespace {
 
 constexpr int kNumPipe = 3;  // streams / staging sets for NRLDPC_MEM_HOST calls
@@ -60,6 +68,8 @@ struct nrldpc_handle {
     PipeSlot pipe[kNumPipe];
     int dec_smem_optin = 0;
     int dec_variant = 1;             // NRLDPC_DECODE_VARIANT=loop selects the generic looped kernel
+    int l2_pin = 1;                  // NRLDPC_L2_PIN=0 drops the evict_last policy on the c2v scratch
+    uint32_t smem_base = 0;          // shared-window address of dynamic shared memory (probed at create)
     nrldpc::DecArgs dec_args;
     cudaEvent_t dev_done = nullptr;  // last NRLDPC_MEM_DEVICE launch that used pipe[0]'s scratch
 };
@@ -112,7 +122,7 @@ int decode_threads(int Z) { return std::max(32, (decode_cwpc(Z) * Z + 31) / 32 *
 size_t decode_smem_bytes(const nrldpc_handle *h, int n_rows) {
     const int cwpc = decode_cwpc(h->d.Z);
     (void)n_rows;
-    return (size_t)cwpc * h->d.n_cw * 4 + (size_t)cwpc * 4 + 16;
+    return (size_t)cwpc * h->d.n_cw * 4 + (size_t)(cwpc + 1) * 4 + 16;
 }
 
 int ensure_scratch(nrldpc_handle *h, PipeSlot &s, size_t recs) {
@@ -135,19 +145,23 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
     const size_t smem = decode_smem_bytes(h, n_rows);
     // variant 0: generic looped layers; 1/2: layer loop unrolled for that base graph (default)
     using Kern = void (*)(const nrldpc::DecArgs);
-    const Kern kern = h->dec_variant == 0 ? (Kern)nrldpc::decode_nms_kernel<0>
-                      : (h->d.bg == 1 ? (Kern)nrldpc::decode_nms_kernel<1> : (Kern)nrldpc::decode_nms_kernel<2>);
-    if ((int)smem > h->dec_smem_optin) {
-        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        h->dec_smem_optin = (int)smem;
-    }
-    if (int rc = ensure_scratch(h, s, (size_t)grid * (n_rows + 1) * threads)) return rc;
+    // FULL: one codeword per CTA and every thread owns a check (Z a multiple of the warp size)
+    const bool full = cwpc == 1 && threads == Z;
+    const Kern kern = h->dec_variant == 0 ? (Kern)nrldpc::decode_nms_kernel<0, false>
+                      : h->d.bg == 1 ? (full ? (Kern)nrldpc::decode_nms_kernel<1, true> : (Kern)nrldpc::decode_nms_kernel<1, false>)
+                                     : (full ? (Kern)nrldpc::decode_nms_kernel<2, true> : (Kern)nrldpc::decode_nms_kernel<2, false>);
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = ensure_scratch(h, s, (size_t)grid * (n_rows + 1) * nrldpc::kRecStride)) return rc;
     CUDA_TRY(h, cudaMemsetAsync(s.counter, 0, sizeof(int), stream));
     nrldpc::DecArgs &a = h->dec_args;  // tables were filled at create()
     a.llr = llr; a.hard = hard; a.soft = soft; a.iters = iters; a.ok = ok;
     a.batch = batch; a.Z = Z; a.ncols = h->d.cols; a.kcols = h->d.kcols; a.n_rows = n_rows;
     a.n_edges = h->h_row_start[n_rows]; a.max_iters = h->cfg.max_iters; a.early_term = h->cfg.early_term;
-    a.cwpc = cwpc; a.alpha = h->cfg.alpha;
+    a.cwpc = cwpc; a.alpha = h->cfg.alpha; a.l2_pin = h->l2_pin; a.one = 1;
+    if (a.smem_base != h->smem_base) {
+        for (int e = 0; e < h->d.edges; ++e) a.ed[e].y += h->smem_base - a.smem_base;
+        a.smem_base = h->smem_base;
+    }
     a.c2v = s.c2v; a.work_counter = s.counter;
     kern<<<grid, threads, smem, stream>>>(a);
     CUDA_TRY(h, cudaGetLastError());
@@ -294,6 +308,7 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
     }
     h->num_sms = prop.multiProcessorCount;
     if (const char *v = getenv("NRLDPC_DECODE_VARIANT")) h->dec_variant = strcmp(v, "loop") == 0 ? 0 : 1;
+    if (const char *v = getenv("NRLDPC_L2_PIN")) h->l2_pin = atoi(v) ? 1 : 0;
 
     const BgView v = bg_view(cfg->bg);
     const int Z = cfg->Z;
@@ -309,6 +324,9 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
         const int sft = v.sh(ils, e) % Z;
         ed[e] = ((uint32_t)(v.col[e] * Z) << 16) | (uint32_t)sft;
         h->dec_args.ed[e] = make_uint2((uint32_t)sft * 4u, (uint32_t)(v.col[e] * Z) * 4u);
+        // the unrolled kernels rely on the extension parity columns being identity circulants
+        if (v.row[e] >= 4 && (e + 1 == v.edges || v.row[e + 1] != v.row[e]) && (sft != 0 || v.col[e] != v.kcols + v.row[e]))
+            h->dec_variant = 0;
     }
     // encoder structure: shifts of the first core-parity column in rows 0..3
     int vals[3], nv = 0;
@@ -328,6 +346,12 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
         CUDA_TRY(h, cudaMalloc(&h->row_start, sizeof(int) * (v.rows + 1)));
         CUDA_TRY(h, cudaMemcpy(h->edesc, ed.data(), ed.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
         CUDA_TRY(h, cudaMemcpy(h->row_start, h->h_row_start, sizeof(int) * (v.rows + 1), cudaMemcpyHostToDevice));
+        uint32_t *d_base = nullptr;
+        CUDA_TRY(h, cudaMalloc(&d_base, sizeof(uint32_t)));
+        nrldpc::smem_base_probe<<<1, 1, 16>>>(d_base);
+        cudaError_t pe = cudaMemcpy(&h->smem_base, d_base, sizeof(uint32_t), cudaMemcpyDeviceToHost);
+        cudaFree(d_base);
+        CUDA_TRY(h, pe);
         return 0;
     };
     rc = up();
@@ -383,6 +407,8 @@ NRLDPC_EXPORT int nrldpc_decode(nrldpc_t *h, const float *llr, int64_t batch, in
     if (mem == NRLDPC_MEM_DEVICE) {
         if ((reinterpret_cast<uintptr_t>(llr) & 15) || (app_soft && (reinterpret_cast<uintptr_t>(app_soft) & 15)))
             return fail(h, NRLDPC_ESHAPE, "device llr / app_soft pointers must be 16-byte aligned");
+        if (reinterpret_cast<uintptr_t>(info_hard) & 3)
+            return fail(h, NRLDPC_ESHAPE, "device info_hard pointer must be 4-byte aligned");
         if (!h->dev_done) CUDA_TRY(h, cudaEventCreateWithFlags(&h->dev_done, cudaEventDisableTiming));
         if (int rc = launch_decode(h, h->pipe[0], static_cast<cudaStream_t>(stream), llr, batch, n_rows, info_hard,
                                    app_soft, iters, parity_ok))
