@@ -67,7 +67,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -187,10 +187,12 @@ def run_reference(args, w, wname):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--llr-dtype", default="f32", choices=["f32", "f16x2"],
+                    help="decoder arithmetic: float32 (default, headline) or packed fp16, two codewords per thread")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -210,7 +212,9 @@ def main():
     torch.cuda.set_device(local_rank)
     stream = torch.cuda.current_stream().cuda_stream
 
-    h = capi.Handle(w["bg"], w["Z"], w["iters"], bool(w["early_term"]), device=local_rank)
+    f16 = args.llr_dtype == "f16x2"
+    h = capi.Handle(w["bg"], w["Z"], w["iters"], bool(w["early_term"]), device=local_rank,
+                    llr_dtype=capi.F16X2 if f16 else capi.F32)
     B, K = w["batch"], h.K
     info, llr = make_inputs(h, capi, torch, w, D.rank_seed(0, rank) & 0x7FFFFFFF, stream)
     hard = torch.empty((B, K), dtype=torch.uint8, device="cuda")
@@ -282,11 +286,11 @@ def main():
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text()).get(args.workload)
+            traffic = json.loads(tp.read_text()).get(args.workload + ("|f16x2" if f16 else ""))
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "decode_nms_kernel", "kernel_ms": k_ms, "bytes_per_codeword": bytes_per_cw,
+                "traffic": traffic, "kernel": "decode_nms_h2_kernel" if f16 else "decode_nms_kernel", "kernel_ms": k_ms, "bytes_per_codeword": bytes_per_cw,
                 "peak_source": peak_src,
                 "note": "state stays on chip for all iterations; the kernel is issue/shared-memory bound by construction "
                         "(SURVEY.md 8d), so the HBM fraction is small; see profiles/ for issue-slot utilisation"}
@@ -303,17 +307,17 @@ def main():
         from oracle import oracle as O
         t0 = time.perf_counter()
         ref = O.decode_nms(w["bg"], w["Z"], sample, w["iters"], early_term=bool(w["early_term"]), n_rows=w["n_rows"],
-                           want_app=False, n_threads=threads)
+                           want_app=False, n_threads=threads, f16=f16)
         dta = time.perf_counter() - t0
-        cpu["like_for_like_nms_f32"] = {"value": bits / dta / 1e9, "unit": "Gb/s", "cores": threads,
+        cpu["like_for_like_nms_" + ("f16" if f16 else "f32")] = {"value": bits / dta / 1e9, "unit": "Gb/s", "cores": threads,
                                         "matches_gpu_bits": bool((ref["hard"] == hard[:CPU_SAMPLE_CW].cpu().numpy()).all())}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "Gb/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "bg": w["bg"], "Z": w["Z"], "K": K, "N": h.N, "E": w["E"],
+            "dtype": "f16" if f16 else "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "llr_dtype": args.llr_dtype, "bg": w["bg"], "Z": w["Z"], "K": K, "N": h.N, "E": w["E"],
                        "rate": round(K / w["E"], 4), "n_rows": w["n_rows"], "iters": w["iters"], "early_term": w["early_term"],
                        "alpha": 0.75, "algorithm": "layered normalized min-sum", "batch_per_gpu": B,
                        "global_batch": B * world, "parallelism": f"dp{world} (independent codeword shards, no data-path collective)",
@@ -321,6 +325,8 @@ def main():
                        "l2": f"inputs larger than L2 ({B * h.n_cw * 4 / 2**20:.0f} MiB LLRs per step vs 126 MB L2)"},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         }
+        if f16:
+            line["metric"] = METRIC + " (packed fp16 arithmetic)"
         print(json.dumps(line), flush=True)
     h.close()
     if world > 1:

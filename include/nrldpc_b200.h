@@ -39,6 +39,9 @@ extern "C" {
 #define NRLDPC_MEM_HOST   0
 #define NRLDPC_MEM_DEVICE 1
 
+#define NRLDPC_F32   0
+#define NRLDPC_F16X2 1
+
 /* Input LLR magnitudes are clamped to this value on load (NaN and +inf filler -> +LLR_MAX). */
 #define NRLDPC_LLR_MAX 1048576.0f
 
@@ -55,7 +58,9 @@ typedef struct nrldpc_cfg {
     int32_t early_term; /* 1 = 'Parity check satisfied' (NRLDPCDecoder.m:120), 0 = 'Maximum iteration count' */
     float   alpha;      /* min-sum normalisation; <= 0 selects the default 0.75 */
     int32_t device;     /* CUDA device ordinal, -1 = current device */
-    int32_t reserved[2];
+    int32_t llr_dtype;  /* decoder arithmetic: NRLDPC_F32 (default) or NRLDPC_F16X2 (two codewords per thread in
+                           packed fp16, inputs clamped to +-2048; the buffers of nrldpc_decode stay float32) */
+    int32_t reserved;
 } nrldpc_cfg;
 
 int  nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg);
@@ -79,11 +84,12 @@ int nrldpc_lifting_size(int32_t K_b, int32_t K_prime);
 int nrldpc_base_graph(int32_t bg, int32_t i_LS, int32_t *rows, int32_t *cols, int32_t *shifts);
 
 /* ---- decode: replaces step(obj.hLDPCDecoder, cw_tilde) at NRLDPCDecoder.m:265 ----------------
- * Layered normalized min-sum (float32) over base rows 0..n_rows-1 (n_rows = 0 -> all rows;
+ * Layered normalized min-sum (float32, or packed fp16 with llr_dtype = NRLDPC_F16X2) over base rows 0..n_rows-1 (n_rows = 0 -> all rows;
  * 4 <= n_rows).  Rows whose parity bit was not transmitted carry zero LLR and contribute nothing,
  * so callers may trim them (DESIGN.md "active rows").
  *   llr       [batch][n_cw] float32, cw layout; +inf / NaN = filler; exact 0 = punctured / unsent
- *   info_hard [batch][K] uint8, hard decision (app < 0) of the information part (required)
+ *   info_hard [batch][K] uint8, hard decision (app < 0) of the information part (required; device
+ *             pointers must be 4-byte aligned)
  *   app_soft  [batch][n_cw] float32 a-posteriori LLRs after the last iteration (nullable)
  *   iters     [batch] int32 iterations executed (nullable)
  *   parity_ok [batch] uint8, 1 if every check of the active rows is satisfied (nullable) */

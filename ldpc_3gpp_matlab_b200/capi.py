@@ -22,6 +22,9 @@ NRLDPC_ENOMEM = -4
 MEM_HOST = 0
 MEM_DEVICE = 1
 LLR_MAX = 1048576.0
+F32 = 0
+F16X2 = 1
+LLR_MAX_F16 = 2048.0
 
 # every symbol include/nrldpc_b200.h declares (tests/test_abi.py checks the header against this)
 SYMBOLS = (
@@ -48,7 +51,7 @@ class CudaError(RuntimeError):
 
 class Cfg(C.Structure):
     _fields_ = [("bg", C.c_int32), ("Z", C.c_int32), ("max_iters", C.c_int32), ("early_term", C.c_int32),
-                ("alpha", C.c_float), ("device", C.c_int32), ("reserved", C.c_int32 * 2)]
+                ("alpha", C.c_float), ("device", C.c_int32), ("llr_dtype", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Dims(C.Structure):
@@ -149,11 +152,11 @@ class Handle:
     """Owner of one nrldpc_t: a (BG, Z) code with its iteration policy on one GPU."""
 
     def __init__(self, bg: int, Z: int, max_iters: int = 8, early_term: bool = False, alpha: float = 0.75,
-                 device: int = -1):
+                 device: int = -1, llr_dtype: int = F32):
         self._lib = load()
         self._h = C.c_void_p()
         cfg = Cfg(bg=int(bg), Z=int(Z), max_iters=int(max_iters), early_term=int(bool(early_term)),
-                  alpha=float(alpha), device=int(device))
+                  alpha=float(alpha), device=int(device), llr_dtype=int(llr_dtype))
         rc = self._lib.nrldpc_create(C.byref(self._h), C.byref(cfg))
         if rc:
             _raise(rc, self._lib.nrldpc_last_error(None).decode())

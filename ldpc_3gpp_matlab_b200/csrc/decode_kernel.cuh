@@ -59,6 +59,7 @@ struct DecArgs {
     int l2_pin;              // 1: c2v scratch accesses carry an L2 evict_last policy
     int one;                 // = 1 (see mad_u32)
     uint32_t smem_base;      // shared-window address of the kernel's dynamic shared memory
+    uint32_t alpha_h2;       // {fp16(alpha), fp16(alpha)} for the packed-half kernel
     uint4 *c2v;              // [grid][n_rows+1][kRecStride] {alpha*min1|sgn, alpha*min2|sgn, argmin | signbits << 5, -}
     int *work_counter;
     unsigned short row_start[kMaxRows + 2];
@@ -78,8 +79,9 @@ template <> struct BgShape<2> {
 };
 
 __device__ __forceinline__ float clamp_llr(float x) {
-    // NaN marks filler upstream (NRLDPCDecoder.m:224,264): fminf(NaN, M) = M.
-    return fmaxf(fminf(x, kLlrMax), -kLlrMax);
+    // NaN marks filler upstream (NRLDPCDecoder.m:224,264): fminf(NaN, M) = M.  The final + 0 turns -0 into +0:
+    // no APP value is ever -0 afterwards, so a hard decision (app < 0) is exactly the sign bit.
+    return __fadd_rn(fmaxf(fminf(x, kLlrMax), -kLlrMax), 0.0f);
 }
 
 __device__ __forceinline__ float lds_f32(uint32_t addr) {

@@ -1,0 +1,292 @@
+// decode_kernel_h2.cuh -- packed-half variant of the layered normalized min-sum decoder
+// (nrldpc_cfg.llr_dtype = NRLDPC_F16X2).
+//
+// Same mapping as decode_kernel.cuh (thread = check z of every layer, APP values resident in shared
+// memory, compressed check-to-variable records in an L2-pinned scratch, layer loop unrolled per
+// base graph), but every thread decodes TWO codewords at once: the a-posteriori LLRs of a codeword
+// pair are interleaved as one 32-bit {fp16 A, fp16 B} word per variable, so one address
+// computation, one LDS/STS and one packed HADD2 / HMNMX2 / HSET2 / LOP3 serve both codewords.
+// The kernel is ALU-pipe bound, so halving the instructions per codeword is
+// what doubles the throughput; HBM traffic is unchanged (the boundary stays float32).
+//
+// Arithmetic (bit-exact against oracle/nrldpc_oracle.c, orc_decode_nms_f16):
+//   input   x -> fp16(min(max(x, -2048), 2048)) (round to nearest even; NaN / +inf filler -> +2048)
+//   check   t_e = app - c_e (fp16, RN);  m1, m2 = two smallest |t_e|, each capped at 2048;
+//           c_e' = sgn_e * fp16(alpha_h * (e is an arg-min ? m2 : m1)) with alpha_h = fp16(alpha);
+//           app = t_e + c_e' (fp16, RN)
+// The caps bound |app| by 2048 + 30 * 1536 < 65504, so no value can overflow to infinity.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "decode_kernel.cuh"
+
+namespace nrldpc {
+
+constexpr float kH2LlrMax = 2048.0f;
+constexpr uint32_t kH2MsgCap = 0x68006800u;   // {2048, 2048} as packed fp16
+constexpr uint32_t kH2Sign = 0x80008000u;
+
+__device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2 *>(&u); }
+__device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t x;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(addr));
+    return x;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ float clamp_llr_h2(float x) { return __fadd_rn(fmaxf(fminf(x, kH2LlrMax), -kH2LlrMax), 0.0f); }
+
+// One check row of degree DEG for check z of a codeword pair.  Record layout (uint4):
+//   x, y : alpha*min1, alpha*min2 of both codewords (packed fp16; sign bits ignored on read)
+//   z    : sign bits of the messages on edges 0..min(DEG,16)-1: edge e at bit 15-(n0-1-e) of each half
+//   w    : arg-min edge index of each codeword in bits 0..4 / 16..20 (compared as fp16 bit patterns),
+//          for DEG > 16 also the sign bits of edges 16..DEG-1 at the top of each half
+template <int DEG, bool IDENT_LAST, bool ONE_CW>
+__device__ __forceinline__ uint4 process_row_h2(const Lane &l, const uint2 *__restrict__ ed, const uint4 rec,
+                                                const uint32_t alpha2) {
+    constexpr int N0 = DEG < 16 ? DEG : 16;
+    constexpr int N1 = DEG - N0;
+    uint32_t t[DEG];
+    uint32_t addr[DEG];
+    __half2 m1 = as_h2(0u), m2 = as_h2(0u);
+    uint32_t sx = 0, s0 = 0, s1 = 0;
+    const uint32_t oargs = N1 > 0 ? (rec.w & 0x001f001fu) : rec.w;
+#pragma unroll
+    for (int e = 0; e < DEG; ++e) {
+        const uint2 d = ed[e];
+        const uint32_t a = edge_addr<ONE_CW>(l, d, IDENT_LAST && e == DEG - 1);
+        addr[e] = a;
+        const uint32_t x = lds_u32(a);
+        const uint32_t e2 = (uint32_t)e * 0x00010001u;
+        const uint32_t is_arg = __heq2_mask(as_h2(oargs), as_h2(e2));
+        const uint32_t mag = bitselect(rec.x, rec.y, is_arg);
+        const uint32_t sw = e < 16 ? rec.z << (N0 - 1 - e) : rec.w << (DEG - 1 - e);
+        const uint32_t c = bitselect(mag, sw, kH2Sign);
+        const __half2 tt = __hsub2(as_h2(x), as_h2(c));
+        t[e] = as_u32(tt);
+        const __half2 ab = __habs2(tt);
+        if (e == 0) {
+            m1 = ab;
+        } else if (e == 1) {
+            m2 = __hmax2(m1, ab);
+            m1 = __hmin2(m1, ab);
+        } else {
+            m2 = __hmin2(m2, __hmax2(ab, m1));
+            m1 = __hmin2(m1, ab);
+        }
+        sx ^= as_u32(tt);
+        if (e < 16) s0 = bitselect(s0 >> 1, as_u32(tt), kH2Sign);
+        else s1 = bitselect(s1 >> 1, as_u32(tt), kH2Sign);
+    }
+    const __half2 m1raw = m1;
+    m1 = __hmin2(m1, as_h2(kH2MsgCap));
+    m2 = __hmin2(m2, as_h2(kH2MsgCap));
+    const uint32_t sg = sx & kH2Sign;
+    uint32_t m1ss = as_u32(__hmul2(as_h2(alpha2), m1)) | sg;
+    uint32_t m2ss = as_u32(__hmul2(as_h2(alpha2), m2)) | sg;
+    asm volatile("" : "+r"(m1ss), "+r"(m2ss));
+    uint32_t args = 0;
+#pragma unroll
+    for (int e = 0; e < DEG; ++e) {
+        // arg-min edges found by value (ties: min2 == min1, every tied edge gets the same message)
+        const uint32_t is_min = __heq2_mask(__habs2(as_h2(t[e])), m1raw);
+        const uint32_t sel = bitselect(m1ss, m2ss, is_min);
+        args = bitselect(args, (uint32_t)e * 0x00010001u, is_min);
+        const uint32_t c = sel ^ (t[e] & kH2Sign);
+        sts_u32(addr[e], as_u32(__hadd2(as_h2(t[e]), as_h2(c))));
+    }
+    // sign of message e = row sign ^ sign(t_e), per codeword
+    const uint32_t flip = ((sx >> 15) & 0x00010001u) * 0xffffu;
+    constexpr uint32_t F0 = (((1u << N0) - 1u) << (16 - N0)) * 0x00010001u;
+    constexpr uint32_t F1 = N1 > 0 ? (((1u << N1) - 1u) << (16 - N1)) * 0x00010001u : 0u;
+    const uint32_t z = s0 ^ (flip & F0);
+    const uint32_t w = N1 > 0 ? (((s1 ^ flip) & F1) | args) : args;
+    return make_uint4(m1ss, m2ss, z, w);
+}
+
+// ---- pieces of the pair kernel ---------------------------------------------------------------------
+struct DecCtxH2 {
+    Lane l;
+    uint4 *my_rec;
+    uint64_t pol;
+    uint4 cur;
+    bool done;   // this thread does no row work (inactive lane, or both codewords of its pair are finished)
+};
+
+// Load one codeword pair (B may be absent: zeros) into its interleaved APP array.
+__device__ __forceinline__ void load_pair(const float *__restrict__ rowA, const float *__restrict__ rowB, uint32_t *app,
+                                          int ncw, int lane, int nlanes) {
+    const float4 *a4 = reinterpret_cast<const float4 *>(rowA);
+    const float4 *b4 = reinterpret_cast<const float4 *>(rowB);
+    uint4 *dst = reinterpret_cast<uint4 *>(app);
+    for (int i = lane; i < (ncw >> 2); i += nlanes) {
+        const float4 va = __ldcs(a4 + i);
+        const float4 vb = rowB ? __ldcs(b4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        uint4 o;
+        o.x = as_u32(__floats2half2_rn(clamp_llr_h2(va.x), clamp_llr_h2(vb.x)));
+        o.y = as_u32(__floats2half2_rn(clamp_llr_h2(va.y), clamp_llr_h2(vb.y)));
+        o.z = as_u32(__floats2half2_rn(clamp_llr_h2(va.z), clamp_llr_h2(vb.z)));
+        o.w = as_u32(__floats2half2_rn(clamp_llr_h2(va.w), clamp_llr_h2(vb.w)));
+        dst[i] = o;
+    }
+}
+
+// Outputs of ONE codeword (half 0 = A, 1 = B) of a pair, written by the pair's own lanes.
+__device__ __forceinline__ void store_half(const DecArgs &a, const uint32_t *app, long long cw, int half, int ncw, int K,
+                                           int lane, int nlanes) {
+    const int sh = half ? 31 : 15;
+    uint8_t *hard = a.hard + cw * K;
+    if ((K & 3) == 0) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(app);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(hard);
+        for (int k = lane; k < (K >> 2); k += nlanes) {
+            const uint4 v = src[k];
+            dst[k] = ((v.x >> sh) & 1u) | (((v.y >> sh) & 1u) << 8) | (((v.z >> sh) & 1u) << 16) | (((v.w >> sh) & 1u) << 24);
+        }
+    } else {
+        for (int k = lane; k < K; k += nlanes) hard[k] = (uint8_t)((app[k] >> sh) & 1u);
+    }
+    if (a.soft) {
+        float *dst = a.soft + cw * ncw;
+        for (int i = lane; i < ncw; i += nlanes) {
+            const float2 f = __half22float2(as_h2(app[i]));
+            __stcs(dst + i, half ? f.y : f.x);
+        }
+    }
+}
+
+// syndrome of hard = (app < 0) over the active rows; bit 15 = codeword A fails, bit 31 = B fails
+__device__ __forceinline__ uint32_t syndrome_fail_h2(const DecArgs &a, const DecCtxH2 &c) {
+    uint32_t fail = 0;
+    for (int r = 0; r < a.n_rows; ++r) {
+        uint32_t par = 0;
+        for (int e = a.row_start[r]; e < a.row_start[r + 1]; ++e) par ^= lds_u32(edge_addr<false>(c.l, a.ed[e]));
+        fail |= par;
+    }
+    return fail & kH2Sign;
+}
+
+template <int BG, int R, bool FULL>
+struct UnrolledRowsH2 {
+    static __device__ __forceinline__ void run(const DecArgs &a, DecCtxH2 &c, const int ld_from, const int ld_to, const bool store_rec) {
+        if (R >= a.n_rows) return;
+        constexpr int DEG = BgShape<BG>::deg(R);
+        constexpr int E0 = BgShape<BG>::start(R);
+        if (FULL || !c.done) {
+            uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
+            if (R >= ld_from && R < ld_to) nxt = ld_rec(c.my_rec + (R + 1) * kRecStride, c.pol);
+            const uint4 rec = process_row_h2<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur, a.alpha_h2);
+            if (store_rec) st_rec(R == 0 ? c.my_rec + (size_t)a.n_rows * kRecStride : c.my_rec + R * kRecStride, rec, c.pol);
+            c.cur = nxt;
+        }
+        __syncthreads();
+        UnrolledRowsH2<BG, R + 1, FULL>::run(a, c, ld_from, ld_to, store_rec);
+    }
+};
+template <int BG, bool FULL>
+struct UnrolledRowsH2<BG, BgShape<BG>::kRows, FULL> {
+    static __device__ __forceinline__ void run(const DecArgs &, DecCtxH2 &, int, int, bool) {}
+};
+
+// Here cwpc counts codeword PAIRS per CTA; FULL = one pair per CTA and every thread owns a check.
+template <int BG, bool FULL>
+__global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kernel(const __grid_constant__ DecArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int Z = a.Z;
+    const int ncw = a.ncols * Z;
+    const int K = a.kcols * Z;
+    uint32_t *app = reinterpret_cast<uint32_t *>(smem_raw);
+    int *s_flag = reinterpret_cast<int *>(app + (size_t)a.cwpc * ncw);  // [2*cwpc] + work-group slot
+    int &s_group = s_flag[2 * a.cwpc];
+    if ((uint32_t)__cvta_generic_to_shared(smem_raw) != a.smem_base) __trap();
+
+    const int tid = threadIdx.x;
+    const int slot = tid / Z;
+    const int z = tid - slot * Z;
+    const bool lane_ok = tid < a.cwpc * Z;
+    const int per_group = 2 * a.cwpc;
+    const long long n_groups = (a.batch + per_group - 1) / per_group;
+    const bool want_ok = a.ok != nullptr;
+
+    DecCtxH2 c;
+    c.l.zoff = (uint32_t)z * 4u;
+    c.l.nZ4 = 0u - (uint32_t)Z * 4u;
+    c.l.slot_off = FULL ? 0u : (uint32_t)(slot * ncw) * 4u;
+    c.l.one = (uint32_t)a.one;
+    c.my_rec = a.c2v + (size_t)blockIdx.x * (a.n_rows + 1) * kRecStride + tid;
+    c.pol = make_l2_policy(a.l2_pin);
+    uint32_t *my_app = app + (size_t)(lane_ok ? slot : 0) * ncw;
+
+    while (true) {
+        __syncthreads();  // previous group's outputs are out of smem
+        if (tid == 0) s_group = atomicAdd(a.work_counter, 1);
+        __syncthreads();
+        const long long group = s_group;
+        if (group >= n_groups) break;
+        const long long cw0 = group * per_group;
+        const int n_here = (int)min((long long)per_group, a.batch - cw0);  // codewords in this group
+
+        const long long cwA = cw0 + 2 * slot, cwB = cwA + 1;
+        const bool active = lane_ok && 2 * slot < n_here;
+        const bool has_b = lane_ok && 2 * slot + 1 < n_here;
+        if (active) load_pair(a.llr + cwA * ncw, has_b ? a.llr + cwB * ncw : nullptr, my_app, ncw, z, Z);
+        if (tid < per_group) s_flag[tid] = 0;
+        __syncthreads();
+
+        bool fin_a = !active, fin_b = !has_b;   // finished (converged and already written out, or absent)
+        c.done = !active;
+        c.cur = make_uint4(0u, 0u, 0u, 0u);
+        int it_a = 0, it_b = 0, ok_a = 0, ok_b = 0;
+
+        for (int it = 0; it < a.max_iters; ++it) {
+            const bool first = it == 0, last = it + 1 == a.max_iters;
+            UnrolledRowsH2<BG, 0, FULL>::run(a, c, first ? a.n_rows - 1 : 0, last ? a.n_rows - 1 : a.n_rows, !last);
+            if (!fin_a) it_a = it + 1;
+            if (!fin_b) it_b = it + 1;
+            if (a.early_term || (want_ok && last)) {
+                if (!c.done) {
+                    const uint32_t f = syndrome_fail_h2(a, c);
+                    if (f & 0x00008000u) s_flag[2 * slot] = 1;
+                    if (f & 0x80000000u) s_flag[2 * slot + 1] = 1;
+                }
+                __syncthreads();
+                if (!fin_a) {
+                    ok_a = s_flag[2 * slot] ? 0 : 1;
+                    if (ok_a && a.early_term) {   // converged: freeze this codeword's outputs now
+                        store_half(a, my_app, cwA, 0, ncw, K, z, Z);
+                        fin_a = true;
+                    }
+                }
+                if (!fin_b) {
+                    ok_b = s_flag[2 * slot + 1] ? 0 : 1;
+                    if (ok_b && a.early_term) {
+                        store_half(a, my_app, cwB, 1, ncw, K, z, Z);
+                        fin_b = true;
+                    }
+                }
+                c.done = fin_a && fin_b;
+                const int all_done = __syncthreads_and(c.done ? 1 : 0);  // also orders the flag reset below
+                if (tid < per_group) s_flag[tid] = 0;
+                if (a.early_term && all_done) break;
+            }
+        }
+        __syncthreads();
+
+        if (active && !fin_a) store_half(a, my_app, cwA, 0, ncw, K, z, Z);
+        if (has_b && !fin_b) store_half(a, my_app, cwB, 1, ncw, K, z, Z);
+        if (active && z == 0) {
+            if (a.iters) a.iters[cwA] = it_a;
+            if (a.ok) a.ok[cwA] = (uint8_t)ok_a;
+            if (has_b) {
+                if (a.iters) a.iters[cwB] = it_b;
+                if (a.ok) a.ok[cwB] = (uint8_t)ok_b;
+            }
+        }
+    }
+}
+
+}  // namespace nrldpc

@@ -2,6 +2,7 @@
 // Handle lifetime, table lifting, argument validation, launch configuration and the pipelined
 // host<->device path.  No CPU compute fallback exists: every entry point either launches the
 // sm_100a kernels or returns an error.
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -16,6 +17,7 @@
 #include "bg_tables.inc"
 #include "chain_kernels.cuh"
 #include "decode_kernel.cuh"
+#include "decode_kernel_h2.cuh"
 
 #define NRLDPC_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -122,7 +124,7 @@ int decode_threads(int Z) { return std::max(32, (decode_cwpc(Z) * Z + 31) / 32 *
 size_t decode_smem_bytes(const nrldpc_handle *h, int n_rows) {
     const int cwpc = decode_cwpc(h->d.Z);
     (void)n_rows;
-    return (size_t)cwpc * h->d.n_cw * 4 + (size_t)(cwpc + 1) * 4 + 16;
+    return (size_t)cwpc * h->d.n_cw * 4 + (size_t)(2 * cwpc + 1) * 4 + 16;
 }
 
 int ensure_scratch(nrldpc_handle *h, PipeSlot &s, size_t recs) {
@@ -139,17 +141,27 @@ int ensure_scratch(nrldpc_handle *h, PipeSlot &s, size_t recs) {
 int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const float *llr, int64_t batch,
                   int n_rows, uint8_t *hard, float *soft, int32_t *iters, uint8_t *ok) {
     const int Z = h->d.Z;
+    const bool h2 = h->cfg.llr_dtype == NRLDPC_F16X2;
+    // cwpc: codewords (float32) or codeword pairs (packed half) resident per CTA
     const int cwpc = decode_cwpc(Z), threads = decode_threads(Z);
-    const int64_t n_groups = (batch + cwpc - 1) / cwpc;
+    const int per_group = h2 ? 2 * cwpc : cwpc;
+    const int64_t n_groups = (batch + per_group - 1) / per_group;
     const int grid = (int)std::min<int64_t>(n_groups, (int64_t)h->num_sms * nrldpc::kDecCtasPerSm);
     const size_t smem = decode_smem_bytes(h, n_rows);
-    // variant 0: generic looped layers; 1/2: layer loop unrolled for that base graph (default)
+    // variant 0: generic looped layers (float32 only); otherwise the layer loop is unrolled for the base graph.
+    // FULL: one codeword (pair) per CTA and every thread owns a check (Z a multiple of the warp size)
     using Kern = void (*)(const nrldpc::DecArgs);
-    // FULL: one codeword per CTA and every thread owns a check (Z a multiple of the warp size)
     const bool full = cwpc == 1 && threads == Z;
-    const Kern kern = h->dec_variant == 0 ? (Kern)nrldpc::decode_nms_kernel<0, false>
-                      : h->d.bg == 1 ? (full ? (Kern)nrldpc::decode_nms_kernel<1, true> : (Kern)nrldpc::decode_nms_kernel<1, false>)
-                                     : (full ? (Kern)nrldpc::decode_nms_kernel<2, true> : (Kern)nrldpc::decode_nms_kernel<2, false>);
+    const bool bg1 = h->d.bg == 1;
+    Kern kern;
+    if (h2)
+        kern = bg1 ? (full ? (Kern)nrldpc::decode_nms_h2_kernel<1, true> : (Kern)nrldpc::decode_nms_h2_kernel<1, false>)
+                   : (full ? (Kern)nrldpc::decode_nms_h2_kernel<2, true> : (Kern)nrldpc::decode_nms_h2_kernel<2, false>);
+    else if (h->dec_variant == 0)
+        kern = (Kern)nrldpc::decode_nms_kernel<0, false>;
+    else
+        kern = bg1 ? (full ? (Kern)nrldpc::decode_nms_kernel<1, true> : (Kern)nrldpc::decode_nms_kernel<1, false>)
+                   : (full ? (Kern)nrldpc::decode_nms_kernel<2, true> : (Kern)nrldpc::decode_nms_kernel<2, false>);
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (int rc = ensure_scratch(h, s, (size_t)grid * (n_rows + 1) * nrldpc::kRecStride)) return rc;
     CUDA_TRY(h, cudaMemsetAsync(s.counter, 0, sizeof(int), stream));
@@ -158,11 +170,13 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
     a.batch = batch; a.Z = Z; a.ncols = h->d.cols; a.kcols = h->d.kcols; a.n_rows = n_rows;
     a.n_edges = h->h_row_start[n_rows]; a.max_iters = h->cfg.max_iters; a.early_term = h->cfg.early_term;
     a.cwpc = cwpc; a.alpha = h->cfg.alpha; a.l2_pin = h->l2_pin; a.one = 1;
+    a.c2v = s.c2v; a.work_counter = s.counter;
+    const uint32_t ah = __half_as_ushort(__float2half_rn(h->cfg.alpha));
+    a.alpha_h2 = ah | (ah << 16);
     if (a.smem_base != h->smem_base) {
         for (int e = 0; e < h->d.edges; ++e) a.ed[e].y += h->smem_base - a.smem_base;
         a.smem_base = h->smem_base;
     }
-    a.c2v = s.c2v; a.work_counter = s.counter;
     kern<<<grid, threads, smem, stream>>>(a);
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
@@ -284,6 +298,8 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
     const int ils = nrldpc_set_index(cfg->Z);
     if (ils < 0) return fail(nullptr, NRLDPC_EUNSUPPORTED, "Invalid lifting size.");
     if (cfg->max_iters < 1) return fail(nullptr, NRLDPC_EUNSUPPORTED, "MaximumIterationCount must be >= 1.");
+    if (cfg->llr_dtype != NRLDPC_F32 && cfg->llr_dtype != NRLDPC_F16X2)
+        return fail(nullptr, NRLDPC_EUNSUPPORTED, "llr_dtype must be NRLDPC_F32 or NRLDPC_F16X2.");
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev == 0)
@@ -422,7 +438,8 @@ NRLDPC_EXPORT int nrldpc_decode(nrldpc_t *h, const float *llr, int64_t batch, in
     if (int rc = ensure_pipe(h)) return rc;
     if (h->dev_done) CUDA_TRY(h, cudaStreamWaitEvent(h->pipe[0].stream, h->dev_done, 0));
     const int cwpc = decode_cwpc(h->d.Z);
-    const int64_t wave = (int64_t)h->num_sms * nrldpc::kDecCtasPerSm * cwpc;  // codewords per full grid
+    const int64_t wave = (int64_t)h->num_sms * nrldpc::kDecCtasPerSm * cwpc *
+                         (h->cfg.llr_dtype == NRLDPC_F16X2 ? 2 : 1);  // codewords per full grid
     int64_t chunk = wave;
     while (chunk * 2 * h->d.n_cw * 4 <= (int64_t)96 << 20 && chunk * 2 * kNumPipe <= batch) chunk *= 2;
     chunk = std::min<int64_t>(chunk, batch);

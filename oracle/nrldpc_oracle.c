@@ -15,6 +15,8 @@
  *     are restated here:
  *       orc_decode_nms  -- oracle A: layered normalized min-sum, float32, the algorithm the
  *                          CUDA kernel implements; defined by us (no reference text exists).
+ *       orc_decode_nms_f16 -- oracle A16: oracle A in IEEE binary16 arithmetic, the target of the
+ *                          packed-half kernel variant.
  *       orc_decode_bp   -- oracle B: flooding sum-product, float64, stop when all parity
  *                          checks are satisfied: MathWorks' published algorithm for
  *                          comm.LDPCDecoder as configured at NRLDPCDecoder.m:120.
@@ -267,7 +269,7 @@ ORC_API long orc_syndrome_weight(int bg, int Z, int n_rows, const uint8_t *cw) {
  *
  * Definition (ours -- the reference has no text for it):
  *   input clamp  x -> min(max(x,-LLR_MAX), LLR_MAX), NaN -> +LLR_MAX (NaN marks filler upstream,
- *                NRLDPCDecoder.m:264), LLR_MAX = 2^20: keeps inf-inf out of the recursion.
+ *                NRLDPCDecoder.m:264), LLR_MAX = 2^20: keeps inf-inf out of the recursion; -0 -> +0.
  *   schedule     base rows 0..n_rows-1 in order, all Z checks of a row independent.
  *   per check    t_e   = app[v_e] - c_e            (c_e = previous message, +0 in iteration 1)
  *                m1,m2 = two smallest |t_e| (strict '<' updates, first index wins ties)
@@ -305,6 +307,7 @@ static int decode_nms_one(int bg, int Z, int ils, int n_rows, int max_iters, int
     for (int i = 0; i < nV; ++i) {
         float x = llr[i];
         app[i] = (x != x) ? ORC_LLR_MAX : (x > ORC_LLR_MAX ? ORC_LLR_MAX : (x < -ORC_LLR_MAX ? -ORC_LLR_MAX : x));
+        app[i] += 0.0f; /* -0 -> +0: from here on no APP value is ever -0, so (app < 0) == sign bit */
     }
     int it = 0, ok = 0;
     while (it < max_iters) {
@@ -366,6 +369,133 @@ ORC_API int orc_decode_nms(int bg, int Z, int n_rows, int max_iters, int early_t
         int it = decode_nms_one(bg, Z, ils, n_rows, max_iters, early_term, alpha, vidx, llr + b * nV,
                                 hard_info + b * K, app_out ? app_out + b * nV : NULL,
                                 parity_ok ? parity_ok + b : NULL);
+        if (iters_out) iters_out[b] = it;
+    }
+    free(vidx);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * Oracle A16 -- the same layered normalized min-sum in IEEE binary16 arithmetic: the bit-exact
+ * target of the packed-half kernel (nrldpc_cfg.llr_dtype = NRLDPC_F16X2).  Ours, like oracle A.
+ *   input        x -> fp16(min(max(x,-2048),2048)), NaN -> +2048, -0 -> +0, round to nearest even
+ *   per check    t_e = fp16(app - c_e);  m1, m2 = two smallest |t_e|;
+ *                c_e' = sgn_e * fp16(alpha_h * min((|t_e| == m1 ? m2 : m1), 2048)), alpha_h = fp16(alpha);
+ *                app = fp16(t_e + c_e')
+ * Every operation is computed exactly in double (sums/products of two binary16 values are exact
+ * there) and rounded once, which is what HADD2 / HMUL2 do.  Values are kept as bit patterns.
+ * ---------------------------------------------------------------------------------------- */
+static double h2d(uint16_t h) {
+    const int s = h >> 15, e = (h >> 10) & 31, m = h & 1023;
+    double v;
+    if (e == 0) v = ldexp((double)m, -24);
+    else if (e == 31) v = m ? NAN : INFINITY;
+    else v = ldexp((double)(m + 1024), e - 25);
+    return s ? -v : v;
+}
+
+static uint16_t d2h(double x) {
+    uint64_t b; memcpy(&b, &x, 8);
+    const uint16_t sign = (uint16_t)((b >> 48) & 0x8000u);
+    const double ax = fabs(x);
+    if (ax != ax) return (uint16_t)(sign | 0x7e00u);
+    if (ax >= 65520.0) return (uint16_t)(sign | 0x7c00u);       /* >= halfway to 2^16: overflows to inf */
+    if (ax == 0.0) return sign;
+    int e = ilogb(ax);
+    if (e < -14) e = -14;                                       /* subnormal range: fixed quantum 2^-24 */
+    const double q = rint(ldexp(ax, 10 - e));                   /* RNE (default rounding mode), exact scaling */
+    double v = ldexp(q, e - 10);
+    if (v == 0.0) return sign;
+    int ev = ilogb(v);
+    if (ev < -14) return (uint16_t)(sign | (uint16_t)ldexp(v, 24));
+    const int m = (int)ldexp(v, 10 - ev) - 1024;
+    return (uint16_t)(sign | ((ev + 15) << 10) | m);
+}
+
+/* test hooks: the binary16 rounding / widening used by oracle A16 (checked against numpy.float16) */
+ORC_API void orc_f16_round(const double *x, long n, uint16_t *out) { for (long i = 0; i < n; ++i) out[i] = d2h(x[i]); }
+ORC_API void orc_f16_widen(const uint16_t *h, long n, double *out) { for (long i = 0; i < n; ++i) out[i] = h2d(h[i]); }
+
+#define ORC_H_LLR_MAX 2048.0f
+#define ORC_H_MSG_CAP 0x6800u /* 2048 */
+
+static int decode_nms_f16_one(int bg, int Z, int ils, int n_rows, int max_iters, int early_term, float alpha,
+                              const int *vidx, const float *llr, uint8_t *hard_info, float *app_out, uint8_t *parity_ok) {
+    int R, C, Kc, E;
+    bg_dims(bg, &R, &C, &Kc, &E);
+    const unsigned char *er = bg_row(bg);
+    int row_start[47];
+    for (int r = 0, e = 0; r <= R; ++r) { while (e < E && er[e] < r) ++e; row_start[r] = e; }
+    const int nV = C * Z;
+    uint16_t *app = (uint16_t *)malloc(sizeof(uint16_t) * nV);
+    uint16_t *c2v = (uint16_t *)calloc((size_t)E * Z, sizeof(uint16_t));
+    const double alpha_h = h2d(d2h((double)alpha));
+    for (int i = 0; i < nV; ++i) {
+        float x = llr[i];
+        x = (x != x) ? ORC_H_LLR_MAX : (x > ORC_H_LLR_MAX ? ORC_H_LLR_MAX : (x < -ORC_H_LLR_MAX ? -ORC_H_LLR_MAX : x));
+        x += 0.0f;
+        app[i] = d2h((double)x);
+    }
+    int it = 0, ok = 0;
+    while (it < max_iters) {
+        for (int r = 0; r < n_rows; ++r) {
+            const int e0 = row_start[r], deg = row_start[r + 1] - e0;
+            for (int z = 0; z < Z; ++z) {
+                uint16_t t[32]; int v[32];
+                uint16_t m1 = 0x7c00u, m2 = 0x7c00u, sgn = 0; /* +inf; non-negative patterns order like integers */
+                for (int k = 0; k < deg; ++k) {
+                    const int e = e0 + k;
+                    v[k] = vidx[(size_t)e * Z + z];
+                    t[k] = d2h(h2d(app[v[k]]) - h2d(c2v[(size_t)e * Z + z]));
+                    const uint16_t a = t[k] & 0x7fffu;
+                    if (a < m1) { m2 = m1; m1 = a; } else if (a < m2) { m2 = a; }
+                    sgn ^= t[k] & 0x8000u;
+                }
+                const uint16_t m1c = m1 < ORC_H_MSG_CAP ? m1 : ORC_H_MSG_CAP, m2c = m2 < ORC_H_MSG_CAP ? m2 : ORC_H_MSG_CAP;
+                const uint16_t m1s = d2h(alpha_h * h2d(m1c)), m2s = d2h(alpha_h * h2d(m2c));
+                for (int k = 0; k < deg; ++k) {
+                    const uint16_t mag = ((t[k] & 0x7fffu) == m1) ? m2s : m1s;
+                    const uint16_t c = (uint16_t)(mag ^ sgn ^ (t[k] & 0x8000u));
+                    c2v[(size_t)(e0 + k) * Z + z] = c;
+                    app[v[k]] = d2h(h2d(t[k]) + h2d(c));
+                }
+            }
+        }
+        ++it;
+        if (early_term || it == max_iters) {
+            ok = 1;
+            for (int r = 0; r < n_rows && ok; ++r)
+                for (int z = 0; z < Z; ++z) {
+                    int par = 0;
+                    for (int e = row_start[r]; e < row_start[r + 1]; ++e) par ^= h2d(app[vidx[(size_t)e * Z + z]]) < 0.0;
+                    if (par) { ok = 0; break; }
+                }
+            if (early_term && ok) break;
+        }
+    }
+    for (int k = 0; k < Kc * Z; ++k) hard_info[k] = h2d(app[k]) < 0.0;
+    if (app_out) for (int i = 0; i < nV; ++i) app_out[i] = (float)h2d(app[i]);
+    if (parity_ok) *parity_ok = (uint8_t)ok;
+    free(app); free(c2v);
+    return it;
+}
+
+ORC_API int orc_decode_nms_f16(int bg, int Z, int n_rows, int max_iters, int early_term, float alpha,
+                               const float *llr, long batch, uint8_t *hard_info, float *app_out,
+                               int32_t *iters_out, uint8_t *parity_ok, int n_threads) {
+    int R, C, Kc, E, ils = orc_set_index(Z);
+    if ((bg != 1 && bg != 2) || ils < 0 || max_iters < 1) return -1;
+    bg_dims(bg, &R, &C, &Kc, &E);
+    if (n_rows <= 0 || n_rows > R) n_rows = R;
+    if (n_rows < 4) return -1;
+    if (n_threads < 1) n_threads = 1;
+    const long nV = (long)C * Z, K = (long)Kc * Z;
+    int *vidx = build_vidx(bg, Z, ils);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
+    for (long b = 0; b < batch; ++b) {
+        int it = decode_nms_f16_one(bg, Z, ils, n_rows, max_iters, early_term, alpha, vidx, llr + b * nV,
+                                    hard_info + b * K, app_out ? app_out + b * nV : NULL,
+                                    parity_ok ? parity_ok + b : NULL);
         if (iters_out) iters_out[b] = it;
     }
     free(vidx);

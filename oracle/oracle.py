@@ -104,8 +104,9 @@ def syndrome_weight(bg, Z, cw, n_rows=0):
 
 
 def decode_nms(bg, Z, llr, max_iters=8, early_term=False, alpha=0.75, n_rows=0, want_app=True,
-               n_threads=None):
-    """Oracle A (layered NMS, f32).  llr: [batch, cols*Z] float32 in cw_tilde layout."""
+               n_threads=None, f16=False):
+    """Oracle A (layered NMS, f32; f16=True: oracle A16, binary16 arithmetic).
+    llr: [batch, cols*Z] float32 in cw_tilde layout."""
     llr = np.ascontiguousarray(llr, dtype=np.float32)
     d = dims(bg, Z)
     llr2 = llr.reshape(-1, d["ncw"])
@@ -115,13 +116,29 @@ def decode_nms(bg, Z, llr, max_iters=8, early_term=False, alpha=0.75, n_rows=0, 
     iters = np.zeros(B, dtype=np.int32)
     ok = np.zeros(B, dtype=np.uint8)
     nt = n_threads or os.cpu_count() or 1
-    rc = lib().orc_decode_nms(bg, Z, n_rows, max_iters, int(early_term), C.c_float(alpha),
+    fn = lib().orc_decode_nms_f16 if f16 else lib().orc_decode_nms
+    rc = fn(bg, Z, n_rows, max_iters, int(early_term), C.c_float(alpha),
                               _p(llr2, C.c_float), C.c_long(B), _p(hard, C.c_uint8),
                               _p(app, C.c_float) if want_app else None, _p(iters, C.c_int32),
                               _p(ok, C.c_uint8), nt)
     if rc:
         raise RuntimeError(f"oracle decode_nms rc={rc}")
     return dict(hard=hard, app=app, iters=iters, parity_ok=ok)
+
+
+def f16_round(x):
+    """binary16 bit patterns of float64 values, as oracle A16 rounds them (round to nearest even)."""
+    x = np.ascontiguousarray(x, dtype=np.float64).ravel()
+    out = np.zeros(x.size, np.uint16)
+    lib().orc_f16_round(_p(x, C.c_double), C.c_long(x.size), _p(out, C.c_uint16))
+    return out
+
+
+def f16_widen(h):
+    h = np.ascontiguousarray(h, dtype=np.uint16).ravel()
+    out = np.zeros(h.size, np.float64)
+    lib().orc_f16_widen(_p(h, C.c_uint16), C.c_long(h.size), _p(out, C.c_double))
+    return out
 
 
 def decode_bp(bg, Z, llr, max_iters=8, n_rows=0, n_threads=None):

@@ -56,6 +56,72 @@ def test_decode_bit_exact_all_51_lifting_sizes(capi, O, bg):
             assert (out["iters"] == ref["iters"]).all() and (out["parity_ok"] == ref["parity_ok"]).all(), (bg, Z, et)
 
 
+@pytest.mark.parametrize("bg", [1, 2])
+def test_decode_f16x2_bit_exact_all_51_lifting_sizes(capi, O, bg):
+    """Packed-half kernel (two codewords per thread) against oracle A16: every (BG, Z), odd batches (a pair with a
+    missing second codeword), fixed iterations and early stop (codewords of one pair converge at different times)."""
+    rng = np.random.default_rng(300 + bg)
+    for Z in ALL_Z:
+        d = O.dims(bg, Z)
+        B = max(3, min(40, 1500 // Z)) | 1
+        E = int(d["N"] * rng.uniform(0.35, 1.0)) // 2 * 2
+        info, llr = make_llr(O, bg, Z, B, E, rng.uniform(-1.0, 3.0), rng)
+        for et in (False, True):
+            ref = O.decode_nms(bg, Z, llr, 6, early_term=et, f16=True)
+            h = capi.Handle(bg, Z, 6, et, llr_dtype=capi.F16X2)
+            out = h.decode(llr, want_soft=True)
+            h.close()
+            assert (out["hard"] == ref["hard"]).all(), (bg, Z, et)
+            assert _same_bits(out["app"], ref["app"]), (bg, Z, et)
+            assert (out["iters"] == ref["iters"]).all() and (out["parity_ok"] == ref["parity_ok"]).all(), (bg, Z, et)
+
+
+@pytest.mark.parametrize("bg,Z,rows", [(1, 384, 46), (1, 384, 5), (2, 52, 33), (2, 6, 13), (1, 30, 4), (2, 208, 20)])
+def test_decode_f16x2_special_values_and_row_trimming(capi, O, bg, Z, rows):
+    """+inf / NaN filler, zeros, -0.0, saturating and sub-resolution magnitudes in the packed-half kernel."""
+    rng = np.random.default_rng(Z + rows + 1)
+    d = O.dims(bg, Z)
+    B = 6
+    llr = (rng.normal(0, 4, (B, d["ncw"]))).astype(np.float32)
+    llr[:, :2 * Z] = 0
+    llr[:, (d["kcols"] + rows) * Z:] = 0
+    llr[0, 3 * Z:3 * Z + 17] = np.inf
+    llr[1, 3 * Z:3 * Z + 17] = np.nan
+    llr[2, 5 * Z:5 * Z + 9] = -np.inf
+    llr[3, ::7] = 0.0
+    llr[3, 1::11] = -0.0
+    llr[4, 2 * Z::5] *= 1e30
+    llr[4, 2 * Z + 1::9] *= 1e-6
+    llr[5] *= 500.0
+    for et in (False, True):
+        for alpha in (0.75, 0.8):
+            ref = O.decode_nms(bg, Z, llr, 7, early_term=et, n_rows=rows, alpha=alpha, f16=True)
+            h = capi.Handle(bg, Z, 7, et, alpha=alpha, llr_dtype=capi.F16X2)
+            out = h.decode(llr, n_rows=rows, want_soft=True)
+            h.close()
+            assert np.isfinite(out["app"]).all()
+            assert (out["hard"] == ref["hard"]).all() and _same_bits(out["app"], ref["app"])
+            assert (out["iters"] == ref["iters"]).all() and (out["parity_ok"] == ref["parity_ok"]).all()
+
+
+def test_decode_f16x2_headline_config_matches_f32_decisions(capi, O):
+    """BG1 Z=384 rate 1/3 at the benchmark operating point: the packed-half kernel equals oracle A16 bit for bit and
+    its block decisions track the float32 kernel (stated tolerance: at most 2 of 64 blocks differ)."""
+    rng = np.random.default_rng(77)
+    info, llr = make_llr(O, 1, 384, 64, 25272, -0.3, rng)
+    ref = O.decode_nms(1, 384, llr, 8, f16=True)
+    h16 = capi.Handle(1, 384, 8, False, llr_dtype=capi.F16X2)
+    out16 = h16.decode(llr, want_soft=True)
+    h16.close()
+    assert (out16["hard"] == ref["hard"]).all() and _same_bits(out16["app"], ref["app"])
+    h32 = capi.Handle(1, 384, 8, False)
+    out32 = h32.decode(llr)
+    h32.close()
+    e16 = (out16["hard"] != info).any(axis=1)
+    e32 = (out32["hard"] != info).any(axis=1)
+    assert int((e16 != e32).sum()) <= 2
+
+
 @pytest.mark.parametrize("bg,Z,rows", [(1, 384, 46), (1, 384, 5), (1, 384, 13), (2, 52, 33), (2, 6, 13), (2, 384, 42),
                                        (1, 30, 4), (2, 208, 20)])
 def test_decode_special_values_and_row_trimming(capi, O, bg, Z, rows):

@@ -116,3 +116,44 @@ def test_qpsk_map_and_llr(O):
     np.testing.assert_allclose(re, [a, a, -a, -a]); np.testing.assert_allclose(im, [a, -a, a, -a])
     llr = O.qpsk_demod(re, im, 0.5)
     np.testing.assert_allclose(llr, (1 - 2.0 * bits) * 2 * np.sqrt(2) * a / 0.5, rtol=1e-6)
+
+
+def test_f16_oracle_rounding_matches_numpy_float16(O):
+    """Oracle A16's own binary16 rounding / widening against numpy.float16 (IEEE RNE), incl. subnormals,
+    ties, overflow to inf and every finite bit pattern."""
+    rng = np.random.default_rng(5)
+    allh = np.arange(0, 0x10000, dtype=np.uint16)
+    finite = allh[(allh & 0x7c00) != 0x7c00]
+    wide = O.f16_widen(finite)
+    assert (wide == finite.view(np.float16).astype(np.float64)).all()
+    assert (O.f16_round(wide) == finite).all()
+    x = np.concatenate([rng.normal(0, s, 20000) for s in (1e-7, 1e-4, 1.0, 300.0, 3e4)])
+    # exact ties between neighbouring binary16 values, sums and 0.75 products of binary16 values
+    a = finite[rng.integers(0, finite.size, 50000)].view(np.float16).astype(np.float64)
+    b = finite[rng.integers(0, finite.size, 50000)].view(np.float16).astype(np.float64)
+    x = np.concatenate([x, (a + np.nextafter(a.astype(np.float16), np.float16(np.inf)).astype(np.float64)) / 2, a + b, a - b, 0.75 * a,
+                        [65504.0, 65519.9, 65520.0, 1e9, -65520.0, 2.0 ** -25, 2.0 ** -25 * 1.0001, 2.0 ** -24, 0.0, -0.0]])
+    with np.errstate(over="ignore"):
+        ref = x.astype(np.float16).view(np.uint16)
+    assert (O.f16_round(x) == ref).all()
+
+
+def test_f16_oracle_decodes_and_tracks_f32(O):
+    """Oracle A16 recovers the information bits at moderate SNR and agrees with oracle A on almost every block."""
+    from conftest import make_llr
+    rng = np.random.default_rng(21)
+    for bg, Z, E, esn0 in ((1, 48, 2800, 0.5), (2, 52, 2000, -1.0), (2, 6, 100, 3.5)):
+        info, llr = make_llr(O, bg, Z, 48, E, esn0, rng)
+        a = O.decode_nms(bg, Z, llr, 8, early_term=True)
+        h = O.decode_nms(bg, Z, llr, 8, early_term=True, f16=True)
+        assert np.isfinite(h["app"]).all() and np.abs(h["app"]).max() < 65504
+        ok32 = (a["hard"] == info).all(axis=1)
+        ok16 = (h["hard"] == info).all(axis=1)
+        assert ok16.mean() > 0.8 and abs(int(ok16.sum()) - int(ok32.sum())) <= 3, (bg, Z, ok16.sum(), ok32.sum())
+    # saturating inputs (+-inf, NaN filler, huge magnitudes) stay finite and decode
+    d = O.dims(2, 52)
+    info, llr = make_llr(O, 2, 52, 8, 2000, 8.0, rng)
+    llr = llr * 1e4
+    llr[:, d["K"] - 104:d["K"]] = np.inf
+    h = O.decode_nms(2, 52, llr, 8, f16=True)
+    assert np.isfinite(h["app"]).all() and np.abs(h["app"]).max() <= 2048 + 30 * 1536
