@@ -40,7 +40,14 @@ constexpr int kDecCtasPerSm = 2;
 constexpr float kLlrMax = 1048576.0f;
 constexpr int kMaxEdges = 316;
 constexpr int kMaxRows = 46;
-constexpr int kRecStride = kDecThreads;  // records per layer slot in the c2v scratch (fixed: immediate offsets)
+// c2v scratch of one CTA: 32-bit words [word index][kRecStride threads].  A layer's record is three words
+// (word index 3*slot + j); layer r >= 1 lives in slot r, layer 0 in slot n_rows, so that "the next layer's
+// record" is always the next slot, also across the iteration boundary.  The packed-half kernel keeps a
+// fourth word for its degree-19 layers (0..3) behind the slots.  296 CTAs x 222,720 B = 66 MB: small enough
+// to stay pinned in L2 (max persisting L2 on B200: 79 MB), which 16-byte records (85 MB) were measured not to be.
+constexpr int kRecStride = kDecThreads;
+constexpr int kRecSlots = kMaxRows + 1;
+constexpr int kRecWords = kRecSlots * 3 + 4;
 
 // Edge descriptor, read from the kernel-parameter constant bank:
 //   x = shift*4               (bytes): lane z reads circulant position (z + shift) mod Z
@@ -60,7 +67,7 @@ struct DecArgs {
     int one;                 // = 1 (see mad_u32)
     uint32_t smem_base;      // shared-window address of the kernel's dynamic shared memory
     uint32_t alpha_h2;       // {fp16(alpha), fp16(alpha)} for the packed-half kernel
-    uint4 *c2v;              // [grid][n_rows+1][kRecStride] {alpha*min1|sgn, alpha*min2|sgn, argmin | signbits << 5, -}
+    uint32_t *c2v;           // [grid][kRecWords][kRecStride]; float32 record = {alpha*min1|sgn, alpha*min2|sgn, argmin | signbits << 5}
     int *work_counter;
     unsigned short row_start[kMaxRows + 2];
     uint2 ed[kMaxEdges];
@@ -101,15 +108,27 @@ __device__ __forceinline__ uint64_t make_l2_policy(int pin) {
     else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
-__device__ __forceinline__ uint4 ld_rec(const uint4 *p, uint64_t pol) {
-    uint4 v;
-    asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
+__device__ __forceinline__ uint32_t ld_word(const uint32_t *p, uint64_t pol) {
+    uint32_t v;
+    asm volatile("ld.global.cg.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
     return v;
 }
-__device__ __forceinline__ void st_rec(uint4 *p, uint4 v, uint64_t pol) {
-    asm volatile("st.global.cg.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
-                 ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+__device__ __forceinline__ void st_word(uint32_t *p, uint32_t v, uint64_t pol) {
+    asm volatile("st.global.cg.L2::cache_hint.u32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(pol) : "memory");
+}
+// three-word record of `slot` in this thread's column (p = word 0 of the column)
+__device__ __forceinline__ uint4 ld_rec(const uint32_t *p, int slot, uint64_t pol) {
+    uint4 v;
+    v.x = ld_word(p + (slot * 3 + 0) * kRecStride, pol);
+    v.y = ld_word(p + (slot * 3 + 1) * kRecStride, pol);
+    v.z = ld_word(p + (slot * 3 + 2) * kRecStride, pol);
+    v.w = 0u;
+    return v;
+}
+__device__ __forceinline__ void st_rec(uint32_t *p, int slot, uint4 v, uint64_t pol) {
+    st_word(p + (slot * 3 + 0) * kRecStride, v.x, pol);
+    st_word(p + (slot * 3 + 1) * kRecStride, v.y, pol);
+    st_word(p + (slot * 3 + 2) * kRecStride, v.z, pol);
 }
 
 // Integer multiply-add whose multiplier is the kernel parameter `one` (always 1): the compiler
@@ -214,7 +233,7 @@ __device__ __forceinline__ uint4 process_row(const Lane &l, const uint2 *__restr
 // ---- pieces shared by all kernel variants --------------------------------------------------------
 struct DecCtx {
     Lane l;
-    uint4 *my_rec;   // slot 0 of this thread's record column
+    uint32_t *my_rec;   // word 0 of this thread's record column
     uint64_t pol;
     uint4 cur;
     bool done;       // this thread does no row work (inactive lane, or its codeword has converged)
@@ -274,19 +293,14 @@ __device__ __forceinline__ void store_outputs(const DecArgs &a, const float *app
     }
 }
 
-// Record slots: layer r >= 1 lives in slot r; layer 0 lives in slot n_rows, so that "the next
-// layer's record" is always the next slot, also across the iteration boundary.
-
 // ---- one full iteration over the layers: looped (generic) --------------------------------------
 __device__ __forceinline__ void iteration_looped(const DecArgs &a, DecCtx &c, const int it) {
     const bool store_rec = it + 1 < a.max_iters;
-    uint4 *rp = c.my_rec;
     for (int r = 0; r < a.n_rows; ++r) {
         // software prefetch of the next layer's record
-        uint4 *np = rp + kRecStride;
         const bool ld = (r + 1 == a.n_rows) ? store_rec : (it > 0);
         uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
-        if (ld && !c.done) nxt = ld_rec(np, c.pol);
+        if (ld && !c.done) nxt = ld_rec(c.my_rec, r + 1, c.pol);
         if (!c.done) {
             const int e0 = a.row_start[r];
             const int deg = a.row_start[r + 1] - e0;
@@ -300,10 +314,9 @@ __device__ __forceinline__ void iteration_looped(const DecArgs &a, DecCtx &c, co
 #undef NRLDPC_ROW_CASE
                 default: break;
             }
-            if (store_rec) st_rec(r == 0 ? c.my_rec + (size_t)a.n_rows * kRecStride : rp, rec, c.pol);
+            if (store_rec) st_rec(c.my_rec, r == 0 ? a.n_rows : r, rec, c.pol);
         }
         c.cur = nxt;
-        rp = np;
         __syncthreads();
     }
 }
@@ -324,9 +337,9 @@ struct UnrolledRows {
         if (FULL || !c.done) {
             // slot R+1; slot n_rows holds layer 0
             uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
-            if (R >= ld_from && R < ld_to) nxt = ld_rec(c.my_rec + (R + 1) * kRecStride, c.pol);
+            if (R >= ld_from && R < ld_to) nxt = ld_rec(c.my_rec, R + 1, c.pol);
             const uint4 rec = process_row<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur.x, c.cur.y, c.cur.z, a.alpha);
-            if (store_rec) st_rec(R == 0 ? c.my_rec + (size_t)a.n_rows * kRecStride : c.my_rec + R * kRecStride, rec, c.pol);
+            if (store_rec) st_rec(c.my_rec, R == 0 ? a.n_rows : R, rec, c.pol);
             c.cur = nxt;
         }
         __syncthreads();
@@ -369,7 +382,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
     c.l.nZ4 = 0u - (uint32_t)Z * 4u;
     c.l.slot_off = FULL ? 0u : (uint32_t)(slot * ncw) * 4u;
     c.l.one = (uint32_t)a.one;
-    c.my_rec = a.c2v + (size_t)blockIdx.x * (a.n_rows + 1) * kRecStride + tid;
+    c.my_rec = a.c2v + (size_t)blockIdx.x * (kRecWords * kRecStride) + tid;
     c.pol = make_l2_policy(a.l2_pin);
 
     while (true) {

@@ -40,11 +40,14 @@ __device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
 
 __device__ __forceinline__ float clamp_llr_h2(float x) { return __fadd_rn(fmaxf(fminf(x, kH2LlrMax), -kH2LlrMax), 0.0f); }
 
-// One check row of degree DEG for check z of a codeword pair.  Record layout (uint4):
+// One check row of degree DEG for check z of a codeword pair.  Record layout (uint4; three words
+// when DEG <= 11, i.e. every layer but the four degree-19 ones of base graph 1):
 //   x, y : alpha*min1, alpha*min2 of both codewords (packed fp16; sign bits ignored on read)
-//   z    : sign bits of the messages on edges 0..min(DEG,16)-1: edge e at bit 15-(n0-1-e) of each half
-//   w    : arg-min edge index of each codeword in bits 0..4 / 16..20 (compared as fp16 bit patterns),
-//          for DEG > 16 also the sign bits of edges 16..DEG-1 at the top of each half
+//   z    : sign bits of the messages on edges 0..min(DEG,16)-1: edge e at bit 15-(n0-1-e) of each half;
+//          DEG <= 11: also the arg-min edge index of each codeword in bits 0..3 / 16..19
+//   w    : DEG > 11 only: arg-min edge indices in bits 0..4 / 16..20 and, for DEG > 16, the sign bits of
+//          edges 16..DEG-1 at the top of each half
+// Arg-min indices are compared as fp16 bit patterns (HSET2 without flush-to-zero).
 template <int DEG, bool IDENT_LAST, bool ONE_CW>
 __device__ __forceinline__ uint4 process_row_h2(const Lane &l, const uint2 *__restrict__ ed, const uint4 rec,
                                                 const uint32_t alpha2) {
@@ -54,7 +57,8 @@ __device__ __forceinline__ uint4 process_row_h2(const Lane &l, const uint2 *__re
     uint32_t addr[DEG];
     __half2 m1 = as_h2(0u), m2 = as_h2(0u);
     uint32_t sx = 0, s0 = 0, s1 = 0;
-    const uint32_t oargs = N1 > 0 ? (rec.w & 0x001f001fu) : rec.w;
+    constexpr bool W3 = DEG <= 11;   // three-word record
+    const uint32_t oargs = W3 ? (rec.z & 0x000f000fu) : (rec.w & 0x001f001fu);
 #pragma unroll
     for (int e = 0; e < DEG; ++e) {
         const uint2 d = ed[e];
@@ -103,15 +107,15 @@ __device__ __forceinline__ uint4 process_row_h2(const Lane &l, const uint2 *__re
     const uint32_t flip = ((sx >> 15) & 0x00010001u) * 0xffffu;
     constexpr uint32_t F0 = (((1u << N0) - 1u) << (16 - N0)) * 0x00010001u;
     constexpr uint32_t F1 = N1 > 0 ? (((1u << N1) - 1u) << (16 - N1)) * 0x00010001u : 0u;
-    const uint32_t z = s0 ^ (flip & F0);
-    const uint32_t w = N1 > 0 ? (((s1 ^ flip) & F1) | args) : args;
+    const uint32_t z = (s0 ^ (flip & F0)) | (W3 ? args : 0u);
+    const uint32_t w = W3 ? 0u : (((s1 ^ flip) & F1) | args);
     return make_uint4(m1ss, m2ss, z, w);
 }
 
 // ---- pieces of the pair kernel ---------------------------------------------------------------------
 struct DecCtxH2 {
     Lane l;
-    uint4 *my_rec;
+    uint32_t *my_rec;
     uint64_t pol;
     uint4 cur;
     bool done;   // this thread does no row work (inactive lane, or both codewords of its pair are finished)
@@ -177,10 +181,21 @@ struct UnrolledRowsH2 {
         constexpr int DEG = BgShape<BG>::deg(R);
         constexpr int E0 = BgShape<BG>::start(R);
         if (FULL || !c.done) {
+            constexpr bool kW4 = DEG > 11;                                                  // this layer has a 4th word
+            constexpr bool kNextW4 = R + 1 < BgShape<BG>::kRows && BgShape<BG>::deg(R + 1 < BgShape<BG>::kRows ? R + 1 : R) > 11;
+            uint32_t *w4 = c.my_rec + kRecSlots * 3 * kRecStride;                           // [layer 0..3][kRecStride]
             uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
-            if (R >= ld_from && R < ld_to) nxt = ld_rec(c.my_rec + (R + 1) * kRecStride, c.pol);
+            if (R >= ld_from && R < ld_to) {
+                nxt = ld_rec(c.my_rec, R + 1, c.pol);
+                if (kNextW4) nxt.w = ld_word(w4 + (R + 1) * kRecStride, c.pol);
+            }
+            // layer 0's 4th word is not prefetched across the iteration boundary: fetch it on entry
+            if (R == 0 && kW4 && ld_from == 0) c.cur.w = ld_word(w4, c.pol);
             const uint4 rec = process_row_h2<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur, a.alpha_h2);
-            if (store_rec) st_rec(R == 0 ? c.my_rec + (size_t)a.n_rows * kRecStride : c.my_rec + R * kRecStride, rec, c.pol);
+            if (store_rec) {
+                st_rec(c.my_rec, R == 0 ? a.n_rows : R, rec, c.pol);
+                if (kW4) st_word(w4 + R * kRecStride, rec.w, c.pol);
+            }
             c.cur = nxt;
         }
         __syncthreads();
@@ -217,7 +232,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
     c.l.nZ4 = 0u - (uint32_t)Z * 4u;
     c.l.slot_off = FULL ? 0u : (uint32_t)(slot * ncw) * 4u;
     c.l.one = (uint32_t)a.one;
-    c.my_rec = a.c2v + (size_t)blockIdx.x * (a.n_rows + 1) * kRecStride + tid;
+    c.my_rec = a.c2v + (size_t)blockIdx.x * (kRecWords * kRecStride) + tid;
     c.pol = make_l2_policy(a.l2_pin);
     uint32_t *my_app = app + (size_t)(lane_ok ? slot : 0) * ncw;
 

@@ -47,7 +47,7 @@ struct PipeSlot {
     float *f_in = nullptr;
     size_t cap_cw = 0;          // capacity in codewords of the decode staging
     size_t cap_bytes = 0;       // capacity of the generic staging buffers
-    uint4 *c2v = nullptr;       // decode scratch (one set per slot: kernels of different slots may overlap)
+    uint32_t *c2v = nullptr;    // decode scratch (one set per slot: kernels of different slots may overlap)
     int *counter = nullptr;
     size_t scratch_recs = 0;
 };
@@ -132,7 +132,7 @@ int ensure_scratch(nrldpc_handle *h, PipeSlot &s, size_t recs) {
     if (recs <= s.scratch_recs) return 0;
     if (s.c2v) cudaFree(s.c2v);
     s.c2v = nullptr; s.scratch_recs = 0;
-    CUDA_TRY(h, cudaMalloc(&s.c2v, recs * sizeof(uint4)));
+    CUDA_TRY(h, cudaMalloc(&s.c2v, recs * sizeof(uint32_t)));
     s.scratch_recs = recs;
     return 0;
 }
@@ -146,7 +146,8 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
     const int cwpc = decode_cwpc(Z), threads = decode_threads(Z);
     const int per_group = h2 ? 2 * cwpc : cwpc;
     const int64_t n_groups = (batch + per_group - 1) / per_group;
-    const int grid = (int)std::min<int64_t>(n_groups, (int64_t)h->num_sms * nrldpc::kDecCtasPerSm);
+    int grid = (int)std::min<int64_t>(n_groups, (int64_t)h->num_sms * nrldpc::kDecCtasPerSm);
+    if (const char *v = getenv("NRLDPC_GRID_CAP")) grid = std::max(1, std::min(grid, atoi(v)));  // experiments only
     const size_t smem = decode_smem_bytes(h, n_rows);
     // variant 0: generic looped layers (float32 only); otherwise the layer loop is unrolled for the base graph.
     // FULL: one codeword (pair) per CTA and every thread owns a check (Z a multiple of the warp size)
@@ -163,7 +164,7 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
         kern = bg1 ? (full ? (Kern)nrldpc::decode_nms_kernel<1, true> : (Kern)nrldpc::decode_nms_kernel<1, false>)
                    : (full ? (Kern)nrldpc::decode_nms_kernel<2, true> : (Kern)nrldpc::decode_nms_kernel<2, false>);
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (int rc = ensure_scratch(h, s, (size_t)grid * (n_rows + 1) * nrldpc::kRecStride)) return rc;
+    if (int rc = ensure_scratch(h, s, (size_t)grid * nrldpc::kRecWords * nrldpc::kRecStride)) return rc;
     CUDA_TRY(h, cudaMemsetAsync(s.counter, 0, sizeof(int), stream));
     nrldpc::DecArgs &a = h->dec_args;  // tables were filled at create()
     a.llr = llr; a.hard = hard; a.soft = soft; a.iters = iters; a.ok = ok;
