@@ -138,6 +138,27 @@ int nrldpc_qpsk_awgn_llr(nrldpc_t *h, const uint8_t *f_bits, int64_t batch, int3
                          float variance, uint64_t seed, uint64_t stream_id, float *f_llr,
                          void *stream);
 
+/* ---- channel leg for every modulation of the reference (device memory only) --------------------
+ * Q_m = 1, 2, 4, 6, 8 <-> 'BPSK', 'QPSK', '16QAM', '64QAM', '256QAM' (NRModulator.m:47-63); bits are taken
+ * Q_m at a time, first bit = b0 of TS 38.211 section 5.1; symbols are interleaved (re, im) float32 pairs.
+ *   nrldpc_modulate    step(hMod, bits)   NRModulator.m:69-89   (the toolbox CustomSymbolMapping vectors at
+ *                      :73-81 are the TS 38.211 maps, which is what is computed here)
+ *   nrldpc_awgn        step(hChan, tx)    comm.AWGNChannel, plot_BLER_vs_SNR.m:50,105,131: adds complex noise of
+ *                      total variance `variance` in place, counter-based generator keyed (seed, stream_id, index)
+ *   nrldpc_demodulate  step(hDemod, rx)   NRDemodulator.m:72-96; method = NRLDPC_DEMOD_LLR ('Log-likelihood
+ *                      ratio', exact), NRLDPC_DEMOD_APPROX ('Approximate log-likelihood ratio', max-log) or
+ *                      NRLDPC_DEMOD_HARD ('Hard decision', outputs 0.0 / 1.0); `variance` is the Variance property
+ *   nrldpc_mod_awgn_llr  the three fused, bit-identical to calling them in sequence with the same keys */
+#define NRLDPC_DEMOD_LLR    0
+#define NRLDPC_DEMOD_APPROX 1
+#define NRLDPC_DEMOD_HARD   2
+int nrldpc_modulate(nrldpc_t *h, const uint8_t *bits, int64_t n_bits, int32_t Q_m, float *sym, void *stream);
+int nrldpc_awgn(nrldpc_t *h, float *sym, int64_t n_sym, float variance, uint64_t seed, uint64_t stream_id, void *stream);
+int nrldpc_demodulate(nrldpc_t *h, const float *sym, int64_t n_sym, int32_t Q_m, float variance, int32_t method,
+                      float *llr, void *stream);
+int nrldpc_mod_awgn_llr(nrldpc_t *h, const uint8_t *bits, int64_t n_bits, int32_t Q_m, float variance, int32_t method,
+                        uint64_t seed, uint64_t stream_id, float *llr, void *stream);
+
 /* Pinned host allocations for callers that want truly asynchronous NRLDPC_MEM_HOST transfers. */
 void *nrldpc_host_alloc(uint64_t bytes);
 void  nrldpc_host_free(void *p);

@@ -46,10 +46,11 @@ def active_rows(p: NRLDPC, E_max: int, rv_ids) -> int:
 
 class BlerSimulator:
     def __init__(self, A, R, BG, Q_m=2, rv_id_sequence=(0,), iterations=8, early_termination=True, alpha=0.75,
-                 batch=4096, seed=0, device=0, rank=0, world=1):
+                 batch=4096, seed=0, device=0, rank=0, world=1, llr_dtype=capi.F32, decision_method=capi.DEMOD_LLR):
         import torch
-        if Q_m != 2:
-            raise capi.UnsupportedParameters("the on-device channel leg implements QPSK only (Q_m = 2)")
+        if Q_m not in (1, 2, 4, 6, 8):
+            raise capi.UnsupportedParameters("Unsupported modulation")          # NRModulator.m:43
+        self.Q_m, self.method = int(Q_m), int(decision_method)
         self.torch = torch
         self.p = NRLDPC(A=A, BG=BG, G=matlab_round(A / R / Q_m) * Q_m, Q_m=Q_m)  # plot_BLER_vs_SNR.m:94
         self.p.validate_properties()
@@ -59,7 +60,7 @@ class BlerSimulator:
         self.E_r = [int(e) for e in p.E_r]
         self.n_rows = active_rows(p, max(self.E_r), self.rvs)
         p.rv_id = 0
-        self.h = capi.Handle(BG, self.Z, iterations, early_termination, alpha, device=device)
+        self.h = capi.Handle(BG, self.Z, iterations, early_termination, alpha, device=device, llr_dtype=llr_dtype)
         self.B = int(batch)
         self.rank, self.world, self.seed = rank, world, seed
         self.gen = torch.Generator(device="cuda").manual_seed(D.rank_seed(seed, rank) & 0x7FFFFFFFFFFF)
@@ -98,14 +99,18 @@ class BlerSimulator:
             self.p.rv_id = rv
             for r in range(C):
                 E = self.E_r[r]
-                rm = capi.Rm(E, int(self.p.k_0), int(self.p.N_cb), int(self.Kp), 2)
+                rm = capi.Rm(E, int(self.p.k_0), int(self.p.N_cb), int(self.Kp), self.Q_m)
                 cw_r = cw3[:, r].contiguous() if C > 1 else self.cw
                 f, fl = self.f[:, :E], self.fl[:, :E]
                 if E != self.f.shape[1]:
                     f, fl = f.contiguous(), fl.contiguous()
                 h.rate_match_raw(cw_r, B, rm, f, mem=capi.MEM_DEVICE, stream=st)
                 self.stream_id += 1
-                h.qpsk_awgn_llr_raw(f, B, E, var, D.rank_seed(self.seed, self.rank), self.stream_id, fl, stream=st)
+                if self.Q_m == 2 and self.method == capi.DEMOD_LLR and (B * E) % 4 == 0:
+                    h.qpsk_awgn_llr_raw(f, B, E, var, D.rank_seed(self.seed, self.rank), self.stream_id, fl, stream=st)
+                else:                                    # modulate + AWGN + demodulate fused, any NRModulator setting
+                    h.mod_awgn_llr_raw(f, B * E, self.Q_m, var, self.method, D.rank_seed(self.seed, self.rank),
+                                       self.stream_id, fl, stream=st)
                 if C > 1:
                     llr_r = torch.empty((B, h.n_cw), dtype=torch.float32, device="cuda")
                     hq = harq3[:, r].contiguous() if harq3 is not None else None
@@ -140,18 +145,23 @@ class BlerSimulator:
                 return tot, True
 
 
+_MOD_NAME = {1: "BPSK", 2: "QPSK", 4: "16QAM", 6: "64QAM", 8: "256QAM"}
+
+
 def sweep(A, R, BG, iterations=8, target_block_errors=100, target_BLER=1e-3, EsN0_start=0.0, EsN0_delta=0.5, seed=0,
-          rv_id_sequence=(0,), batch=4096, max_blocks=None, early_termination=True, out_dir="results", log=print):
+          rv_id_sequence=(0,), batch=4096, max_blocks=None, early_termination=True, out_dir="results", log=print,
+          Q_m=2, llr_dtype=capi.F32):
     """plot_BLER_vs_SNR.m:53-171 for one (A, R, BG): returns [(EsN0, BLER, blocks, errors, mean_iters)]."""
     rank, local_rank, world = D.init()
     import torch
     torch.cuda.set_device(local_rank)
-    sim = BlerSimulator(A, R, BG, 2, rv_id_sequence, iterations, early_termination, 0.75, batch, seed, local_rank, rank, world)
+    sim = BlerSimulator(A, R, BG, Q_m, rv_id_sequence, iterations, early_termination, 0.75, batch, seed, local_rank, rank, world,
+                        llr_dtype=llr_dtype)
     rows, esn0, bler, found = [], float(EsN0_start), 1.0, False
     fid = None
     if rank == 0 and out_dir:
         Path(out_dir).mkdir(parents=True, exist_ok=True)
-        name = f"BLER_vs_SNR_{A}_{R:g}_{BG}_QPSK_{iterations}_{target_block_errors}_{EsN0_start:g}_{seed}.txt"  # :79
+        name = f"BLER_vs_SNR_{A}_{R:g}_{BG}_{_MOD_NAME[Q_m]}_{iterations}_{target_block_errors}_{EsN0_start:g}_{seed}.txt"  # :79
         fid = open(Path(out_dir) / name, "w")
     while bler > target_BLER:
         tot, found = sim.run_point(esn0, target_block_errors, max_blocks, found)
@@ -180,9 +190,12 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=0); ap.add_argument("--rv", type=int, nargs="+", default=[0])
     ap.add_argument("--batch", type=int, default=4096); ap.add_argument("--max-blocks", type=int, default=None)
     ap.add_argument("--out-dir", default="results")
+    ap.add_argument("--modulation", default="QPSK", choices=sorted(_MOD_NAME.values()))
+    ap.add_argument("--llr-dtype", default="f32", choices=["f32", "f16x2"])
     a = ap.parse_args(argv)
+    Q_m = {v: k for k, v in _MOD_NAME.items()}[a.modulation]
     sweep(a.A, a.R, a.BG, a.iterations, a.target_block_errors, a.target_BLER, a.EsN0_start, a.EsN0_delta, a.seed, a.rv,
-          a.batch, a.max_blocks, True, a.out_dir)
+          a.batch, a.max_blocks, True, a.out_dir, Q_m=Q_m, llr_dtype=capi.F16X2 if a.llr_dtype == "f16x2" else capi.F32)
 
 
 if __name__ == "__main__":

@@ -24,6 +24,7 @@ MEM_DEVICE = 1
 LLR_MAX = 1048576.0
 F32 = 0
 F16X2 = 1
+DEMOD_LLR, DEMOD_APPROX, DEMOD_HARD = 0, 1, 2
 LLR_MAX_F16 = 2048.0
 
 # every symbol include/nrldpc_b200.h declares (tests/test_abi.py checks the header against this)
@@ -32,6 +33,7 @@ SYMBOLS = (
     "nrldpc_set_index", "nrldpc_lifting_size", "nrldpc_base_graph", "nrldpc_decode", "nrldpc_encode",
     "nrldpc_rate_match", "nrldpc_rate_recover", "nrldpc_qpsk_awgn_llr", "nrldpc_host_alloc",
     "nrldpc_host_free", "nrldpc_launch_count", "nrldpc_version",
+    "nrldpc_modulate", "nrldpc_awgn", "nrldpc_demodulate", "nrldpc_mod_awgn_llr",
 )
 
 
@@ -91,6 +93,10 @@ def load():
     lib.nrldpc_rate_match.argtypes = [vp, vp, i64, C.POINTER(Rm), vp, i32, vp]
     lib.nrldpc_rate_recover.argtypes = [vp, vp, i64, C.POINTER(Rm), vp, vp, i32, vp]
     lib.nrldpc_qpsk_awgn_llr.argtypes = [vp, vp, i64, i32, C.c_float, u64, u64, vp, vp]
+    lib.nrldpc_modulate.argtypes = [vp, vp, i64, i32, vp, vp]
+    lib.nrldpc_awgn.argtypes = [vp, vp, i64, C.c_float, u64, u64, vp]
+    lib.nrldpc_demodulate.argtypes = [vp, vp, i64, i32, C.c_float, i32, vp, vp]
+    lib.nrldpc_mod_awgn_llr.argtypes = [vp, vp, i64, i32, C.c_float, i32, u64, u64, vp, vp]
     lib.nrldpc_host_alloc.argtypes = [u64]
     lib.nrldpc_host_alloc.restype = vp
     lib.nrldpc_host_free.argtypes = [vp]
@@ -206,6 +212,20 @@ class Handle:
     def qpsk_awgn_llr_raw(self, f_bits, batch, E, variance, seed, stream_id, f_llr, stream=None):
         self._check(self._lib.nrldpc_qpsk_awgn_llr(self._h, _ptr(f_bits), int(batch), int(E), float(variance),
                                                    int(seed), int(stream_id), _ptr(f_llr), stream))
+
+    def modulate_raw(self, bits, n_bits, Q_m, sym, stream=None):
+        self._check(self._lib.nrldpc_modulate(self._h, _ptr(bits), int(n_bits), int(Q_m), _ptr(sym), stream))
+
+    def awgn_raw(self, sym, n_sym, variance, seed, stream_id, stream=None):
+        self._check(self._lib.nrldpc_awgn(self._h, _ptr(sym), int(n_sym), float(variance), int(seed), int(stream_id), stream))
+
+    def demodulate_raw(self, sym, n_sym, Q_m, variance, method, llr, stream=None):
+        self._check(self._lib.nrldpc_demodulate(self._h, _ptr(sym), int(n_sym), int(Q_m), float(variance), int(method),
+                                                _ptr(llr), stream))
+
+    def mod_awgn_llr_raw(self, bits, n_bits, Q_m, variance, method, seed, stream_id, llr, stream=None):
+        self._check(self._lib.nrldpc_mod_awgn_llr(self._h, _ptr(bits), int(n_bits), int(Q_m), float(variance), int(method),
+                                                  int(seed), int(stream_id), _ptr(llr), stream))
 
     # numpy conveniences (host memory, synchronous) ----------------------------------------------
     def decode(self, llr, n_rows=0, want_soft=False):

@@ -221,4 +221,174 @@ __global__ void __launch_bounds__(256) qpsk_awgn_llr_kernel(const uint8_t *__res
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Channel leg for every modulation of NRModulator.m / NRDemodulator.m (BPSK, QPSK, 16/64/256-QAM).
+// Constellations follow the TS 38.211 section 5.1 formulas, which the reference expresses as toolbox
+// CustomSymbolMapping vectors (NRModulator.m:73-81); they are separable: the real part is a PAM level of
+// the even bits b0,b2,.., the imaginary part of the odd bits b1,b3,.. (BPSK: both parts from b0).
+//   level(c0..c_{m-1}) = (1-2c0) * [2^(m-1) - (1-2c1) * [2^(m-2) - ... [2 - (1-2c_{m-1})]]]   (odd integer)
+//   amplitude = level * {1/sqrt2, 1/sqrt10, 1/sqrt42, 1/sqrt170}
+// Demodulation (NRDemodulator.m:72-92, DecisionMethod): exact LLR = log sum_{s:b=0} exp(-|r-s|^2/var)
+// - log sum_{s:b=1} exp(-|r-s|^2/var) (separable, so a log-sum-exp over the 2^m levels of one dimension),
+// approximate LLR = max-log, hard decision = bit of the nearest point.  BPSK / QPSK use the closed
+// forms 2*sqrt2*(x+y)/var and 2*sqrt2*x/var.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDemodExact = 0, kDemodApprox = 1, kDemodHard = 2;
+
+__host__ __device__ __forceinline__ int pam_level(const int m, const uint32_t code) {
+    // code: c0 is the most significant of the m bits
+    int r = 1;
+    for (int j = m - 1; j >= 1; --j) r = (1 << (m - j)) - (1 - 2 * (int)((code >> (m - 1 - j)) & 1u)) * r;
+    return (1 - 2 * (int)((code >> (m - 1)) & 1u)) * r;
+}
+
+__host__ __device__ __forceinline__ float qam_norm(const int Qm) {
+    return Qm <= 2 ? 0.70710678118654752440f : Qm == 4 ? 0.31622776601683793320f
+         : Qm == 6 ? 0.15430334996209191026f : 0.07669649888473704465f;
+}
+
+// bits (one per byte, b0 first) of one symbol -> (re, im)
+__device__ __forceinline__ float2 map_symbol(const uint8_t *__restrict__ b, const int Qm) {
+    const float norm = qam_norm(Qm);
+    if (Qm == 1) {
+        const float a = (b[0] & 1) ? -norm : norm;
+        return make_float2(a, a);
+    }
+    const int m = Qm >> 1;
+    uint32_t cr = 0, ci = 0;
+    for (int j = 0; j < m; ++j) {
+        cr = (cr << 1) | (b[2 * j] & 1u);
+        ci = (ci << 1) | (b[2 * j + 1] & 1u);
+    }
+    return make_float2(__fmul_rn((float)pam_level(m, cr), norm), __fmul_rn((float)pam_level(m, ci), norm));
+}
+
+// LLRs (or hard bits) of the m bits carried by one dimension; out[j] belongs to c_j
+template <int M>
+__device__ __forceinline__ void pam_demod(const float x, const float inv_var, const float norm, const int method, float *out) {
+    float d[1 << M];
+#pragma unroll
+    for (int l = 0; l < (1 << M); ++l) {
+        const float diff = __fsub_rn(x, __fmul_rn((float)pam_level(M, (uint32_t)l), norm));
+        d[l] = -__fmul_rn(__fmul_rn(diff, diff), inv_var);
+    }
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int l = 0; l < (1 << M); ++l) {
+            if ((l >> (M - 1 - j)) & 1) m1 = fmaxf(m1, d[l]);
+            else m0 = fmaxf(m0, d[l]);
+        }
+        float v;
+        if (method == kDemodHard) {
+            v = m1 > m0 ? 1.0f : 0.0f;
+        } else if (method == kDemodApprox) {
+            v = __fsub_rn(m0, m1);
+        } else {
+            float s0 = 0.0f, s1 = 0.0f;
+#pragma unroll
+            for (int l = 0; l < (1 << M); ++l) {
+                if ((l >> (M - 1 - j)) & 1) s1 += expf(d[l] - m1);
+                else s0 += expf(d[l] - m0);
+            }
+            v = (m0 - m1) + (logf(s0) - logf(s1));
+        }
+        out[j] = v;
+    }
+}
+
+// one received symbol -> Qm outputs in bit order b0..b_{Qm-1}
+__device__ __forceinline__ void demod_symbol(const float2 r, const int Qm, const float inv_var, const int method, float *__restrict__ out) {
+    const float norm = qam_norm(Qm);
+    if (Qm <= 2) {
+        const float gain = __fmul_rn(2.8284271247461900976f, inv_var);
+        if (Qm == 1) {
+            const float v = __fmul_rn(gain, __fadd_rn(r.x, r.y));
+            out[0] = method == kDemodHard ? (v < 0.0f ? 1.0f : 0.0f) : v;
+        } else {
+            const float vx = __fmul_rn(gain, r.x), vy = __fmul_rn(gain, r.y);
+            out[0] = method == kDemodHard ? (vx < 0.0f ? 1.0f : 0.0f) : vx;
+            out[1] = method == kDemodHard ? (vy < 0.0f ? 1.0f : 0.0f) : vy;
+        }
+        return;
+    }
+    float lr[4], li[4];
+    const int m = Qm >> 1;
+    if (m == 2) { pam_demod<2>(r.x, inv_var, norm, method, lr); pam_demod<2>(r.y, inv_var, norm, method, li); }
+    else if (m == 3) { pam_demod<3>(r.x, inv_var, norm, method, lr); pam_demod<3>(r.y, inv_var, norm, method, li); }
+    else { pam_demod<4>(r.x, inv_var, norm, method, lr); pam_demod<4>(r.y, inv_var, norm, method, li); }
+    for (int j = 0; j < m; ++j) {
+        out[2 * j] = lr[j];
+        out[2 * j + 1] = li[j];
+    }
+}
+
+// complex AWGN for the symbol pair `pair` (symbols 2*pair, 2*pair+1): same keying as qpsk_awgn_llr_kernel
+__device__ __forceinline__ void pair_noise(const long long pair, const uint64_t seed, const uint64_t stream_id, float n[4]) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)stream_id, (uint32_t)(stream_id >> 32),
+                  (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    box_muller(r[0], r[1], n[0], n[1]);
+    box_muller(r[2], r[3], n[2], n[3]);
+}
+
+// NRModulator.step (NRModulator.m:87-89)
+__global__ void __launch_bounds__(256) modulate_kernel(const uint8_t *__restrict__ bits, float2 *__restrict__ sym,
+                                                       long long n_sym, int Qm) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_sym; i += (long long)gridDim.x * blockDim.x)
+        sym[i] = map_symbol(bits + i * Qm, Qm);
+}
+
+// comm.AWGNChannel in SNR mode with unit signal power (plot_BLER_vs_SNR.m:50,105): sigma = sqrt(variance/2) per dimension
+__global__ void __launch_bounds__(256) awgn_kernel(float2 *__restrict__ sym, long long n_sym, float sigma, uint64_t seed,
+                                                   uint64_t stream_id) {
+    const long long n_pairs = (n_sym + 1) >> 1;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n_pairs; p += (long long)gridDim.x * blockDim.x) {
+        float n[4];
+        pair_noise(p, seed, stream_id, n);
+        float2 a = sym[2 * p];
+        a.x = __fadd_rn(a.x, __fmul_rn(sigma, n[0]));
+        a.y = __fadd_rn(a.y, __fmul_rn(sigma, n[1]));
+        sym[2 * p] = a;
+        if (2 * p + 1 < n_sym) {
+            float2 b = sym[2 * p + 1];
+            b.x = __fadd_rn(b.x, __fmul_rn(sigma, n[2]));
+            b.y = __fadd_rn(b.y, __fmul_rn(sigma, n[3]));
+            sym[2 * p + 1] = b;
+        }
+    }
+}
+
+// NRDemodulator.step (NRDemodulator.m:90-92)
+__global__ void __launch_bounds__(256) demodulate_kernel(const float2 *__restrict__ sym, float *__restrict__ out,
+                                                         long long n_sym, int Qm, float inv_var, int method) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_sym; i += (long long)gridDim.x * blockDim.x) {
+        float v[8];
+        demod_symbol(sym[i], Qm, inv_var, method, v);
+        for (int j = 0; j < Qm; ++j) out[i * Qm + j] = v[j];
+    }
+}
+
+// the three stages fused (no symbols in HBM): bits -> LLRs, bit-identical to modulate + awgn + demodulate
+__global__ void __launch_bounds__(256) mod_awgn_demod_kernel(const uint8_t *__restrict__ bits, float *__restrict__ out,
+                                                             long long n_sym, int Qm, float sigma, float inv_var, int method,
+                                                             uint64_t seed, uint64_t stream_id) {
+    const long long n_pairs = (n_sym + 1) >> 1;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n_pairs; p += (long long)gridDim.x * blockDim.x) {
+        float n[4];
+        pair_noise(p, seed, stream_id, n);
+        for (int h = 0; h < 2; ++h) {
+            const long long i = 2 * p + h;
+            if (i >= n_sym) break;
+            float2 a = map_symbol(bits + i * Qm, Qm);
+            a.x = __fadd_rn(a.x, __fmul_rn(sigma, n[2 * h]));
+            a.y = __fadd_rn(a.y, __fmul_rn(sigma, n[2 * h + 1]));
+            float v[8];
+            demod_symbol(a, Qm, inv_var, method, v);
+            for (int j = 0; j < Qm; ++j) out[i * Qm + j] = v[j];
+        }
+    }
+}
+
 }  // namespace nrldpc

@@ -146,8 +146,6 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
     const int cwpc = decode_cwpc(Z), threads = decode_threads(Z);
     const int per_group = h2 ? 2 * cwpc : cwpc;
     const int64_t n_groups = (batch + per_group - 1) / per_group;
-    int grid = (int)std::min<int64_t>(n_groups, (int64_t)h->num_sms * nrldpc::kDecCtasPerSm);
-    if (const char *v = getenv("NRLDPC_GRID_CAP")) grid = std::max(1, std::min(grid, atoi(v)));  // experiments only
     const size_t smem = decode_smem_bytes(h, n_rows);
     // variant 0: generic looped layers (float32 only); otherwise the layer loop is unrolled for the base graph.
     // FULL: one codeword (pair) per CTA and every thread owns a check (Z a multiple of the warp size)
@@ -164,6 +162,12 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
         kern = bg1 ? (full ? (Kern)nrldpc::decode_nms_kernel<1, true> : (Kern)nrldpc::decode_nms_kernel<1, false>)
                    : (full ? (Kern)nrldpc::decode_nms_kernel<2, true> : (Kern)nrldpc::decode_nms_kernel<2, false>);
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // persistent grid: every SM filled to its occupancy (2 CTAs of 384 threads at Z = 384, more for narrower CTAs)
+    int occ = 0;
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    occ = std::max(1, std::min(occ, 4));
+    int grid = (int)std::min<int64_t>(n_groups, (int64_t)h->num_sms * occ);
+    if (const char *v = getenv("NRLDPC_GRID_CAP")) grid = std::max(1, std::min(grid, atoi(v)));  // experiments only
     if (int rc = ensure_scratch(h, s, (size_t)grid * nrldpc::kRecWords * nrldpc::kRecStride)) return rc;
     CUDA_TRY(h, cudaMemsetAsync(s.counter, 0, sizeof(int), stream));
     nrldpc::DecArgs &a = h->dec_args;  // tables were filled at create()
@@ -592,6 +596,79 @@ NRLDPC_EXPORT int nrldpc_qpsk_awgn_llr(nrldpc_t *h, const uint8_t *f_bits, int64
     const long long quads = total / 4;
     nrldpc::qpsk_awgn_llr_kernel<<<grid_for(h, quads, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         f_bits, f_llr, quads, sqrtf(0.5f * variance), 2.8284271247461900976f / variance, seed, stream_id);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Modulation / channel / demodulation for every NRModulator / NRDemodulator setting (device memory only)
+namespace {
+int check_modem(nrldpc_handle *h, int64_t n_bits, int32_t Q_m, const void *a, const void *b) {
+    if (!(Q_m == 1 || Q_m == 2 || Q_m == 4 || Q_m == 6 || Q_m == 8))
+        return fail(h, NRLDPC_EUNSUPPORTED, "Unsupported modulation");
+    if (n_bits < 0 || n_bits % Q_m) return fail(h, NRLDPC_ESHAPE, "the number of bits must be a non-negative multiple of Q_m");
+    if (n_bits && (!a || !b)) return fail(h, NRLDPC_ESHAPE, "buffers must not be NULL");
+    return 0;
+}
+}  // namespace
+
+NRLDPC_EXPORT int nrldpc_modulate(nrldpc_t *h, const uint8_t *bits, int64_t n_bits, int32_t Q_m, float *sym, void *stream) {
+    if (!h) return NRLDPC_ESHAPE;
+    if (int rc = check_modem(h, n_bits, Q_m, bits, sym)) return rc;
+    if (n_bits == 0) return 0;
+    if (reinterpret_cast<uintptr_t>(sym) & 7) return fail(h, NRLDPC_ESHAPE, "sym must be 8-byte aligned");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const long long n_sym = n_bits / Q_m;
+    nrldpc::modulate_kernel<<<grid_for(h, n_sym, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        bits, reinterpret_cast<float2 *>(sym), n_sym, Q_m);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+NRLDPC_EXPORT int nrldpc_awgn(nrldpc_t *h, float *sym, int64_t n_sym, float variance, uint64_t seed, uint64_t stream_id,
+                              void *stream) {
+    if (!h) return NRLDPC_ESHAPE;
+    if (n_sym < 0) return fail(h, NRLDPC_ESHAPE, "n_sym must be >= 0");
+    if (!(variance >= 0.0f)) return fail(h, NRLDPC_EUNSUPPORTED, "variance must be non-negative");
+    if (n_sym == 0) return 0;
+    if (!sym || (reinterpret_cast<uintptr_t>(sym) & 7)) return fail(h, NRLDPC_ESHAPE, "sym must be a non-NULL 8-byte aligned pointer");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    nrldpc::awgn_kernel<<<grid_for(h, (n_sym + 1) / 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<float2 *>(sym), n_sym, sqrtf(0.5f * variance), seed, stream_id);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+NRLDPC_EXPORT int nrldpc_demodulate(nrldpc_t *h, const float *sym, int64_t n_sym, int32_t Q_m, float variance, int32_t method,
+                                    float *llr, void *stream) {
+    if (!h) return NRLDPC_ESHAPE;
+    if (int rc = check_modem(h, n_sym < 0 ? -1 : n_sym * Q_m, Q_m, sym, llr)) return rc;
+    if (method < 0 || method > 2) return fail(h, NRLDPC_EUNSUPPORTED, "Unsupported decision method");
+    if (!(variance > 0.0f)) return fail(h, NRLDPC_EUNSUPPORTED, "variance must be positive");
+    if (n_sym == 0) return 0;
+    if (reinterpret_cast<uintptr_t>(sym) & 7) return fail(h, NRLDPC_ESHAPE, "sym must be 8-byte aligned");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    nrldpc::demodulate_kernel<<<grid_for(h, n_sym, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float2 *>(sym), llr, n_sym, Q_m, 1.0f / variance, method);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+NRLDPC_EXPORT int nrldpc_mod_awgn_llr(nrldpc_t *h, const uint8_t *bits, int64_t n_bits, int32_t Q_m, float variance,
+                                      int32_t method, uint64_t seed, uint64_t stream_id, float *llr, void *stream) {
+    if (!h) return NRLDPC_ESHAPE;
+    if (int rc = check_modem(h, n_bits, Q_m, bits, llr)) return rc;
+    if (method < 0 || method > 2) return fail(h, NRLDPC_EUNSUPPORTED, "Unsupported decision method");
+    if (!(variance > 0.0f)) return fail(h, NRLDPC_EUNSUPPORTED, "variance must be positive");
+    if (n_bits == 0) return 0;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const long long n_sym = n_bits / Q_m;
+    nrldpc::mod_awgn_demod_kernel<<<grid_for(h, (n_sym + 1) / 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        bits, llr, n_sym, Q_m, sqrtf(0.5f * variance), 1.0f / variance, method, seed, stream_id);
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
     return 0;

@@ -696,3 +696,73 @@ ORC_API void orc_qpsk_demod(const float *re, const float *im, long n_sym, float 
     const float g = 2.8284271247461900976f / variance;
     for (long i = 0; i < n_sym; ++i) { llr[2 * i] = g * re[i]; llr[2 * i + 1] = g * im[i]; }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * NRModulator.m:69-89 / NRDemodulator.m:72-96 for every Modulation value.
+ * Constellations: TS 38.211 section 5.1, which is what the toolbox CustomSymbolMapping vectors at
+ * NRModulator.m:73-81 encode (tools/make_golden_mod.py checks the two against each other and
+ * tests/golden/constellations.json holds the reference's own vectors turned into points).
+ *   BPSK   d = [(1-2b0) + j(1-2b0)]/sqrt2            QPSK  d = [(1-2b0) + j(1-2b1)]/sqrt2
+ *   16QAM  d = {(1-2b0)[2-(1-2b2)] + j(1-2b1)[2-(1-2b3)]}/sqrt10
+ *   64QAM  d = {(1-2b0)[4-(1-2b2)[2-(1-2b4)]] + j(1-2b1)[4-(1-2b3)[2-(1-2b5)]]}/sqrt42
+ *   256QAM d = {(1-2b0)[8-(1-2b2)[4-(1-2b4)[2-(1-2b6)]]] + j(1-2b1)[8-(1-2b3)[4-(1-2b5)[2-(1-2b7)]]]}/sqrt170
+ * Demodulation is the literal two-dimensional definition in double precision:
+ *   exact   L(b_k) = log sum_{s: b_k=0} exp(-|r-s|^2/var) - log sum_{s: b_k=1} exp(-|r-s|^2/var)
+ *   approx  L(b_k) = (min_{s: b_k=1} |r-s|^2 - min_{s: b_k=0} |r-s|^2)/var
+ *   hard    bits of the nearest constellation point
+ * ---------------------------------------------------------------------------------------- */
+static void orc_point(int Qm, unsigned sym, float *re, float *im) {
+    int b[8];
+    for (int k = 0; k < Qm; ++k) b[k] = (sym >> (Qm - 1 - k)) & 1; /* first bit = MSB of the symbol integer */
+    int x, y;
+    float norm;
+    switch (Qm) {
+    case 1: x = 1 - 2 * b[0]; y = x; norm = 0.70710678118654752440f; break;
+    case 2: x = 1 - 2 * b[0]; y = 1 - 2 * b[1]; norm = 0.70710678118654752440f; break;
+    case 4: x = (1 - 2 * b[0]) * (2 - (1 - 2 * b[2])); y = (1 - 2 * b[1]) * (2 - (1 - 2 * b[3])); norm = 0.31622776601683793320f; break;
+    case 6: x = (1 - 2 * b[0]) * (4 - (1 - 2 * b[2]) * (2 - (1 - 2 * b[4])));
+            y = (1 - 2 * b[1]) * (4 - (1 - 2 * b[3]) * (2 - (1 - 2 * b[5]))); norm = 0.15430334996209191026f; break;
+    default: x = (1 - 2 * b[0]) * (8 - (1 - 2 * b[2]) * (4 - (1 - 2 * b[4]) * (2 - (1 - 2 * b[6]))));
+             y = (1 - 2 * b[1]) * (8 - (1 - 2 * b[3]) * (4 - (1 - 2 * b[5]) * (2 - (1 - 2 * b[7])))); norm = 0.07669649888473704465f; break;
+    }
+    *re = (float)x * norm;
+    *im = (float)y * norm;
+}
+
+ORC_API int orc_modulate(const uint8_t *bits, long n_sym, int Qm, float *re, float *im) {
+    if (!(Qm == 1 || Qm == 2 || Qm == 4 || Qm == 6 || Qm == 8)) return -1;
+    for (long i = 0; i < n_sym; ++i) {
+        unsigned s = 0;
+        for (int k = 0; k < Qm; ++k) s = (s << 1) | (bits[i * Qm + k] & 1u);
+        orc_point(Qm, s, re + i, im + i);
+    }
+    return 0;
+}
+
+ORC_API int orc_demodulate(const float *re, const float *im, long n_sym, int Qm, double variance, int method, double *out) {
+    if (!(Qm == 1 || Qm == 2 || Qm == 4 || Qm == 6 || Qm == 8) || method < 0 || method > 2 || !(variance > 0)) return -1;
+    const int M = 1 << Qm;
+    float pr[256], pi[256];
+    for (int s = 0; s < M; ++s) orc_point(Qm, (unsigned)s, pr + s, pi + s);
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < n_sym; ++i) {
+        double d[256], dmin = INFINITY;
+        int best = 0;
+        for (int s = 0; s < M; ++s) {
+            const double dx = (double)re[i] - (double)pr[s], dy = (double)im[i] - (double)pi[s];
+            d[s] = dx * dx + dy * dy;
+            if (d[s] < dmin) { dmin = d[s]; best = s; }
+        }
+        for (int k = 0; k < Qm; ++k) {
+            const int bit = Qm - 1 - k;
+            if (method == 2) { out[i * Qm + k] = (best >> bit) & 1; continue; }
+            double m0 = INFINITY, m1 = INFINITY;
+            for (int s = 0; s < M; ++s) { if ((s >> bit) & 1) { if (d[s] < m1) m1 = d[s]; } else if (d[s] < m0) m0 = d[s]; }
+            if (method == 1) { out[i * Qm + k] = (m1 - m0) / variance; continue; }
+            double s0 = 0, s1 = 0;
+            for (int s = 0; s < M; ++s) { if ((s >> bit) & 1) s1 += exp(-(d[s] - m1) / variance); else s0 += exp(-(d[s] - m0) / variance); }
+            out[i * Qm + k] = (m1 - m0) / variance + log(s0) - log(s1);
+        }
+    }
+    return 0;
+}

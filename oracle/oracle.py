@@ -236,3 +236,27 @@ def qpsk_demod(re, im, variance):
     llr = np.zeros(2 * len(re), dtype=np.float32)
     lib().orc_qpsk_demod(_p(re, C.c_float), _p(im, C.c_float), C.c_long(len(re)), C.c_float(variance), _p(llr, C.c_float))
     return llr
+
+
+def modulate(bits, Q_m):
+    """NRModulator.step for Q_m in {1,2,4,6,8}: complex64 symbols (TS 38.211 section 5.1 maps)."""
+    bits = np.ascontiguousarray(bits, dtype=np.uint8).ravel()
+    n = bits.size // Q_m
+    re = np.zeros(n, np.float32); im = np.zeros(n, np.float32)
+    if lib().orc_modulate(_p(bits, C.c_uint8), C.c_long(n), int(Q_m), _p(re, C.c_float), _p(im, C.c_float)):
+        raise ValueError("Unsupported modulation")
+    return re + 1j * im
+
+
+METHODS = {"Log-likelihood ratio": 0, "Approximate log-likelihood ratio": 1, "Hard decision": 2}
+
+
+def demodulate(sym, Q_m, variance, method="Log-likelihood ratio"):
+    """NRDemodulator.step: float64, the literal two-dimensional definition (see nrldpc_oracle.c)."""
+    sym = np.asarray(sym).ravel()
+    re = np.ascontiguousarray(sym.real, dtype=np.float32); im = np.ascontiguousarray(sym.imag, dtype=np.float32)
+    out = np.zeros(re.size * Q_m, np.float64)
+    if lib().orc_demodulate(_p(re, C.c_float), _p(im, C.c_float), C.c_long(re.size), int(Q_m), C.c_double(variance),
+                            METHODS[method], _p(out, C.c_double)):
+        raise ValueError("Unsupported modulation / method / variance")
+    return out

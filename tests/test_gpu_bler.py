@@ -50,3 +50,28 @@ def test_bler_segmented_and_harq():
     c4, _ = four.run_batch(-1.0)
     assert c1[1] == 128 and c4[1] == 0          # rate 5/6 fails at -1 dB; four redundancy versions combine to rate ~0.21
     one.close(); four.close()
+
+
+def test_bler_higher_order_modulations_and_packed_half():
+    """Every NRModulator setting through the device loop (fused modulate + AWGN + exact-LLR kernel, Q_m-aware
+    interleaver): error-free well above threshold, all blocks lost well below it; the packed-half decoder tracks
+    the float32 one on the same noise."""
+    from ldpc_3gpp_matlab_b200 import capi
+    from ldpc_3gpp_matlab_b200.bler import BlerSimulator
+    for Q_m, hi, lo in ((1, 2.0, -8.0), (4, 9.0, -2.0), (6, 14.0, 2.0), (8, 19.0, 6.0)):
+        sim = BlerSimulator(2000, 0.5, 1, Q_m=Q_m, iterations=10, batch=128, seed=Q_m)
+        assert sim.p.G % Q_m == 0
+        c_hi, _ = sim.run_batch(hi)
+        c_lo, _ = sim.run_batch(lo)
+        assert c_hi[1] == 0 and c_lo[1] == 128, (Q_m, c_hi, c_lo)
+        sim.close()
+    a = BlerSimulator(2000, 0.5, 1, Q_m=4, iterations=8, batch=512, seed=9)
+    b = BlerSimulator(2000, 0.5, 1, Q_m=4, iterations=8, batch=512, seed=9, llr_dtype=capi.F16X2)
+    found = False
+    for esn0 in np.arange(5.6, 8.5, 0.3):            # walk both decoders through the waterfall on identical noise
+        ca, _ = a.run_batch(float(esn0))
+        cb, _ = b.run_batch(float(esn0))
+        assert abs(int(ca[1]) - int(cb[1])) <= 16, (esn0, ca, cb)
+        found |= 0 < ca[1] < 512
+    assert found
+    a.close(); b.close()

@@ -350,3 +350,68 @@ def test_small_z_high_batch_config3(capi, O):
     for rep in (0, 57, 127):
         assert (out1["hard"][rep * 512:(rep + 1) * 512] == ref["hard"]).all()
     h.close()
+
+
+@pytest.mark.parametrize("Qm", [1, 2, 4, 6, 8])
+def test_modulate_demodulate_against_oracle(capi, O, Qm):
+    """nrldpc_modulate bit-exact against the oracle map; nrldpc_demodulate (exact / max-log / hard) against the
+    float64 two-dimensional definition within 2e-3 + 2e-4*|L| (float32 log-sum-exp); the fused channel kernel is
+    bit-identical to modulate + awgn + demodulate; noise has the requested variance."""
+    import torch
+    rng = np.random.default_rng(40 + Qm)
+    n_sym = 20001
+    bits = rng.integers(0, 2, n_sym * Qm, dtype=np.uint8)
+    h = capi.Handle(2, 6, 4)
+    st = torch.cuda.current_stream().cuda_stream
+    d_bits = torch.from_numpy(bits).cuda()
+    sym = torch.empty((n_sym, 2), dtype=torch.float32, device="cuda")
+    h.modulate_raw(d_bits, bits.size, Qm, sym, stream=st)
+    ref = O.modulate(bits, Qm)
+    got = sym.cpu().numpy()
+    assert (got[:, 0] == ref.real.astype(np.float32)).all() and (got[:, 1] == ref.imag.astype(np.float32)).all()
+    for var in (0.5, 0.02):
+        noisy = sym.clone()
+        h.awgn_raw(noisy, n_sym, var, 99, 3, stream=st)
+        n = (noisy - sym).cpu().numpy().astype(np.float64)
+        assert abs(n.mean()) < 4 * np.sqrt(var / 2 / n.size) and abs(n.var() - var / 2) < 0.03 * var / 2
+        assert abs(np.mean(n[:, 0] * n[:, 1])) < 0.03 * var / 2
+        rx = noisy.cpu().numpy()
+        rxc = rx[:, 0] + 1j * rx[:, 1]
+        for name, method in (("Log-likelihood ratio", capi.DEMOD_LLR), ("Approximate log-likelihood ratio", capi.DEMOD_APPROX),
+                             ("Hard decision", capi.DEMOD_HARD)):
+            out = torch.empty(n_sym * Qm, dtype=torch.float32, device="cuda")
+            h.demodulate_raw(noisy, n_sym, Qm, var, method, out, stream=st)
+            o = out.cpu().numpy().astype(np.float64)
+            r = O.demodulate(rxc, Qm, var, name)
+            if method == capi.DEMOD_HARD:
+                assert (o != r).mean() < 1e-4        # a float32 / float64 tie-break on a decision boundary at most
+            else:
+                assert (np.abs(o - r) <= 2e-3 + 2e-4 * np.abs(r)).all(), (Qm, name, np.abs(o - r).max())
+            fused = torch.empty(n_sym * Qm, dtype=torch.float32, device="cuda")
+            h.mod_awgn_llr_raw(d_bits, bits.size, Qm, var, method, 99, 3, fused, stream=st)
+            assert torch.equal(fused.view(torch.int32), out.view(torch.int32))
+    with pytest.raises(capi.UnsupportedParameters):
+        h.modulate_raw(d_bits, 6, 3, sym, stream=st)
+    with pytest.raises(capi.NRLDPCError):
+        h.modulate_raw(d_bits, 7, 2, sym, stream=st)
+    h.close()
+
+
+def test_modem_system_objects(capi, O):
+    """NRModulator / NRDemodulator mirrors: property names, step protocol, tunable Variance, error identifier."""
+    from ldpc_3gpp_matlab_b200.modem import NRModulator, NRDemodulator
+    rng = np.random.default_rng(3)
+    for name, Qm in (("BPSK", 1), ("QPSK", 2), ("16QAM", 4), ("64QAM", 6), ("256QAM", 8)):
+        mod, dem = NRModulator(Modulation=name), NRDemodulator(Modulation=name)
+        assert mod.Q_m == Qm and dem.ModulationOrder == 1 << Qm
+        bits = rng.integers(0, 2, 120 * Qm, dtype=np.uint8)
+        tx = mod.step(bits)
+        assert np.allclose(tx, O.modulate(bits, Qm), atol=1e-7)
+        dem.Variance = 0.01
+        assert ((dem.step(tx) < 0) == (bits == 1)).all()
+        dem2 = NRDemodulator(Modulation=name, DecisionMethod="Hard decision")
+        assert (dem2.step(tx) == bits).all()
+        for o in (mod, dem, dem2):
+            o.release()
+    with pytest.raises(capi.UnsupportedParameters):
+        NRModulator(Modulation="8PSK").step(np.zeros(3, np.uint8))

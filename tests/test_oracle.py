@@ -157,3 +157,47 @@ def test_f16_oracle_decodes_and_tracks_f32(O):
     llr[:, d["K"] - 104:d["K"]] = np.inf
     h = O.decode_nms(2, 52, llr, 8, f16=True)
     assert np.isfinite(h["app"]).all() and np.abs(h["app"]).max() <= 2048 + 30 * 1536
+
+
+def test_constellations_match_reference_mapping_vectors(O):
+    """Oracle modulator (TS 38.211 formulas) against tests/golden/constellations.json, which holds the points the
+    reference's own CustomSymbolMapping vectors define (NRModulator.m:73-81; generated by tools/make_golden_mod.py)."""
+    import json
+    from pathlib import Path
+    gold = json.loads((Path(__file__).parent / "golden" / "constellations.json").read_text())
+    assert sorted(gold) == ["16QAM", "256QAM", "64QAM", "BPSK", "QPSK"]
+    for name, g in gold.items():
+        Qm, pts = g["Q_m"], np.array(g["points"])
+        M = 1 << Qm
+        bits = ((np.arange(M)[:, None] >> np.arange(Qm - 1, -1, -1)) & 1).astype(np.uint8)
+        sym = O.modulate(bits, Qm)
+        assert np.allclose(sym.real, pts[:, 0], atol=1e-7) and np.allclose(sym.imag, pts[:, 1], atol=1e-7), name
+        assert abs(np.mean(np.abs(sym) ** 2) - 1.0) < 1e-6, name      # 'Average power' normalisation
+    with pytest.raises(ValueError):
+        O.modulate(np.zeros(6, np.uint8), 3)
+
+
+def test_demodulator_oracle_properties(O):
+    """Exact LLR: closed forms for BPSK / QPSK, sign = hard decision, max-log agrees at high SNR, noiseless
+    symbols decode to their own bits for every modulation."""
+    rng = np.random.default_rng(11)
+    for Qm in (1, 2, 4, 6, 8):
+        bits = rng.integers(0, 2, 600 * Qm, dtype=np.uint8)
+        tx = O.modulate(bits, Qm)
+        hard = O.demodulate(tx, Qm, 0.1, "Hard decision")
+        assert (hard == bits).all()
+        var = 0.05
+        rx = tx + rng.normal(0, np.sqrt(var / 2), tx.size) + 1j * rng.normal(0, np.sqrt(var / 2), tx.size)
+        rx = rx.astype(np.complex64)
+        llr = O.demodulate(rx, Qm, var)
+        apx = O.demodulate(rx, Qm, var, "Approximate log-likelihood ratio")
+        hd = O.demodulate(rx, Qm, var, "Hard decision")
+        assert ((apx < 0) == (hd == 1)).all()          # max-log sign = nearest-point decision
+        assert ((llr < 0) == (hd == 1)).mean() > 0.99
+        assert np.abs(llr - apx).max() < np.log(1 << Qm) + 1e-9
+        if Qm == 1:
+            assert np.allclose(llr, 2 * np.sqrt(2) * (rx.real + rx.imag) / var, rtol=1e-6, atol=1e-6)
+        if Qm == 2:
+            ref = np.stack([rx.real, rx.imag], axis=1).ravel() * 2 * np.sqrt(2) / var
+            assert np.allclose(llr, ref, rtol=1e-6, atol=1e-6)
+            assert np.allclose(llr, O.qpsk_demod(rx.real.astype(np.float32), rx.imag.astype(np.float32), var), rtol=1e-5, atol=1e-5)
