@@ -258,6 +258,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+    phys_gpu = int(visible.split(",")[local_rank]) if visible and visible.split(",")[local_rank].isdigit() else local_rank
+    numa_bound = D.bind_to_gpu_numa_node(phys_gpu) if world > 1 else False
     stream = torch.cuda.current_stream().cuda_stream
 
     f16 = args.llr_dtype == "f16x2"
@@ -350,7 +353,8 @@ def main():
         e2e = {"value": world * B * K / dt / 1e9, "unit": "Gb/s", "h2d_bytes_per_step": B * h.n_cw * 4,
                "d2h_bytes_per_step": B * K, "ms_per_step": dt * 1e3, "steps": n_e2e,
                "timer": "host perf_counter around the synchronous host-memory C-ABI call, max over ranks",
-               "pipeline": "3 streams, chunked H2D / kernel / D2H overlap inside nrldpc_decode"}
+               "pipeline": "3 streams, chunked H2D / kernel / D2H overlap inside nrldpc_decode",
+               "numa_bound": bool(numa_bound)}
         del llr_h, hard_h
 
     # ---- roofline of the dominant (only) kernel --------------------------------------------------

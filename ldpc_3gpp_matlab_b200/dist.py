@@ -30,6 +30,27 @@ def init(backend: str | None = None):
     return rank, local_rank, world
 
 
+def bind_to_gpu_numa_node(gpu_index: int) -> bool:
+    """Pin this process to the CPUs NVML reports as local to `gpu_index`, so that the pinned host staging
+    buffers it allocates afterwards (first touch) sit on the GPU's own NUMA node: with one process per GPU the
+    host<->device copies of all ranks then do not funnel through one socket's memory controllers."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        dev = pynvml.nvmlDeviceGetHandleByIndex(int(gpu_index))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(dev, (n_cpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return True
+    except Exception:
+        pass
+    return False
+
+
 def shard_range(total: int, rank: int, world: int):
     """Contiguous [lo, hi) slice of `total` units for `rank`; sizes differ by at most one."""
     base, rem = divmod(int(total), int(world))

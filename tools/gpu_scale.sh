@@ -1,0 +1,14 @@
+#!/bin/bash
+# Multi-GPU visit: bench at N = 1, 2, 4, 8 (whatever the box has), then the config-5 sweep on all GPUs.
+mkdir -p gpurun_out
+NG=$(nvidia-smi -L | wc -l)
+echo "GPUs: $NG"
+python bench.py --gpus 1 --steps 100 --warmup 3 2>&1 | tail -1 > gpurun_out/scale_n1.json
+for n in 2 4 8; do
+  if [ $n -le $NG ]; then
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 100 --warmup 3 2>&1 | grep '^{"metric"' | tail -1 > gpurun_out/scale_n$n.json
+  fi
+done
+for f in gpurun_out/scale_n*.json; do python -c "import json,sys;d=json.load(open('$f'));print(d['n_gpus'],round(d['value'],3),round(d['ms_per_step'],4),round(d['e2e']['value'],3) if d['e2e'] else None, round(d['f16x2']['value'],3), d['clocks'])"; done
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 tools/sweep.py --out gpurun_out/sweep_${NG}gpu > gpurun_out/sweep_${NG}gpu.log 2>&1
+tail -3 gpurun_out/sweep_${NG}gpu.log
