@@ -1,7 +1,7 @@
 // chain_kernels.cuh -- companion kernels either side of the decoder: QC encoder, rate matching,
 // rate recovery (+HARQ combine, filler / puncture handling) and the QPSK/AWGN/LLR channel leg.
-// All HBM-bound byte/float streaming: coalesced accesses, one thread per output element, no
-// tensor cores.
+// All HBM-bound byte/float streaming: whole rows staged through shared memory with coalesced vector
+// accesses on the HBM side, permutations applied on chip; no tensor cores.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -14,7 +14,6 @@ namespace nrldpc {
 //   lambda_r = sum_{systematic cols} P^{s} c      (r = 0..3)
 //   P^{delta} p0 = lambda_0 + lambda_1 + lambda_2 + lambda_3
 //   p1, p2, p3 by substitution down the diagonal; extension parity p_r = row r times [c p0..p3].
-// One CTA per codeword, thread z owns lane z of every circulant; bits as bytes in shared memory.
 // ------------------------------------------------------------------------------------------------
 struct EncArgs {
     const uint8_t *info;      // [batch][K]
@@ -32,69 +31,99 @@ __device__ __forceinline__ int wrap_add(int z, int s, int Z) {
     return p >= Z ? p - Z : p;
 }
 
+// Bit-sliced: a CTA encodes a slab of 32 codewords at once, codeword c living in bit c of one 32-bit word
+// per codeword position (shared memory: cols*Z words), so every XOR of the back-substitution serves 32
+// codewords and the byte-per-bit boundary costs one pack pass (uchar4 loads) and one unpack pass (uchar4
+// stores, 128 contiguous bytes per warp and codeword row).  HBM-bound: K bytes in, cols*Z bytes out.
+constexpr int kEncSlab = 32;
+
 __global__ void __launch_bounds__(384) encode_kernel(const EncArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Z = a.Z, K = a.kcols * Z, ncw = a.ncols * Z;
-    uint8_t *sys = smem_raw;                                  // [(kcols+4)*Z] info + core parity
-    uint32_t *s_ed = reinterpret_cast<uint32_t *>(smem_raw + (((a.kcols + 4) * Z + 15) & ~15));
+    uint32_t *w = reinterpret_cast<uint32_t *>(smem_raw);     // [ncw] bit-sliced codeword positions
+    uint32_t *s_ed = w + ncw;
     int *s_rs = reinterpret_cast<int *>(s_ed + a.n_edges);
-    const int tid = threadIdx.x;
-    for (int i = tid; i < a.n_edges; i += blockDim.x) s_ed[i] = a.edesc[i];
-    for (int i = tid; i <= a.n_rows; i += blockDim.x) s_rs[i] = a.row_start[i];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < a.n_edges; i += nt) s_ed[i] = a.edesc[i];
+    for (int i = tid; i <= a.n_rows; i += nt) s_rs[i] = a.row_start[i];
+    const long long n_slabs = (a.batch + kEncSlab - 1) / kEncSlab;
+    const bool vec4 = (K & 3) == 0;   // K = kcols*Z, ncw = cols*Z: multiples of 4 for every even Z (and ncw always)
 
-    for (long long b = blockIdx.x; b < a.batch; b += gridDim.x) {
+    for (long long slab = blockIdx.x; slab < n_slabs; slab += gridDim.x) {
         __syncthreads();
-        const uint8_t *src = a.info + b * K;
-        uint8_t *dst = a.cw + b * ncw;
-        for (int i = tid; i < K; i += blockDim.x) {
-            const uint8_t v = src[i] & 1;
-            sys[i] = v;
-            dst[i] = v;
+        const long long cw0 = slab * kEncSlab;
+        const int n_here = (int)min((long long)kEncSlab, a.batch - cw0);
+        // ---- pack: info bytes of the slab's codewords -> bit-sliced words
+        if (vec4) {
+            for (int q = tid; q < (K >> 2); q += nt) {
+                uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+                const uchar4 *src = reinterpret_cast<const uchar4 *>(a.info + cw0 * K) + q;
+                for (int c = 0; c < n_here; ++c) {
+                    const uchar4 v = src[(size_t)c * (K >> 2)];
+                    w0 |= (uint32_t)(v.x & 1) << c; w1 |= (uint32_t)(v.y & 1) << c;
+                    w2 |= (uint32_t)(v.z & 1) << c; w3 |= (uint32_t)(v.w & 1) << c;
+                }
+                reinterpret_cast<uint4 *>(w)[q] = make_uint4(w0, w1, w2, w3);
+            }
+        } else {
+            for (int i = tid; i < K; i += nt) {
+                uint32_t acc = 0;
+                for (int c = 0; c < n_here; ++c) acc |= (uint32_t)(a.info[(cw0 + c) * K + i] & 1) << c;
+                w[i] = acc;
+            }
         }
         __syncthreads();
-        for (int z = tid; z < Z; z += blockDim.x) {  // blockDim >= Z in practice: one pass
-            uint8_t lam[4];
+        // ---- core parity: lambda_r, p0, then substitution down the dual diagonal
+        for (int z = tid; z < Z; z += nt) {
+            uint32_t lam[4];
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                uint8_t acc = 0;
+                uint32_t acc = 0;
                 for (int e = s_rs[r]; e < s_rs[r + 1]; ++e) {
                     const uint32_t d = s_ed[e];
                     const int cb = (int)(d >> 16);
-                    if (cb < K) acc ^= sys[cb + wrap_add(z, (int)(d & 0xffffu), Z)];
+                    if (cb < K) acc ^= w[cb + wrap_add(z, (int)(d & 0xffffu), Z)];
                 }
                 lam[r] = acc;
             }
-            sys[K + wrap_add(z, a.delta, Z)] = lam[0] ^ lam[1] ^ lam[2] ^ lam[3];
-            // stash lambda for the substitution after the barrier
-            sys[K + Z + z] = lam[0];
-            sys[K + 2 * Z + z] = lam[1];
-            sys[K + 3 * Z + z] = lam[2];
+            w[K + wrap_add(z, a.delta, Z)] = lam[0] ^ lam[1] ^ lam[2] ^ lam[3];
+            w[K + Z + z] = lam[0];       // stash lambda for the substitution after the barrier
+            w[K + 2 * Z + z] = lam[1];
+            w[K + 3 * Z + z] = lam[2];
         }
         __syncthreads();
-        for (int z = tid; z < Z; z += blockDim.x) {
-            uint8_t prev = 0;
+        for (int z = tid; z < Z; z += nt) {
+            uint32_t prev = 0;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                uint8_t v = sys[K + (r + 1) * Z + z];  // lambda_r (thread-private slot)
-                if (a.s0[r] >= 0) v ^= sys[K + wrap_add(z, a.s0[r], Z)];
+                uint32_t v = w[K + (r + 1) * Z + z];  // lambda_r (thread-private slot)
+                if (a.s0[r] >= 0) v ^= w[K + wrap_add(z, a.s0[r], Z)];
                 if (r > 0) v ^= prev;
                 prev = v;
-                sys[K + (r + 1) * Z + z] = v;          // p_{r+1}[z]
+                w[K + (r + 1) * Z + z] = v;            // p_{r+1}[z]
             }
         }
         __syncthreads();
-        for (int i = tid; i < 4 * Z; i += blockDim.x) dst[K + i] = sys[K + i];
-        // extension rows: independent of each other
-        for (int z = tid; z < Z; z += blockDim.x) {
+        // ---- extension rows: independent of each other
+        for (int z = tid; z < Z; z += nt) {
             for (int r = 4; r < a.n_rows; ++r) {
-                uint8_t acc = 0;
+                uint32_t acc = 0;
                 const int e1 = s_rs[r + 1] - 1;  // last entry of an extension row is its own identity
                 for (int e = s_rs[r]; e < e1; ++e) {
                     const uint32_t d = s_ed[e];
-                    acc ^= sys[(int)(d >> 16) + wrap_add(z, (int)(d & 0xffffu), Z)];
+                    acc ^= w[(int)(d >> 16) + wrap_add(z, (int)(d & 0xffffu), Z)];
                 }
-                dst[K + r * Z + z] = acc;
+                w[K + r * Z + z] = acc;
             }
+        }
+        __syncthreads();
+        // ---- unpack: bit c of every word -> codeword row cw0 + c (four positions per 32-bit store)
+        for (int q = tid; q < (ncw >> 2); q += nt) {
+            const uint4 v = reinterpret_cast<const uint4 *>(w)[q];
+            uint32_t *dst = reinterpret_cast<uint32_t *>(a.cw + cw0 * ncw) + q;
+            for (int c = 0; c < n_here; ++c)
+                dst[(size_t)c * (ncw >> 2)] = ((v.x >> c) & 1u) | (((v.y >> c) & 1u) << 8) | (((v.z >> c) & 1u) << 16) |
+                                              (((v.w >> c) & 1u) << 24);
         }
     }
 }
@@ -167,6 +196,190 @@ __global__ void __launch_bounds__(256) rate_recover_kernel(const float *__restri
             }
         }
         out[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Shared-memory staged variants (one CTA per code block at a time): the HBM side of both kernels becomes
+// plain coalesced vector loads / stores of whole rows; the permutation (circular buffer, filler gap,
+// bit interleaver) is applied between shared memory and registers.  Used whenever a row fits in shared
+// memory; the element-wise kernels above remain as the fallback for very long E.
+// ------------------------------------------------------------------------------------------------
+template <int QM>
+__device__ __forceinline__ int rm_src(const RmGeom &g, const int n, const bool wraps) {
+    // f[n] = e[(n % Qm) * E/Qm + n / Qm]; e[k] = d[unrank((rank(k0) + k) mod Nnf)]
+    const int j = n / QM, i = n - j * QM;
+    int m = g.rank_k0 + i * g.EQ + j;
+    if (wraps) m %= g.Nnf;
+    else if (m >= g.Nnf) m -= g.Nnf;
+    return g.Z2 + rm_unrank(g, m);
+}
+
+template <int QM>
+__global__ void __launch_bounds__(256) rate_match_staged_kernel(const uint8_t *__restrict__ cw, uint8_t *__restrict__ f,
+                                                                long long batch, RmGeom g) {
+    extern __shared__ __align__(16) unsigned char rm_smem[];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const bool wraps = (long long)g.rank_k0 + g.E > 2LL * g.Nnf;   // more than one lap of the circular buffer
+    for (long long b = blockIdx.x; b < batch; b += gridDim.x) {
+        __syncthreads();
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(cw + b * g.ncw);   // ncw is a multiple of 4
+        for (int i = tid; i < (g.ncw >> 2); i += nt) reinterpret_cast<uint32_t *>(rm_smem)[i] = src[i];
+        __syncthreads();
+        uint8_t *dst = f + b * g.E;
+        const int head = (int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);    // bytes before 4-byte alignment
+        const int nq = g.E > head ? (g.E - head) >> 2 : 0;
+        for (int q = tid; q < nq; q += nt) {
+            const int n = head + 4 * q;
+            const uint32_t v = (uint32_t)rm_smem[rm_src<QM>(g, n, wraps)] | ((uint32_t)rm_smem[rm_src<QM>(g, n + 1, wraps)] << 8) |
+                               ((uint32_t)rm_smem[rm_src<QM>(g, n + 2, wraps)] << 16) | ((uint32_t)rm_smem[rm_src<QM>(g, n + 3, wraps)] << 24);
+            *reinterpret_cast<uint32_t *>(dst + n) = v;
+        }
+        for (int n = tid; n < g.E; n += nt)
+            if (n < head || n >= head + 4 * nq) dst[n] = rm_smem[rm_src<QM>(g, n, wraps)];
+    }
+}
+
+template <int QM>
+__global__ void __launch_bounds__(256) rate_recover_staged_kernel(const float *__restrict__ f, float *__restrict__ harq,
+                                                                  float *__restrict__ out, long long batch, RmGeom g) {
+    extern __shared__ __align__(16) unsigned char rm_smem[];
+    float *e_s = reinterpret_cast<float *>(rm_smem);            // de-interleaved LLRs e[k], NRDecoder.m:191-195
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (long long b = blockIdx.x; b < batch; b += gridDim.x) {
+        __syncthreads();
+        const float *fb = f + b * g.E;
+        for (int n = tid; n < g.E; n += nt) {
+            const int j = n / QM, i = n - j * QM;
+            e_s[i * g.EQ + j] = fb[n];
+        }
+        __syncthreads();
+        float4 *ob = reinterpret_cast<float4 *>(out + b * g.ncw);   // ncw*4 bytes is a multiple of 16
+        for (int q = tid; q < (g.ncw >> 2); q += nt) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int n = 4 * q + u - g.Z2;
+                float r = 0.0f;
+                if (n >= 0) {
+                    if (n >= g.F0u && n < g.F1u) {
+                        r = __int_as_float(0x7f800000);  // filler: known 0 (NRLDPCDecoder.m:264)
+                    } else if (n < g.Ncb) {
+                        int first = rm_rank(g, n) - g.rank_k0;
+                        if (first < 0) first += g.Nnf;
+                        float acc = 0.0f;
+                        for (int k = first; k < g.E; k += g.Nnf) acc = __fadd_rn(acc, e_s[k]);   // same order as :230
+                        if (harq) {
+                            float *hb = harq + b * g.N + n;
+                            acc = __fadd_rn(acc, *hb);
+                            *hb = acc;
+                        }
+                        r = acc;
+                    }
+                }
+                v[u] = r;
+            }
+            ob[q] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA variant of rate recovery: each demodulator-LLR row (E floats) is brought into shared memory by ONE
+// bulk asynchronous copy (cp.async.bulk, completion on an mbarrier), double-buffered so the copy of the
+// next code block runs under the gather / soft-combine / store of the current one.  The bit de-interleaver
+// is folded into the gather index (e[k] = f[k / (E/Qm) + (k mod E/Qm) * Qm], NRLDPCDecoder.m:191-195).
+// Needs 16-byte aligned rows (E a multiple of 4); other shapes use the kernels above.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared.b64 p, [%0], %1;\n\t"
+        "@p bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                 "r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src_gmem), "r"(bytes),
+                 "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+template <int QM>
+__global__ void __launch_bounds__(512) rate_recover_tma_kernel(const float *__restrict__ f, float *__restrict__ harq,
+                                                               float *__restrict__ out, long long batch, RmGeom g,
+                                                               int n_buf, uint32_t magic_eq) {
+    extern __shared__ __align__(128) unsigned char rr_tma_smem[];
+    __shared__ __align__(8) uint64_t bar[2];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const uint32_t row_bytes = (uint32_t)g.E * 4u;
+    float *buf[2] = {reinterpret_cast<float *>(rr_tma_smem), reinterpret_cast<float *>(rr_tma_smem + (n_buf > 1 ? row_bytes : 0))};
+    if (tid == 0) {
+        mbar_init(&bar[0], 1);
+        mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    long long b = blockIdx.x;
+    if (tid == 0 && b < batch) {
+        mbar_expect_tx(&bar[0], row_bytes);
+        bulk_g2s(buf[0], f + b * g.E, row_bytes, &bar[0]);
+    }
+    uint32_t phase[2] = {0u, 0u};
+    for (int it = 0; b < batch; b += gridDim.x, ++it) {
+        const int cur = n_buf > 1 ? (it & 1) : 0;
+        const long long nb = b + gridDim.x;
+        if (n_buf > 1 && tid == 0 && nb < batch) {          // prefetch the next row into the other buffer (free since the
+            mbar_expect_tx(&bar[cur ^ 1], row_bytes);       // barrier at the end of the previous iteration)
+            bulk_g2s(buf[cur ^ 1], f + nb * g.E, row_bytes, &bar[cur ^ 1]);
+        }
+        mbar_wait(&bar[cur], phase[cur]);
+        phase[cur] ^= 1u;
+        const float *e_f = buf[cur];
+        float4 *ob = reinterpret_cast<float4 *>(out + b * g.ncw);
+        for (int q = tid; q < (g.ncw >> 2); q += nt) {
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int n = 4 * q + u - g.Z2;
+                float r = 0.0f;
+                if (n >= 0) {
+                    if (n >= g.F0u && n < g.F1u) {
+                        r = __int_as_float(0x7f800000);  // filler: known 0 (NRLDPCDecoder.m:264)
+                    } else if (n < g.Ncb) {
+                        int first = rm_rank(g, n) - g.rank_k0;
+                        if (first < 0) first += g.Nnf;
+                        float acc = 0.0f;
+                        for (int k = first; k < g.E; k += g.Nnf) {
+                            int i = (int)__umulhi((uint32_t)k, magic_eq);      // k / EQ, one below at most
+                            int j = k - i * g.EQ;
+                            if (j >= g.EQ) { j -= g.EQ; ++i; }
+                            acc = __fadd_rn(acc, e_f[i + j * QM]);             // same addition order as :230
+                        }
+                        if (harq) {
+                            float *hb = harq + b * g.N + n;
+                            acc = __fadd_rn(acc, *hb);
+                            *hb = acc;
+                        }
+                        r = acc;
+                    }
+                }
+                v[u] = r;
+            }
+            __stcs(ob + q, make_float4(v[0], v[1], v[2], v[3]));
+        }
+        __syncthreads();   // every thread is done with buf[cur] before it is refilled
+        if (n_buf == 1 && tid == 0 && nb < batch) {
+            mbar_expect_tx(&bar[0], row_bytes);
+            bulk_g2s(buf[0], f + nb * g.E, row_bytes, &bar[0]);
+        }
     }
 }
 

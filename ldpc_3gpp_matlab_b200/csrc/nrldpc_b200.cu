@@ -69,6 +69,7 @@ struct nrldpc_handle {
     int enc_delta = 0;
     PipeSlot pipe[kNumPipe];
     int dec_smem_optin = 0;
+    int enc_smem_optin = 0;
     int dec_variant = 1;             // NRLDPC_DECODE_VARIANT=loop selects the generic looped kernel
     int l2_pin = 1;                  // NRLDPC_L2_PIN=0 drops the evict_last policy on the c2v scratch
     uint32_t smem_base = 0;          // shared-window address of dynamic shared memory (probed at create)
@@ -248,6 +249,94 @@ int make_geom(nrldpc_handle *h, const nrldpc_rm *rm, nrldpc::RmGeom *g) {
 int grid_for(const nrldpc_handle *h, long long work_items, int threads) {
     long long blocks = (work_items + threads - 1) / threads;
     return (int)std::max<long long>(1, std::min<long long>(blocks, (long long)h->num_sms * 16));
+}
+
+// rate matching / recovery launchers: shared-memory staged kernels when a row fits, element-wise otherwise
+constexpr size_t kStageSmemMax = 200 * 1024;
+
+template <int QM>
+int launch_rm_staged(nrldpc_handle *h, cudaStream_t st, const uint8_t *cw, uint8_t *f, int64_t n, const nrldpc::RmGeom &g) {
+    const size_t smem = (size_t)g.ncw;
+    CUDA_TRY(h, cudaFuncSetAttribute(nrldpc::rate_match_staged_kernel<QM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<int64_t>(n, (int64_t)h->num_sms * 8);
+    nrldpc::rate_match_staged_kernel<QM><<<grid, 256, smem, st>>>(cw, f, n, g);
+    return 0;
+}
+
+int launch_rate_match(nrldpc_handle *h, cudaStream_t st, const uint8_t *cw, uint8_t *f, int64_t n, const nrldpc::RmGeom &g) {
+    const bool aligned = (reinterpret_cast<uintptr_t>(cw) & 3) == 0;
+    int rc = 0;
+    if (aligned && (size_t)g.ncw <= kStageSmemMax) {
+        switch (g.Qm) {
+            case 1: rc = launch_rm_staged<1>(h, st, cw, f, n, g); break;
+            case 2: rc = launch_rm_staged<2>(h, st, cw, f, n, g); break;
+            case 4: rc = launch_rm_staged<4>(h, st, cw, f, n, g); break;
+            case 6: rc = launch_rm_staged<6>(h, st, cw, f, n, g); break;
+            default: rc = launch_rm_staged<8>(h, st, cw, f, n, g); break;
+        }
+        if (rc) return rc;
+    } else {
+        nrldpc::rate_match_kernel<<<grid_for(h, n * g.E, 256), 256, 0, st>>>(cw, f, n, g);
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+template <int QM>
+int launch_rr_staged(nrldpc_handle *h, cudaStream_t st, const float *f, float *harq, float *out, int64_t n, const nrldpc::RmGeom &g) {
+    const size_t smem = (size_t)g.E * sizeof(float);
+    CUDA_TRY(h, cudaFuncSetAttribute(nrldpc::rate_recover_staged_kernel<QM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<int64_t>(n, (int64_t)h->num_sms * 8);
+    nrldpc::rate_recover_staged_kernel<QM><<<grid, 256, smem, st>>>(f, harq, out, n, g);
+    return 0;
+}
+
+template <int QM>
+int launch_rr_tma(nrldpc_handle *h, cudaStream_t st, const float *f, float *harq, float *out, int64_t n, const nrldpc::RmGeom &g) {
+    const size_t row = (size_t)g.E * sizeof(float);
+    // double-buffer only while two CTAs still fit on an SM: measured on Cfg-H, two single-buffered CTAs per SM
+    // (243 us) beat one double-buffered CTA (313 us)
+    const int n_buf = 4 * row <= kStageSmemMax ? 2 : 1;
+    const size_t smem = n_buf * row;
+    CUDA_TRY(h, cudaFuncSetAttribute(nrldpc::rate_recover_tma_kernel<QM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nrldpc::rate_recover_tma_kernel<QM>, 512, smem));
+    const int grid = (int)std::min<int64_t>(n, (int64_t)h->num_sms * std::max(1, occ));
+    const uint32_t magic = (uint32_t)((1ull << 32) / (uint64_t)g.EQ);   // floor: quotient estimate is exact or one low
+    nrldpc::rate_recover_tma_kernel<QM><<<grid, 512, smem, st>>>(f, harq, out, n, g, n_buf, g.EQ == 1 ? 0xffffffffu : magic);
+    return 0;
+}
+
+int launch_rate_recover(nrldpc_handle *h, cudaStream_t st, const float *f, float *harq, float *out, int64_t n, const nrldpc::RmGeom &g) {
+    const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    int rc = 0;
+    const bool tma_ok = aligned && (g.E & 3) == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0 && g.EQ > 1 &&
+                        (size_t)g.E * sizeof(float) <= kStageSmemMax && !getenv("NRLDPC_NO_TMA");
+    if (tma_ok) {
+        switch (g.Qm) {
+            case 1: rc = launch_rr_tma<1>(h, st, f, harq, out, n, g); break;
+            case 2: rc = launch_rr_tma<2>(h, st, f, harq, out, n, g); break;
+            case 4: rc = launch_rr_tma<4>(h, st, f, harq, out, n, g); break;
+            case 6: rc = launch_rr_tma<6>(h, st, f, harq, out, n, g); break;
+            default: rc = launch_rr_tma<8>(h, st, f, harq, out, n, g); break;
+        }
+        if (rc) return rc;
+    } else if (aligned && (size_t)g.E * sizeof(float) <= kStageSmemMax) {
+        switch (g.Qm) {
+            case 1: rc = launch_rr_staged<1>(h, st, f, harq, out, n, g); break;
+            case 2: rc = launch_rr_staged<2>(h, st, f, harq, out, n, g); break;
+            case 4: rc = launch_rr_staged<4>(h, st, f, harq, out, n, g); break;
+            case 6: rc = launch_rr_staged<6>(h, st, f, harq, out, n, g); break;
+            default: rc = launch_rr_staged<8>(h, st, f, harq, out, n, g); break;
+        }
+        if (rc) return rc;
+    } else {
+        nrldpc::rate_recover_kernel<<<grid_for(h, n * g.ncw, 256), 256, 0, st>>>(f, harq, out, n, g);
+    }
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
 }
 
 }  // namespace
@@ -478,9 +567,15 @@ int launch_encode(nrldpc_handle *h, cudaStream_t st, const uint8_t *info, int64_
     a.n_rows = h->d.rows; a.n_edges = h->d.edges; a.edesc = h->edesc; a.row_start = h->row_start;
     for (int r = 0; r < 4; ++r) a.s0[r] = h->enc_s0[r];
     a.delta = h->enc_delta;
-    const int threads = std::min(384, std::max(32, (h->d.Z + 31) / 32 * 32));
-    const size_t smem = (((size_t)(h->d.kcols + 4) * h->d.Z + 15) & ~(size_t)15) + (size_t)h->d.edges * 4 + (h->d.rows + 1) * 4;
-    const int grid = (int)std::min<int64_t>(batch, (int64_t)h->num_sms * 4);
+    // one CTA per slab of 32 codewords; wide CTAs: the pack / unpack passes stride over all cols*Z positions
+    const int threads = std::min(384, std::max(64, (h->d.n_cw / 4 + 31) / 32 * 32));
+    const size_t smem = (size_t)h->d.n_cw * 4 + (size_t)h->d.edges * 4 + (h->d.rows + 1) * 4;
+    const int64_t n_slabs = (batch + nrldpc::kEncSlab - 1) / nrldpc::kEncSlab;
+    const int grid = (int)std::min<int64_t>(n_slabs, (int64_t)h->num_sms * 8);
+    if ((int)smem > h->enc_smem_optin) {
+        CUDA_TRY(h, cudaFuncSetAttribute(nrldpc::encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        h->enc_smem_optin = (int)smem;
+    }
     nrldpc::encode_kernel<<<grid, threads, smem, st>>>(a);
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
@@ -494,7 +589,11 @@ NRLDPC_EXPORT int nrldpc_encode(nrldpc_t *h, const uint8_t *info, int64_t batch,
     if (batch == 0) return 0;
     if (!info || !cw) return fail(h, NRLDPC_ESHAPE, "info and cw must not be NULL");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    if (mem == NRLDPC_MEM_DEVICE) return launch_encode(h, static_cast<cudaStream_t>(stream), info, batch, cw);
+    if (mem == NRLDPC_MEM_DEVICE) {
+        if ((reinterpret_cast<uintptr_t>(info) & 3) || (reinterpret_cast<uintptr_t>(cw) & 3))
+            return fail(h, NRLDPC_ESHAPE, "device info / cw pointers must be 4-byte aligned");
+        return launch_encode(h, static_cast<cudaStream_t>(stream), info, batch, cw);
+    }
     if (mem != NRLDPC_MEM_HOST) return fail(h, NRLDPC_ESHAPE, "mem must be NRLDPC_MEM_HOST or NRLDPC_MEM_DEVICE");
     if (int rc = ensure_pipe(h)) return rc;
     PipeSlot &s = h->pipe[0];
@@ -520,10 +619,7 @@ NRLDPC_EXPORT int nrldpc_rate_match(nrldpc_t *h, const uint8_t *cw, int64_t batc
     if (!cw || !f) return fail(h, NRLDPC_ESHAPE, "cw and f must not be NULL");
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (mem == NRLDPC_MEM_DEVICE) {
-        nrldpc::rate_match_kernel<<<grid_for(h, batch * g.E, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(cw, f, batch, g);
-        CUDA_TRY(h, cudaGetLastError());
-        h->launches += 1;
-        return 0;
+        return launch_rate_match(h, static_cast<cudaStream_t>(stream), cw, f, batch, g);
     }
     if (mem != NRLDPC_MEM_HOST) return fail(h, NRLDPC_ESHAPE, "mem must be NRLDPC_MEM_HOST or NRLDPC_MEM_DEVICE");
     if (int rc = ensure_pipe(h)) return rc;
@@ -534,9 +630,7 @@ NRLDPC_EXPORT int nrldpc_rate_match(nrldpc_t *h, const uint8_t *cw, int64_t batc
     for (int64_t off = 0; off < batch; off += chunk) {
         const int64_t n = std::min<int64_t>(chunk, batch - off);
         CUDA_TRY(h, cudaMemcpyAsync(s.bytes_in, cw + off * h->d.n_cw, (size_t)n * h->d.n_cw, cudaMemcpyHostToDevice, s.stream));
-        nrldpc::rate_match_kernel<<<grid_for(h, n * g.E, 256), 256, 0, s.stream>>>(s.bytes_in, s.bytes_out, n, g);
-        CUDA_TRY(h, cudaGetLastError());
-        h->launches += 1;
+        if (int rc = launch_rate_match(h, s.stream, s.bytes_in, s.bytes_out, n, g)) return rc;
         CUDA_TRY(h, cudaMemcpyAsync(f + off * g.E, s.bytes_out, (size_t)n * g.E, cudaMemcpyDeviceToHost, s.stream));
         CUDA_TRY(h, cudaStreamSynchronize(s.stream));
     }
@@ -553,10 +647,7 @@ NRLDPC_EXPORT int nrldpc_rate_recover(nrldpc_t *h, const float *f, int64_t batch
     if (!f || !llr_cw) return fail(h, NRLDPC_ESHAPE, "f and llr_cw must not be NULL");
     CUDA_TRY(h, cudaSetDevice(h->device));
     if (mem == NRLDPC_MEM_DEVICE) {
-        nrldpc::rate_recover_kernel<<<grid_for(h, batch * g.ncw, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(f, harq, llr_cw, batch, g);
-        CUDA_TRY(h, cudaGetLastError());
-        h->launches += 1;
-        return 0;
+        return launch_rate_recover(h, static_cast<cudaStream_t>(stream), f, harq, llr_cw, batch, g);
     }
     if (mem != NRLDPC_MEM_HOST) return fail(h, NRLDPC_ESHAPE, "mem must be NRLDPC_MEM_HOST or NRLDPC_MEM_DEVICE");
     if (int rc = ensure_pipe(h)) return rc;
@@ -570,9 +661,7 @@ NRLDPC_EXPORT int nrldpc_rate_recover(nrldpc_t *h, const float *f, int64_t batch
         CUDA_TRY(h, cudaMemcpyAsync(d_f, f + off * g.E, (size_t)n * g.E * sizeof(float), cudaMemcpyHostToDevice, s.stream));
         if (harq)
             CUDA_TRY(h, cudaMemcpyAsync(d_harq, harq + off * g.N, (size_t)n * g.N * sizeof(float), cudaMemcpyHostToDevice, s.stream));
-        nrldpc::rate_recover_kernel<<<grid_for(h, n * g.ncw, 256), 256, 0, s.stream>>>(d_f, harq ? d_harq : nullptr, d_out, n, g);
-        CUDA_TRY(h, cudaGetLastError());
-        h->launches += 1;
+        if (int rc = launch_rate_recover(h, s.stream, d_f, harq ? d_harq : nullptr, d_out, n, g)) return rc;
         CUDA_TRY(h, cudaMemcpyAsync(llr_cw + off * g.ncw, d_out, (size_t)n * g.ncw * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
         if (harq)
             CUDA_TRY(h, cudaMemcpyAsync(harq + off * g.N, d_harq, (size_t)n * g.N * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
