@@ -159,6 +159,18 @@ int nrldpc_demodulate(nrldpc_t *h, const float *sym, int64_t n_sym, int32_t Q_m,
 int nrldpc_mod_awgn_llr(nrldpc_t *h, const uint8_t *bits, int64_t n_bits, int32_t Q_m, float variance, int32_t method,
                         uint64_t seed, uint64_t stream_id, float *llr, void *stream);
 
+/* ---- CRC attach / check on device: comm.CRCGenerator / comm.CRCDetector with the polynomials of
+ * get_3gpp_crc_polynomial.m:3-17 as used at NRLDPCEncoder.m:70-89,114 and NRLDPCDecoder.m:300,336.
+ *   bits   [batch] rows of n_bits bits (one per byte), row b at bits + b*stride  (device memory)
+ *   parity nullable: the L parity bits of each row are written at parity + b*parity_stride (may alias the
+ *          tail of the same row buffer: parity = bits + n_bits, parity_stride = stride)
+ *   ok     nullable [batch]: 1 iff the remainder of the n_bits bits is zero (row with its parity attached passes) */
+#define NRLDPC_CRC16  0
+#define NRLDPC_CRC24A 1
+#define NRLDPC_CRC24B 2
+int nrldpc_crc(nrldpc_t *h, const uint8_t *bits, int64_t batch, int32_t n_bits, int64_t stride, int32_t kind,
+               uint8_t *parity, int64_t parity_stride, uint8_t *ok, void *stream);
+
 /* Pinned host allocations for callers that want truly asynchronous NRLDPC_MEM_HOST transfers. */
 void *nrldpc_host_alloc(uint64_t bytes);
 void  nrldpc_host_free(void *p);

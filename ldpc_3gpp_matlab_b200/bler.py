@@ -8,12 +8,12 @@ QPSK + AWGN + exact LLR -> rate recover (+HARQ combine over the rv_id sequence, 
 collective is a sum of four counters per SNR point.
 
 Block-error criterion.  The reference counts ~isequal(a, a_hat) with a_hat = [] whenever the TB CRC
-or a CB CRC fails (NRLDPCDecoder.m:337-339, plot_BLER_vs_SNR.m:146).  Any wrong bit among the K'
-payload+CRC bits of any code block makes a CRC fail or the payload differ, and no wrong bit means
-both pass, so "block error <=> some code block has an error in its first K' decoded bits" is the same
-event; it is evaluated on device without materialising the CRCs.  The K' bits are drawn uniformly
-(the code is linear and the channel symmetric, so BLER does not depend on the transmitted word);
-the host-side NRLDPCEncoder/NRLDPCDecoder mirrors do attach and check the real CRCs.
+or a CB CRC fails (NRLDPCDecoder.m:337-339, plot_BLER_vs_SNR.m:146).  With crc=True (default) exactly
+that is evaluated on device: TB CRC attach, segmentation with CB CRC24B, and after decoding the CB and
+TB CRC checks plus the payload comparison (nrldpc_crc).  With crc=False the K' bits of every code block
+are drawn uniformly and a block error is "some code block has an error in its first K' decoded bits",
+which is the same event except for undetected errors that leave the payload intact while corrupting
+only CRC bits (the code is linear and the channel symmetric, so BLER does not depend on the word sent).
 
 Results are written in the reference's file format ("%f\\t%e\\n" per SNR point, :165) so curves can be
 overlaid file for file.
@@ -46,11 +46,11 @@ def active_rows(p: NRLDPC, E_max: int, rv_ids) -> int:
 
 class BlerSimulator:
     def __init__(self, A, R, BG, Q_m=2, rv_id_sequence=(0,), iterations=8, early_termination=True, alpha=0.75,
-                 batch=4096, seed=0, device=0, rank=0, world=1, llr_dtype=capi.F32, decision_method=capi.DEMOD_LLR):
+                 batch=4096, seed=0, device=0, rank=0, world=1, llr_dtype=capi.F32, decision_method=capi.DEMOD_LLR, crc=True):
         import torch
         if Q_m not in (1, 2, 4, 6, 8):
             raise capi.UnsupportedParameters("Unsupported modulation")          # NRModulator.m:43
-        self.Q_m, self.method = int(Q_m), int(decision_method)
+        self.Q_m, self.method, self.use_crc = int(Q_m), int(decision_method), bool(crc)
         self.torch = torch
         self.p = NRLDPC(A=A, BG=BG, G=matlab_round(A / R / Q_m) * Q_m, Q_m=Q_m)  # plot_BLER_vs_SNR.m:94
         self.p.validate_properties()
@@ -74,6 +74,14 @@ class BlerSimulator:
         self.iters = torch.empty(n, dtype=torch.int32, device=dev)
         self.harq = torch.zeros((n, self.N), dtype=torch.float32, device=dev) if len(self.rvs) > 1 else None
         Emax = max(self.E_r)
+        # CRC bookkeeping (NRLDPC.m:297-377): payload A, transport block B_ = A + L_tb, code-block CRC L_cb when C > 1
+        self.A, self.Bsz = int(p.A), int(p.B)
+        self.tb_kind = capi.CRC_KIND[p.transport_block_CRC]
+        self.L_cb = 24 if self.C > 1 else 0
+        self.tb = torch.zeros((self.B, self.Bsz), dtype=torch.uint8, device=dev)
+        self.tb_hat = torch.zeros((self.B, self.Bsz), dtype=torch.uint8, device=dev)
+        self.cb_flag = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.tb_flag = torch.zeros(self.B, dtype=torch.uint8, device=dev)
         self.f = torch.empty((self.B, Emax), dtype=torch.uint8, device=dev)
         self.fl = torch.empty((self.B, Emax), dtype=torch.float32, device=dev)
 
@@ -85,7 +93,19 @@ class BlerSimulator:
         torch, h, B, C = self.torch, self.h, self.B, self.C
         st = torch.cuda.current_stream().cuda_stream
         var = 10 ** (-esn0_db / 10)                      # plot_BLER_vs_SNR.m:105-106
-        self.info[:, :self.Kp] = torch.randint(0, 2, (B * C, self.Kp), dtype=torch.uint8, device="cuda", generator=self.gen)
+        if self.use_crc:
+            # a -> b = [a ; TB CRC] (NRLDPCEncoder.m:70-89) -> C blocks of K'-L_cb bits + CB CRC24B (:92-124), on device
+            A, Kp, Lcb = self.A, self.Kp, self.L_cb
+            self.tb[:, :A] = torch.randint(0, 2, (B, A), dtype=torch.uint8, device="cuda", generator=self.gen)
+            h.crc_raw(self.tb, B, A, self.Bsz, self.tb_kind, parity=self.tb.data_ptr() + A, parity_stride=self.Bsz, stream=st)
+            if C == 1:
+                self.info[:, :Kp] = self.tb
+            else:
+                self.info.view(B, C, -1)[:, :, :Kp - Lcb] = self.tb.view(B, C, Kp - Lcb)
+                h.crc_raw(self.info, B * C, Kp - Lcb, self.K, capi.CRC24B, parity=self.info.data_ptr() + Kp - Lcb,
+                          parity_stride=self.K, stream=st)
+        else:
+            self.info[:, :self.Kp] = torch.randint(0, 2, (B * C, self.Kp), dtype=torch.uint8, device="cuda", generator=self.gen)
         h.encode_raw(self.info, B * C, self.cw, mem=capi.MEM_DEVICE, stream=st)
         if self.harq is not None:
             self.harq.zero_()                            # reset(hDec), plot_BLER_vs_SNR.m:122
@@ -121,7 +141,21 @@ class BlerSimulator:
                 else:
                     h.rate_recover_raw(fl, B, rm, self.harq, self.llr, mem=capi.MEM_DEVICE, stream=st)
             h.decode_raw(self.llr, B * C, self.hard, iters=self.iters, n_rows=self.n_rows, mem=capi.MEM_DEVICE, stream=st)
-            cb_ok = (self.hard[:, :self.Kp] == self.info[:, :self.Kp]).all(dim=1).view(B, C).all(dim=1)
+            if self.use_crc:
+                # a_hat = [] unless every CB CRC and the TB CRC pass (NRLDPCDecoder.m:300,336-339); a block error is
+                # ~isequal(a, a_hat) (plot_BLER_vs_SNR.m:146)
+                A, Kp, Lcb = self.A, self.Kp, self.L_cb
+                if C == 1:
+                    self.tb_hat.copy_(self.hard[:, :Kp])
+                    cb_pass = torch.ones(B, dtype=torch.bool, device="cuda")
+                else:
+                    h.crc_raw(self.hard, B * C, Kp, self.K, capi.CRC24B, ok=self.cb_flag, stream=st)
+                    cb_pass = self.cb_flag.view(B, C).bool().all(dim=1)
+                    self.tb_hat.view(B, C, Kp - Lcb).copy_(self.hard.view(B, C, -1)[:, :, :Kp - Lcb])
+                h.crc_raw(self.tb_hat, B, self.Bsz, self.Bsz, self.tb_kind, ok=self.tb_flag, stream=st)
+                cb_ok = cb_pass & self.tb_flag.bool() & (self.tb_hat[:, :A] == self.tb[:, :A]).all(dim=1)
+            else:
+                cb_ok = (self.hard[:, :self.Kp] == self.info[:, :self.Kp]).all(dim=1).view(B, C).all(dim=1)
             iters_total += int(self.iters.sum())
             ok_latched |= cb_ok
             if bool(ok_latched.all()):

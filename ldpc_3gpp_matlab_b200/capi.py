@@ -25,6 +25,8 @@ LLR_MAX = 1048576.0
 F32 = 0
 F16X2 = 1
 DEMOD_LLR, DEMOD_APPROX, DEMOD_HARD = 0, 1, 2
+CRC16, CRC24A, CRC24B = 0, 1, 2
+CRC_KIND = {"CRC16": CRC16, "CRC24A": CRC24A, "CRC24B": CRC24B}
 LLR_MAX_F16 = 2048.0
 
 # every symbol include/nrldpc_b200.h declares (tests/test_abi.py checks the header against this)
@@ -33,7 +35,7 @@ SYMBOLS = (
     "nrldpc_set_index", "nrldpc_lifting_size", "nrldpc_base_graph", "nrldpc_decode", "nrldpc_encode",
     "nrldpc_rate_match", "nrldpc_rate_recover", "nrldpc_qpsk_awgn_llr", "nrldpc_host_alloc",
     "nrldpc_host_free", "nrldpc_launch_count", "nrldpc_version",
-    "nrldpc_modulate", "nrldpc_awgn", "nrldpc_demodulate", "nrldpc_mod_awgn_llr",
+    "nrldpc_modulate", "nrldpc_awgn", "nrldpc_demodulate", "nrldpc_mod_awgn_llr", "nrldpc_crc",
 )
 
 
@@ -97,6 +99,7 @@ def load():
     lib.nrldpc_awgn.argtypes = [vp, vp, i64, C.c_float, u64, u64, vp]
     lib.nrldpc_demodulate.argtypes = [vp, vp, i64, i32, C.c_float, i32, vp, vp]
     lib.nrldpc_mod_awgn_llr.argtypes = [vp, vp, i64, i32, C.c_float, i32, u64, u64, vp, vp]
+    lib.nrldpc_crc.argtypes = [vp, vp, i64, i32, i64, i32, vp, i64, vp, vp]
     lib.nrldpc_host_alloc.argtypes = [u64]
     lib.nrldpc_host_alloc.restype = vp
     lib.nrldpc_host_free.argtypes = [vp]
@@ -226,6 +229,10 @@ class Handle:
     def mod_awgn_llr_raw(self, bits, n_bits, Q_m, variance, method, seed, stream_id, llr, stream=None):
         self._check(self._lib.nrldpc_mod_awgn_llr(self._h, _ptr(bits), int(n_bits), int(Q_m), float(variance), int(method),
                                                   int(seed), int(stream_id), _ptr(llr), stream))
+
+    def crc_raw(self, bits, batch, n_bits, stride, kind, parity=None, parity_stride=0, ok=None, stream=None):
+        self._check(self._lib.nrldpc_crc(self._h, _ptr(bits), int(batch), int(n_bits), int(stride), int(kind), _ptr(parity),
+                                         int(parity_stride), _ptr(ok), stream))
 
     # numpy conveniences (host memory, synchronous) ----------------------------------------------
     def decode(self, llr, n_rows=0, want_soft=False):

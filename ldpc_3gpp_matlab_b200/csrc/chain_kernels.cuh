@@ -604,4 +604,29 @@ __global__ void __launch_bounds__(256) mod_awgn_demod_kernel(const uint8_t *__re
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// CRC attach / check for batches of blocks: comm.CRCGenerator / comm.CRCDetector with the polynomials of
+// get_3gpp_crc_polynomial.m:3-17 (zero initial state, no reflection, no final XOR), one thread per block
+// walking its bits MSB-first through an L-bit LFSR.  parity != NULL: the L parity bits of bits[0..n_bits)
+// are written to parity (NRLDPCEncoder.m:80,114).  ok != NULL: 1 iff the remainder of all n_bits is zero,
+// i.e. a block that already carries its parity passes (NRLDPCDecoder.m:300,336).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) crc_kernel(const uint8_t *__restrict__ bits, long long batch, int n_bits, long long stride,
+                                                  uint32_t poly, int L, uint8_t *__restrict__ parity, long long parity_stride,
+                                                  uint8_t *__restrict__ ok) {
+    const uint32_t mask = L == 32 ? 0xffffffffu : ((1u << L) - 1u);
+    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < batch; b += (long long)gridDim.x * blockDim.x) {
+        const uint8_t *row = bits + b * stride;
+        uint32_t reg = 0;
+        for (int i = 0; i < n_bits; ++i) {
+            const uint32_t fb = ((reg >> (L - 1)) ^ row[i]) & 1u;
+            reg = (reg << 1) & mask;
+            if (fb) reg ^= poly;
+        }
+        if (parity)
+            for (int i = 0; i < L; ++i) parity[b * parity_stride + i] = (uint8_t)((reg >> (L - 1 - i)) & 1u);
+        if (ok) ok[b] = reg == 0 ? 1 : 0;
+    }
+}
+
 }  // namespace nrldpc

@@ -762,3 +762,26 @@ NRLDPC_EXPORT int nrldpc_mod_awgn_llr(nrldpc_t *h, const uint8_t *bits, int64_t 
     h->launches += 1;
     return 0;
 }
+
+// ------------------------------------------------------------------------------------------------
+NRLDPC_EXPORT int nrldpc_crc(nrldpc_t *h, const uint8_t *bits, int64_t batch, int32_t n_bits, int64_t stride, int32_t kind,
+                             uint8_t *parity, int64_t parity_stride, uint8_t *ok, void *stream) {
+    if (!h) return NRLDPC_ESHAPE;
+    uint32_t poly; int L;
+    switch (kind) {   // get_3gpp_crc_polynomial.m:3-17
+        case NRLDPC_CRC16: poly = 0x1021u; L = 16; break;
+        case NRLDPC_CRC24A: poly = 0x864CFBu; L = 24; break;
+        case NRLDPC_CRC24B: poly = 0x800063u; L = 24; break;
+        default: return fail(h, NRLDPC_EUNSUPPORTED, "Invalid CRC identifier.");
+    }
+    if (batch < 0 || n_bits < 0 || stride < n_bits) return fail(h, NRLDPC_ESHAPE, "batch, n_bits >= 0 and stride >= n_bits required");
+    if (batch == 0) return 0;
+    if (!bits || (!parity && !ok)) return fail(h, NRLDPC_ESHAPE, "bits and one of parity / ok must not be NULL");
+    if (parity && parity_stride < L) return fail(h, NRLDPC_ESHAPE, "parity_stride must be at least the CRC length");
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    nrldpc::crc_kernel<<<grid_for(h, batch, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(bits, batch, n_bits, stride, poly, L,
+                                                                                             parity, parity_stride, ok);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}

@@ -75,3 +75,41 @@ def test_bler_higher_order_modulations_and_packed_half():
         found |= 0 < ca[1] < 512
     assert found
     a.close(); b.close()
+
+
+def test_device_crc_matches_oracle_and_bler_criterion(O):
+    """nrldpc_crc (attach + check) against the oracle CRCs for the three 3GPP polynomials, and the CRC-based block-error
+    criterion of the device loop against the direct bit comparison on the same noise (segmented TB, C = 2)."""
+    import torch
+    from ldpc_3gpp_matlab_b200 import capi
+    from ldpc_3gpp_matlab_b200.bler import BlerSimulator
+    rng = np.random.default_rng(8)
+    h = capi.Handle(2, 2, 1)
+    st = torch.cuda.current_stream().cuda_stream
+    for name, kind, L in (("CRC16", capi.CRC16, 16), ("CRC24A", capi.CRC24A, 24), ("CRC24B", capi.CRC24B, 24)):
+        for n in (1, 7, 20, 333, 8424):
+            B, stride = 37, n + L + 5
+            bits = rng.integers(0, 2, (B, stride), dtype=np.uint8)
+            d = torch.from_numpy(bits).cuda()
+            ok = torch.zeros(B, dtype=torch.uint8, device="cuda")
+            h.crc_raw(d, B, n, stride, kind, parity=d.data_ptr() + n, parity_stride=stride, stream=st)
+            h.crc_raw(d, B, n + L, stride, kind, ok=ok, stream=st)
+            got = d.cpu().numpy()
+            for b in range(0, B, 9):
+                assert (got[b, n:n + L] == O.crc(name, bits[b, :n])).all(), (name, n, b)
+            assert bool(ok.all())
+            d[:, n // 2] ^= 1
+            h.crc_raw(d, B, n + L, stride, kind, ok=ok, stream=st)
+            assert not bool(ok.any())
+    with pytest.raises(capi.UnsupportedParameters):
+        h.crc_raw(d, 1, 8, 8, 7, ok=ok, stream=st)
+    h.close()
+    a = BlerSimulator(3842, 1 / 3, 2, iterations=8, batch=256, seed=4, crc=True)
+    b = BlerSimulator(3842, 1 / 3, 2, iterations=8, batch=256, seed=4, crc=False)
+    assert a.C == 2 and a.L_cb == 24 and a.Bsz == 3866
+    for esn0 in (-1.6, -1.3, -1.0):
+        ca, _ = a.run_batch(esn0)
+        cb, _ = b.run_batch(esn0)
+        assert ca[0] == cb[0] == 256 and ca[1] == cb[1], (esn0, ca, cb)     # symmetric decoder: same noise, same failures
+    assert 0 < ca[1] + cb[1]
+    a.close(); b.close()
