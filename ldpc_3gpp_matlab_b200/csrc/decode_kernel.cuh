@@ -239,13 +239,23 @@ struct DecCtx {
     bool done;       // this thread does no row work (inactive lane, or its codeword has converged)
 };
 
-__device__ __forceinline__ void load_group(const DecArgs &a, float *app, long long cw0, int n_here, int ncw) {
-    // the group's codewords are contiguous in HBM; ncw*4 bytes is a multiple of 16 for every (BG,Z)
-    const float4 *src = reinterpret_cast<const float4 *>(a.llr + cw0 * ncw);
+// TMA staging of a codeword group: the group's rows are contiguous in HBM, so ONE bulk asynchronous copy
+// (cp.async.bulk -> UBLKCP, completion counted on an mbarrier) brings all cols*Z circulant blocks into shared
+// memory without passing through registers; the clamp (+-LLR_MAX, NaN filler, -0) is then applied in place.
+__device__ __forceinline__ void load_group(const DecArgs &a, float *app, long long cw0, int n_here, int ncw,
+                                           uint64_t *bar, uint32_t &parity) {
+    const uint32_t bytes = (uint32_t)(n_here * ncw) * 4u;     // ncw*4 is a multiple of 16 for every (BG, Z)
+    if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses to app vs the async write
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(app, a.llr + cw0 * ncw, bytes, bar);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1u;
     float4 *dst = reinterpret_cast<float4 *>(app);
     const int n4 = (n_here * ncw) >> 2;
     for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-        float4 v = __ldcs(src + i);
+        float4 v = dst[i];
         v.x = clamp_llr(v.x); v.y = clamp_llr(v.y); v.z = clamp_llr(v.z); v.w = clamp_llr(v.w);
         dst[i] = v;
     }
@@ -367,6 +377,12 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
     float *app = reinterpret_cast<float *>(smem_raw);
     int *s_flag = reinterpret_cast<int *>(app + (size_t)a.cwpc * ncw);  // [cwpc] + work-group slot
     int &s_group = s_flag[a.cwpc];
+    uint64_t *bar = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(s_flag + a.cwpc + 1) + 7) & ~(uintptr_t)7);
+    uint32_t bar_parity = 0;
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     // the edge descriptors carry absolute shared addresses (DecArgs::ed): fail loudly if the window moved
     if ((uint32_t)__cvta_generic_to_shared(smem_raw) != a.smem_base) __trap();
 
@@ -394,7 +410,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
         const long long cw0 = group * a.cwpc;
         const int n_here = (int)min((long long)a.cwpc, a.batch - cw0);
 
-        load_group(a, app, cw0, n_here, ncw);
+        load_group(a, app, cw0, n_here, ncw, bar, bar_parity);
         if (tid < a.cwpc) s_flag[tid] = 0;
         __syncthreads();
 

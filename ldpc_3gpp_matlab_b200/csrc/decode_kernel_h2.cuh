@@ -128,6 +128,7 @@ __device__ __forceinline__ void load_pair(const float *__restrict__ rowA, const 
     const float4 *a4 = reinterpret_cast<const float4 *>(rowA);
     const float4 *b4 = reinterpret_cast<const float4 *>(rowB);
     uint4 *dst = reinterpret_cast<uint4 *>(app);
+#pragma unroll 4
     for (int i = lane; i < (ncw >> 2); i += nlanes) {
         const float4 va = __ldcs(a4 + i);
         const float4 vb = rowB ? __ldcs(b4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
