@@ -355,7 +355,24 @@ def main():
                "timer": "host perf_counter around the synchronous host-memory C-ABI call, max over ranks",
                "pipeline": "3 streams, chunked H2D / kernel / D2H overlap inside nrldpc_decode",
                "numa_bound": bool(numa_bound)}
-        del llr_h, hard_h
+        # same call with the LLRs transported as binary16 (nrldpc_decode16): half the H2D bytes; reported beside the
+        # float32-boundary figure above, which stays the e2e headline
+        llr_h16 = torch.empty((B, h.n_cw), dtype=torch.float16, pin_memory=True)
+        llr_h16.copy_(llr.clamp(-60000.0, 60000.0))
+        torch.cuda.synchronize()
+        for _ in range(2):
+            h.decode16_raw(llr_h16, B, hard_h, n_rows=w["n_rows"], mem=capi.MEM_HOST)
+        D.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            h.decode16_raw(llr_h16, B, hard_h, n_rows=w["n_rows"], mem=capi.MEM_HOST)
+        torch.cuda.synchronize()
+        dt16 = D.max_over_ranks((time.perf_counter() - t0) / n_e2e)
+        e2e["f16_transport"] = {"value": world * B * K / dt16 / 1e9, "unit": "Gb/s", "h2d_bytes_per_step": B * h.n_cw * 2,
+                                "d2h_bytes_per_step": B * K, "ms_per_step": dt16 * 1e3,
+                                "bler_at_esn0": float((hard_h.cuda() != info).any(dim=1).float().mean())}
+        del llr_h, hard_h, llr_h16
 
     # ---- roofline of the dominant (only) kernel --------------------------------------------------
     peak, peak_src = peaks()

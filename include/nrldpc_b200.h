@@ -97,6 +97,13 @@ int nrldpc_decode(nrldpc_t *h, const float *llr, int64_t batch, int32_t n_rows,
                   uint8_t *info_hard, float *app_soft, int32_t *iters, uint8_t *parity_ok,
                   int32_t mem, void *stream);
 
+/* Same call with the LLRs transported as IEEE binary16 (half the host<->device bytes): the values are widened
+ * exactly to float32 on the device and decoded as by nrldpc_decode.  With llr_dtype = NRLDPC_F16X2 the result
+ * is bit-identical to nrldpc_decode on float32 LLRs that were rounded to binary16 (round to nearest even). */
+int nrldpc_decode16(nrldpc_t *h, const uint16_t *llr_f16, int64_t batch, int32_t n_rows,
+                    uint8_t *info_hard, float *app_soft, int32_t *iters, uint8_t *parity_ok,
+                    int32_t mem, void *stream);
+
 /* ---- encode: replaces step(obj.hLDPCEncoder, c) at NRLDPCEncoder.m:158 ------------------------
  *   info [batch][K] uint8 (filler positions must already be 0, NRLDPCEncoder.m:153)
  *   cw   [batch][n_cw] uint8 systematic codeword [info ; parity], H*cw = 0 */

@@ -22,6 +22,16 @@
 #define NRLDPC_EXPORT extern "C" __attribute__((visibility("default")))
 
 namespace nrldpc {
+// fp16 LLR transport (nrldpc_decode16): widen to the float32 layout the decode kernels read (exact conversion)
+__global__ void __launch_bounds__(256) widen_f16_kernel(const uint2 *__restrict__ in, float4 *__restrict__ out, long long n4) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const uint2 v = __ldcs(in + i);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&v.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&v.y));
+        out[i] = make_float4(a.x, a.y, b.x, b.y);
+    }
+}
+
 // Shared-window address at which a kernel without static shared memory sees its dynamic shared memory.
 __global__ void smem_base_probe(uint32_t *out) {
     extern __shared__ __align__(16) unsigned char probe_smem[];
@@ -39,6 +49,7 @@ struct PipeSlot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     float *llr = nullptr;       // device staging
+    uint16_t *llr16 = nullptr;  // fp16 transport staging (nrldpc_decode16)
     uint8_t *hard = nullptr;
     float *soft = nullptr;
     int32_t *iters = nullptr;
@@ -75,6 +86,8 @@ struct nrldpc_handle {
     uint32_t smem_base = 0;          // shared-window address of dynamic shared memory (probed at create)
     nrldpc::DecArgs dec_args;
     cudaEvent_t dev_done = nullptr;  // last NRLDPC_MEM_DEVICE launch that used pipe[0]'s scratch
+    float *dev_widen = nullptr;      // float32 copy of device fp16 input (nrldpc_decode16, NRLDPC_MEM_DEVICE)
+    size_t dev_widen_cw = 0;
 };
 
 namespace {
@@ -197,10 +210,10 @@ int ensure_pipe(nrldpc_handle *h) {
     return 0;
 }
 
-int ensure_decode_staging(nrldpc_handle *h, PipeSlot &s, size_t cw, bool soft) {
+int ensure_decode_staging(nrldpc_handle *h, PipeSlot &s, size_t cw, bool soft, bool half_in) {
     if (cw > s.cap_cw) {
-        cudaFree(s.llr); cudaFree(s.hard); cudaFree(s.iters); cudaFree(s.ok); cudaFree(s.soft);
-        s.llr = nullptr; s.hard = nullptr; s.iters = nullptr; s.ok = nullptr; s.soft = nullptr; s.cap_cw = 0;
+        cudaFree(s.llr); cudaFree(s.hard); cudaFree(s.iters); cudaFree(s.ok); cudaFree(s.soft); cudaFree(s.llr16);
+        s.llr = nullptr; s.hard = nullptr; s.iters = nullptr; s.ok = nullptr; s.soft = nullptr; s.llr16 = nullptr; s.cap_cw = 0;
         CUDA_TRY(h, cudaMalloc(&s.llr, cw * h->d.n_cw * sizeof(float)));
         CUDA_TRY(h, cudaMalloc(&s.hard, cw * h->d.K));
         CUDA_TRY(h, cudaMalloc(&s.iters, cw * sizeof(int32_t)));
@@ -208,6 +221,7 @@ int ensure_decode_staging(nrldpc_handle *h, PipeSlot &s, size_t cw, bool soft) {
         s.cap_cw = cw;
     }
     if (soft && !s.soft) CUDA_TRY(h, cudaMalloc(&s.soft, s.cap_cw * h->d.n_cw * sizeof(float)));
+    if (half_in && !s.llr16) CUDA_TRY(h, cudaMalloc(&s.llr16, s.cap_cw * h->d.n_cw * sizeof(uint16_t)));
     return 0;
 }
 
@@ -479,13 +493,14 @@ NRLDPC_EXPORT void nrldpc_destroy(nrldpc_t *h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (auto &s : h->pipe) {
-        cudaFree(s.llr); cudaFree(s.hard); cudaFree(s.soft); cudaFree(s.iters); cudaFree(s.ok);
+        cudaFree(s.llr); cudaFree(s.hard); cudaFree(s.soft); cudaFree(s.iters); cudaFree(s.ok); cudaFree(s.llr16);
         cudaFree(s.bytes_in); cudaFree(s.bytes_out); cudaFree(s.f_in);
         cudaFree(s.c2v); cudaFree(s.counter);
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     if (h->dev_done) cudaEventDestroy(h->dev_done);
+    cudaFree(h->dev_widen);
     cudaFree(h->edesc);
     cudaFree(h->row_start);
     delete h;
@@ -505,8 +520,18 @@ NRLDPC_EXPORT int nrldpc_get_dims(const nrldpc_t *h, nrldpc_dims *out) {
 }
 
 // ------------------------------------------------------------------------------------------------
-NRLDPC_EXPORT int nrldpc_decode(nrldpc_t *h, const float *llr, int64_t batch, int32_t n_rows, uint8_t *info_hard,
-                                float *app_soft, int32_t *iters, uint8_t *parity_ok, int32_t mem, void *stream) {
+namespace {
+int widen(nrldpc_handle *h, cudaStream_t st, const uint16_t *in, float *out, int64_t n_cw_total) {
+    const long long n4 = (long long)n_cw_total * h->d.n_cw / 4;   // n_cw is a multiple of 4
+    nrldpc::widen_f16_kernel<<<grid_for(h, n4, 256), 256, 0, st>>>(reinterpret_cast<const uint2 *>(in), reinterpret_cast<float4 *>(out), n4);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+// llr: float32 (half_in = false) or IEEE binary16 (half_in = true) rows in cw layout
+int decode_impl(nrldpc_t *h, const void *llr, bool half_in, int64_t batch, int32_t n_rows, uint8_t *info_hard,
+                float *app_soft, int32_t *iters, uint8_t *parity_ok, int32_t mem, void *stream) {
     if (!h) return NRLDPC_ESHAPE;
     if (batch < 0) return fail(h, NRLDPC_ESHAPE, "batch must be >= 0");
     if (batch == 0) return 0;
@@ -514,37 +539,54 @@ NRLDPC_EXPORT int nrldpc_decode(nrldpc_t *h, const float *llr, int64_t batch, in
     if (n_rows == 0) n_rows = h->d.rows;
     if (n_rows < 4 || n_rows > h->d.rows) return fail(h, NRLDPC_EUNSUPPORTED, "n_rows must be 0 or in [4, %d]", h->d.rows);
     CUDA_TRY(h, cudaSetDevice(h->device));
+    const size_t in_elt = half_in ? sizeof(uint16_t) : sizeof(float);
     if (mem == NRLDPC_MEM_DEVICE) {
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
         if ((reinterpret_cast<uintptr_t>(llr) & 15) || (app_soft && (reinterpret_cast<uintptr_t>(app_soft) & 15)))
             return fail(h, NRLDPC_ESHAPE, "device llr / app_soft pointers must be 16-byte aligned");
         if (reinterpret_cast<uintptr_t>(info_hard) & 3)
             return fail(h, NRLDPC_ESHAPE, "device info_hard pointer must be 4-byte aligned");
         if (!h->dev_done) CUDA_TRY(h, cudaEventCreateWithFlags(&h->dev_done, cudaEventDisableTiming));
-        if (int rc = launch_decode(h, h->pipe[0], static_cast<cudaStream_t>(stream), llr, batch, n_rows, info_hard,
-                                   app_soft, iters, parity_ok))
-            return rc;
-        CUDA_TRY(h, cudaEventRecord(h->dev_done, static_cast<cudaStream_t>(stream)));
+        const float *src = static_cast<const float *>(llr);
+        if (half_in) {
+            if ((size_t)batch > h->dev_widen_cw) {
+                CUDA_TRY(h, cudaStreamSynchronize(st));
+                cudaFree(h->dev_widen);
+                h->dev_widen = nullptr; h->dev_widen_cw = 0;
+                CUDA_TRY(h, cudaMalloc(&h->dev_widen, (size_t)batch * h->d.n_cw * sizeof(float)));
+                h->dev_widen_cw = (size_t)batch;
+            }
+            if (int rc = widen(h, st, static_cast<const uint16_t *>(llr), h->dev_widen, batch)) return rc;
+            src = h->dev_widen;
+        }
+        if (int rc = launch_decode(h, h->pipe[0], st, src, batch, n_rows, info_hard, app_soft, iters, parity_ok)) return rc;
+        CUDA_TRY(h, cudaEventRecord(h->dev_done, st));
         return 0;
     }
     if (mem != NRLDPC_MEM_HOST) return fail(h, NRLDPC_ESHAPE, "mem must be NRLDPC_MEM_HOST or NRLDPC_MEM_DEVICE");
 
-    // Host buffers: chunked 3-deep pipeline, H2D / kernel / D2H of different chunks overlap.
+    // Host buffers: chunked 3-deep pipeline, H2D / kernel / D2H of different chunks overlap.  Chunks are one
+    // persistent-grid wave of codewords (doubled while small) so the un-overlapped tail stays short.
     if (int rc = ensure_pipe(h)) return rc;
     if (h->dev_done) CUDA_TRY(h, cudaStreamWaitEvent(h->pipe[0].stream, h->dev_done, 0));
     const int cwpc = decode_cwpc(h->d.Z);
     const int64_t wave = (int64_t)h->num_sms * nrldpc::kDecCtasPerSm * cwpc *
                          (h->cfg.llr_dtype == NRLDPC_F16X2 ? 2 : 1);  // codewords per full grid
     int64_t chunk = wave;
-    while (chunk * 2 * h->d.n_cw * 4 <= (int64_t)96 << 20 && chunk * 2 * kNumPipe <= batch) chunk *= 2;
+    while (chunk * 2 * h->d.n_cw * 4 <= (int64_t)40 << 20 && chunk * 2 * kNumPipe <= batch) chunk *= 2;
     chunk = std::min<int64_t>(chunk, batch);
     for (auto &s : h->pipe)
-        if (int rc = ensure_decode_staging(h, s, (size_t)chunk, app_soft != nullptr)) return rc;
+        if (int rc = ensure_decode_staging(h, s, (size_t)chunk, app_soft != nullptr, half_in)) return rc;
     int k = 0;
+    const unsigned char *llr_b = static_cast<const unsigned char *>(llr);
     for (int64_t off = 0; off < batch; off += chunk, k = (k + 1) % kNumPipe) {
         PipeSlot &s = h->pipe[k];
         const int64_t n = std::min<int64_t>(chunk, batch - off);
-        CUDA_TRY(h, cudaMemcpyAsync(s.llr, llr + off * h->d.n_cw, (size_t)n * h->d.n_cw * sizeof(float),
+        CUDA_TRY(h, cudaMemcpyAsync(half_in ? static_cast<void *>(s.llr16) : static_cast<void *>(s.llr),
+                                    llr_b + (size_t)off * h->d.n_cw * in_elt, (size_t)n * h->d.n_cw * in_elt,
                                     cudaMemcpyHostToDevice, s.stream));
+        if (half_in)
+            if (int rc = widen(h, s.stream, s.llr16, s.llr, n)) return rc;
         if (int rc = launch_decode(h, s, s.stream, s.llr, n, n_rows, s.hard, app_soft ? s.soft : nullptr,
                                    iters ? s.iters : nullptr, parity_ok ? s.ok : nullptr))
             return rc;
@@ -557,6 +599,17 @@ NRLDPC_EXPORT int nrldpc_decode(nrldpc_t *h, const float *llr, int64_t batch, in
     }
     for (auto &s : h->pipe) CUDA_TRY(h, cudaStreamSynchronize(s.stream));
     return 0;
+}
+}  // namespace
+
+NRLDPC_EXPORT int nrldpc_decode(nrldpc_t *h, const float *llr, int64_t batch, int32_t n_rows, uint8_t *info_hard,
+                                float *app_soft, int32_t *iters, uint8_t *parity_ok, int32_t mem, void *stream) {
+    return decode_impl(h, llr, false, batch, n_rows, info_hard, app_soft, iters, parity_ok, mem, stream);
+}
+
+NRLDPC_EXPORT int nrldpc_decode16(nrldpc_t *h, const uint16_t *llr_f16, int64_t batch, int32_t n_rows, uint8_t *info_hard,
+                                  float *app_soft, int32_t *iters, uint8_t *parity_ok, int32_t mem, void *stream) {
+    return decode_impl(h, llr_f16, true, batch, n_rows, info_hard, app_soft, iters, parity_ok, mem, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -415,3 +415,32 @@ def test_modem_system_objects(capi, O):
             o.release()
     with pytest.raises(capi.UnsupportedParameters):
         NRModulator(Modulation="8PSK").step(np.zeros(3, np.uint8))
+
+
+def test_decode16_half_transport(capi, O):
+    """nrldpc_decode16 (LLRs transported as binary16): host and device paths, both arithmetic modes.  Packed-half handle:
+    bit-identical to nrldpc_decode on the float32 originals (the kernel rounds them the same way).  Float32 handle:
+    equals the oracle on the binary16-rounded LLRs."""
+    import torch
+    rng = np.random.default_rng(61)
+    for bg, Z, B, E in ((1, 384, 9, 25272), (2, 52, 77, 2000), (2, 6, 300, 100)):
+        info, llr = make_llr(O, bg, Z, B, E, 0.5, rng)
+        llr[0, 5 * Z:5 * Z + 3] = np.inf
+        with np.errstate(over="ignore"):
+            l16 = llr.astype(np.float16)
+        for dt, f16 in ((capi.F16X2, True), (capi.F32, False)):
+            h = capi.Handle(bg, Z, 6, True, llr_dtype=dt)
+            hard = np.zeros((B, h.K), np.uint8); soft = np.zeros((B, h.n_cw), np.float32)
+            it = np.zeros(B, np.int32); ok = np.zeros(B, np.uint8)
+            h.decode16_raw(l16, B, hard, soft, it, ok)
+            ref = O.decode_nms(bg, Z, l16.astype(np.float32), 6, early_term=True, f16=f16)
+            assert (hard == ref["hard"]).all() and _same_bits(soft, ref["app"]) and (it == ref["iters"]).all()
+            if f16:
+                direct = h.decode(llr, want_soft=True)
+                assert (direct["hard"] == hard).all() and _same_bits(direct["app"], soft)
+            d16 = torch.from_numpy(l16).cuda()
+            dh = torch.zeros((B, h.K), dtype=torch.uint8, device="cuda")
+            h.decode16_raw(d16, B, dh, mem=capi.MEM_DEVICE, stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert (dh.cpu().numpy() == hard).all()
+            h.close()
