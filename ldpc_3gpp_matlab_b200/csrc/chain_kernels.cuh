@@ -306,6 +306,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "bra.uni WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t}" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
+// streamed-once input: evict_first so that it does not displace L2-pinned state
+__device__ __forceinline__ void bulk_g2s_stream(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+                 "r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src_gmem), "r"(bytes),
+                 "r"((uint32_t)__cvta_generic_to_shared(bar)), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
                  "r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src_gmem), "r"(bytes),
@@ -330,7 +338,7 @@ __global__ void __launch_bounds__(512) rate_recover_tma_kernel(const float *__re
     long long b = blockIdx.x;
     if (tid == 0 && b < batch) {
         mbar_expect_tx(&bar[0], row_bytes);
-        bulk_g2s(buf[0], f + b * g.E, row_bytes, &bar[0]);
+        bulk_g2s_stream(buf[0], f + b * g.E, row_bytes, &bar[0]);
     }
     uint32_t phase[2] = {0u, 0u};
     for (int it = 0; b < batch; b += gridDim.x, ++it) {
@@ -338,7 +346,7 @@ __global__ void __launch_bounds__(512) rate_recover_tma_kernel(const float *__re
         const long long nb = b + gridDim.x;
         if (n_buf > 1 && tid == 0 && nb < batch) {          // prefetch the next row into the other buffer (free since the
             mbar_expect_tx(&bar[cur ^ 1], row_bytes);       // barrier at the end of the previous iteration)
-            bulk_g2s(buf[cur ^ 1], f + nb * g.E, row_bytes, &bar[cur ^ 1]);
+            bulk_g2s_stream(buf[cur ^ 1], f + nb * g.E, row_bytes, &bar[cur ^ 1]);
         }
         mbar_wait(&bar[cur], phase[cur]);
         phase[cur] ^= 1u;
@@ -378,7 +386,7 @@ __global__ void __launch_bounds__(512) rate_recover_tma_kernel(const float *__re
         __syncthreads();   // every thread is done with buf[cur] before it is refilled
         if (n_buf == 1 && tid == 0 && nb < batch) {
             mbar_expect_tx(&bar[0], row_bytes);
-            bulk_g2s(buf[0], f + nb * g.E, row_bytes, &bar[0]);
+            bulk_g2s_stream(buf[0], f + nb * g.E, row_bytes, &bar[0]);
         }
     }
 }

@@ -248,7 +248,7 @@ __device__ __forceinline__ void load_group(const DecArgs &a, float *app, long lo
     if (threadIdx.x == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses to app vs the async write
         mbar_expect_tx(bar, bytes);
-        bulk_g2s(app, a.llr + cw0 * ncw, bytes, bar);
+        bulk_g2s_stream(app, a.llr + cw0 * ncw, bytes, bar);   // evict_first: must not displace the pinned c2v scratch
     }
     mbar_wait(bar, parity);
     parity ^= 1u;

@@ -46,6 +46,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         cfg.early_term = (int32_t)mxGetScalar(prhs[4]);
         cfg.alpha = nrhs > 5 ? (float)mxGetScalar(prhs[5]) : 0.75f;
         cfg.device = -1;
+        cfg.llr_dtype = nrhs > 6 ? (int32_t)mxGetScalar(prhs[6]) : NRLDPC_F32;   /* NRLDPC_F16X2 = packed-half decoder */
         nrldpc_t *h = nullptr;
         check(nrldpc_create(&h, &cfg), nullptr);
         plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
