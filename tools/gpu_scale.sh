@@ -9,6 +9,6 @@ for n in 2 4 8; do
     python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 100 --warmup 3 2>&1 | grep '^{"metric"' | tail -1 > gpurun_out/scale_n$n.json
   fi
 done
-for f in gpurun_out/scale_n*.json; do python -c "import json,sys;d=json.load(open('$f'));print(d['n_gpus'],round(d['value'],3),round(d['ms_per_step'],4),round(d['e2e']['value'],3) if d['e2e'] else None, round(d['f16x2']['value'],3), d['clocks'])"; done
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 tools/sweep.py --out gpurun_out/sweep_${NG}gpu > gpurun_out/sweep_${NG}gpu.log 2>&1
-tail -3 gpurun_out/sweep_${NG}gpu.log
+for f in gpurun_out/scale_n*.json; do python -c "import json,sys;d=json.load(open('$f'));print(d["n_gpus"],round(d["value"],3),round(d["ms_per_step"],4),"e2e",round(d["e2e"]["value"],3),"f16t",round(d["e2e"]["f16_transport"]["value"],3),"numa",d["e2e"]["numa_bound"],"h2",round(d["f16x2"]["value"],3),d["clocks"]["sm_mhz"],d["clocks"]["reasons"])"; done
+[ -n "$SKIP_SWEEP" ] || python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29512 tools/sweep.py --out gpurun_out/sweep_${NG}gpu > gpurun_out/sweep_${NG}gpu.log 2>&1
+[ -n "$SKIP_SWEEP" ] || tail -3 gpurun_out/sweep_${NG}gpu.log
