@@ -179,8 +179,9 @@ def cpu_reference_time(w, llr_sample, threads, steps=1, warmup=0):
         O.decode_bp(w["bg"], w["Z"], llr_sample, w["iters"], n_threads=threads)
     t0 = time.perf_counter()
     for _ in range(steps):
-        O.decode_bp(w["bg"], w["Z"], llr_sample, w["iters"], n_threads=threads)
+        out = O.decode_bp(w["bg"], w["Z"], llr_sample, w["iters"], n_threads=threads)
     dt = (time.perf_counter() - t0) / max(1, steps)
+    cpu_reference_time.last = out
     return dt, llr_sample.shape[0] * O.dims(w["bg"], w["Z"])["K"]
 
 
@@ -332,6 +333,33 @@ def main():
         h2.close()
         del hard2
 
+    # ---- secondary figure: the REFERENCE's algorithm on the device (flooding sum-product, float64, parity-check
+    # stop, whole H: NRLDPC_ALG_BP) on the same LLRs -- the like-for-like twin of the --impl reference arm
+    bp = None
+    if not f16 and not args.no_alt:
+        hb = capi.Handle(w["bg"], w["Z"], w["iters"], True, device=local_rank, algorithm=capi.ALG_BP)
+        hard_bp = torch.empty_like(hard)
+        iters_bp = torch.empty(B, dtype=torch.int32, device="cuda")
+
+        def step_bp():
+            hb.decode_raw(llr, B, hard_bp, iters=iters_bp, n_rows=0, mem=capi.MEM_DEVICE, stream=stream)
+        step_bp()
+        D.barrier()
+        torch.cuda.synchronize()
+        n_bp = 3
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n_bp):
+            step_bp()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_bp = D.max_over_ranks(e0.elapsed_time(e1)) / n_bp
+        bp = {"algorithm": "flooding sum-product f64, parity-check stop, all base rows (NRLDPC_ALG_BP = comm.LDPCDecoder "
+                           "as configured at NRLDPCDecoder.m:120)", "dtype": "f64", "value": world * B * K / (ms_bp * 1e-3) / 1e9,
+              "unit": "Gb/s", "ms_per_step": ms_bp, "steps": n_bp, "mean_iters": float(iters_bp.float().mean()),
+              "bler_at_esn0": float((hard_bp != info).any(dim=1).float().mean())}
+        hb.close()
+
     # ---- e2e: pinned host buffers through the synchronous host-memory C-ABI call ----------------
     e2e = None
     if not args.no_e2e:
@@ -406,6 +434,10 @@ def main():
         ref = O.decode_nms(w["bg"], w["Z"], sample, w["iters"], early_term=bool(w["early_term"]), n_rows=w["n_rows"],
                            want_app=False, n_threads=threads, f16=f16)
         dta = time.perf_counter() - t0
+        if bp is not None:     # the device's sum-product kernel against the CPU restatement on the same codewords
+            rb = cpu_reference_time.last
+            bp["matches_cpu_reference_bits"] = bool((rb["hard"] == hard_bp[:CPU_BASELINE_CW].cpu().numpy()).all() and
+                                                    (rb["iters"] == iters_bp[:CPU_BASELINE_CW].cpu().numpy()).all())
         cpu["like_for_like_nms_" + ("f16" if f16 else "f32")] = {"value": bits / dta / 1e9, "unit": "Gb/s", "cores": threads,
                                         "matches_gpu_bits": bool((ref["hard"] == hard[:CPU_BASELINE_CW].cpu().numpy()).all())}
 
@@ -428,6 +460,8 @@ def main():
             line["metric"] += " (packed fp16 arithmetic)"
         if alt is not None:
             line["f16x2"] = alt
+        if bp is not None:
+            line["reference_algorithm_on_gpu"] = bp
         print(json.dumps(line), flush=True)
     h.close()
     if world > 1:

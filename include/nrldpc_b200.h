@@ -42,6 +42,14 @@ extern "C" {
 #define NRLDPC_F32   0
 #define NRLDPC_F16X2 1
 
+/* Decoding algorithm (nrldpc_cfg.algorithm).
+ *   NRLDPC_ALG_NMS  layered normalized min-sum (default; the fast path)
+ *   NRLDPC_ALG_BP   the reference's own algorithm: flooding sum-product in float64 with the termination rule of
+ *                   comm.LDPCDecoder as configured at NRLDPCDecoder.m:120 -- same BLER curve and iteration counts
+ *                   as the reference, for users who need to reproduce its results rather than beat them */
+#define NRLDPC_ALG_NMS 0
+#define NRLDPC_ALG_BP  1
+
 /* Input LLR magnitudes are clamped to this value on load (NaN and +inf filler -> +LLR_MAX). */
 #define NRLDPC_LLR_MAX 1048576.0f
 
@@ -60,7 +68,8 @@ typedef struct nrldpc_cfg {
     int32_t device;     /* CUDA device ordinal, -1 = current device */
     int32_t llr_dtype;  /* decoder arithmetic: NRLDPC_F32 (default) or NRLDPC_F16X2 (two codewords per thread in
                            packed fp16, inputs clamped to +-2048; the buffers of nrldpc_decode stay float32) */
-    int32_t reserved;
+    int32_t algorithm;  /* NRLDPC_ALG_NMS (0, default) or NRLDPC_ALG_BP; NRLDPC_ALG_BP requires llr_dtype = NRLDPC_F32
+                           and ignores alpha */
 } nrldpc_cfg;
 
 int  nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg);
@@ -84,8 +93,9 @@ int nrldpc_lifting_size(int32_t K_b, int32_t K_prime);
 int nrldpc_base_graph(int32_t bg, int32_t i_LS, int32_t *rows, int32_t *cols, int32_t *shifts);
 
 /* ---- decode: replaces step(obj.hLDPCDecoder, cw_tilde) at NRLDPCDecoder.m:265 ----------------
- * Layered normalized min-sum (float32, or packed fp16 with llr_dtype = NRLDPC_F16X2) over base rows 0..n_rows-1 (n_rows = 0 -> all rows;
- * 4 <= n_rows).  Rows whose parity bit was not transmitted carry zero LLR and contribute nothing,
+ * Layered normalized min-sum (float32, or packed fp16 with llr_dtype = NRLDPC_F16X2) -- or, with algorithm =
+ * NRLDPC_ALG_BP, the reference's flooding sum-product in float64 -- over base rows 0..n_rows-1 (n_rows = 0 -> all
+ * rows; 4 <= n_rows).  Rows whose parity bit was not transmitted carry zero LLR and contribute nothing,
  * so callers may trim them (DESIGN.md "active rows").
  *   llr       [batch][n_cw] float32, cw layout; +inf / NaN = filler; exact 0 = punctured / unsent
  *   info_hard [batch][K] uint8, hard decision (app < 0) of the information part (required; device
@@ -102,6 +112,13 @@ int nrldpc_decode(nrldpc_t *h, const float *llr, int64_t batch, int32_t n_rows,
  * is bit-identical to nrldpc_decode on float32 LLRs that were rounded to binary16 (round to nearest even). */
 int nrldpc_decode16(nrldpc_t *h, const uint16_t *llr_f16, int64_t batch, int32_t n_rows,
                     uint8_t *info_hard, float *app_soft, int32_t *iters, uint8_t *parity_ok,
+                    int32_t mem, void *stream);
+
+/* Same call on float64 buffers, the type the reference hands to step() (cw_tilde is double, NRLDPCDecoder.m:262).
+ * With NRLDPC_ALG_BP the doubles are decoded as they are (float64 arithmetic, app_soft in float64); with the
+ * default algorithm they are rounded to float32 on the device and app_soft must be NULL. */
+int nrldpc_decode64(nrldpc_t *h, const double *llr_f64, int64_t batch, int32_t n_rows,
+                    uint8_t *info_hard, double *app_soft, int32_t *iters, uint8_t *parity_ok,
                     int32_t mem, void *stream);
 
 /* ---- encode: replaces step(obj.hLDPCEncoder, c) at NRLDPCEncoder.m:158 ------------------------

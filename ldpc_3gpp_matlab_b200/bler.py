@@ -46,7 +46,8 @@ def active_rows(p: NRLDPC, E_max: int, rv_ids) -> int:
 
 class BlerSimulator:
     def __init__(self, A, R, BG, Q_m=2, rv_id_sequence=(0,), iterations=8, early_termination=True, alpha=0.75,
-                 batch=4096, seed=0, device=0, rank=0, world=1, llr_dtype=capi.F32, decision_method=capi.DEMOD_LLR, crc=True):
+                 batch=4096, seed=0, device=0, rank=0, world=1, llr_dtype=capi.F32, decision_method=capi.DEMOD_LLR, crc=True,
+                 algorithm=capi.ALG_NMS):
         import torch
         if Q_m not in (1, 2, 4, 6, 8):
             raise capi.UnsupportedParameters("Unsupported modulation")          # NRModulator.m:43
@@ -59,8 +60,11 @@ class BlerSimulator:
         self.C, self.K, self.Kp, self.Z, self.N = p.C, p.K, p.K_prime, p.Z_c, p.N
         self.E_r = [int(e) for e in p.E_r]
         self.n_rows = active_rows(p, max(self.E_r), self.rvs)
+        if algorithm == capi.ALG_BP:          # the reference decodes on the whole H (NRLDPCDecoder.m:120)
+            self.n_rows = 46 if BG == 1 else 42
         p.rv_id = 0
-        self.h = capi.Handle(BG, self.Z, iterations, early_termination, alpha, device=device, llr_dtype=llr_dtype)
+        self.h = capi.Handle(BG, self.Z, iterations, early_termination, alpha, device=device, llr_dtype=llr_dtype,
+                             algorithm=algorithm)
         self.B = int(batch)
         self.rank, self.world, self.seed = rank, world, seed
         self.gen = torch.Generator(device="cuda").manual_seed(D.rank_seed(seed, rank) & 0x7FFFFFFFFFFF)
@@ -184,13 +188,13 @@ _MOD_NAME = {1: "BPSK", 2: "QPSK", 4: "16QAM", 6: "64QAM", 8: "256QAM"}
 
 def sweep(A, R, BG, iterations=8, target_block_errors=100, target_BLER=1e-3, EsN0_start=0.0, EsN0_delta=0.5, seed=0,
           rv_id_sequence=(0,), batch=4096, max_blocks=None, early_termination=True, out_dir="results", log=print,
-          Q_m=2, llr_dtype=capi.F32):
+          Q_m=2, llr_dtype=capi.F32, algorithm=capi.ALG_NMS):
     """plot_BLER_vs_SNR.m:53-171 for one (A, R, BG): returns [(EsN0, BLER, blocks, errors, mean_iters)]."""
     rank, local_rank, world = D.init()
     import torch
     torch.cuda.set_device(local_rank)
     sim = BlerSimulator(A, R, BG, Q_m, rv_id_sequence, iterations, early_termination, 0.75, batch, seed, local_rank, rank, world,
-                        llr_dtype=llr_dtype)
+                        llr_dtype=llr_dtype, algorithm=algorithm)
     rows, esn0, bler, found = [], float(EsN0_start), 1.0, False
     fid = None
     if rank == 0 and out_dir:
@@ -226,10 +230,13 @@ def main(argv=None):
     ap.add_argument("--out-dir", default="results")
     ap.add_argument("--modulation", default="QPSK", choices=sorted(_MOD_NAME.values()))
     ap.add_argument("--llr-dtype", default="f32", choices=["f32", "f16x2"])
+    ap.add_argument("--algorithm", default="nms", choices=["nms", "bp"],
+                    help="nms: layered normalized min-sum (default); bp: the reference's flooding sum-product in float64")
     a = ap.parse_args(argv)
     Q_m = {v: k for k, v in _MOD_NAME.items()}[a.modulation]
     sweep(a.A, a.R, a.BG, a.iterations, a.target_block_errors, a.target_BLER, a.EsN0_start, a.EsN0_delta, a.seed, a.rv,
-          a.batch, a.max_blocks, True, a.out_dir, Q_m=Q_m, llr_dtype=capi.F16X2 if a.llr_dtype == "f16x2" else capi.F32)
+          a.batch, a.max_blocks, True, a.out_dir, Q_m=Q_m, llr_dtype=capi.F16X2 if a.llr_dtype == "f16x2" else capi.F32,
+          algorithm=capi.ALG_BP if a.algorithm == "bp" else capi.ALG_NMS)
 
 
 if __name__ == "__main__":

@@ -24,6 +24,8 @@ MEM_DEVICE = 1
 LLR_MAX = 1048576.0
 F32 = 0
 F16X2 = 1
+ALG_NMS = 0   # layered normalized min-sum (default)
+ALG_BP = 1    # the reference's flooding sum-product in float64 (comm.LDPCDecoder, NRLDPCDecoder.m:120)
 DEMOD_LLR, DEMOD_APPROX, DEMOD_HARD = 0, 1, 2
 CRC16, CRC24A, CRC24B = 0, 1, 2
 CRC_KIND = {"CRC16": CRC16, "CRC24A": CRC24A, "CRC24B": CRC24B}
@@ -35,7 +37,7 @@ SYMBOLS = (
     "nrldpc_set_index", "nrldpc_lifting_size", "nrldpc_base_graph", "nrldpc_decode", "nrldpc_encode",
     "nrldpc_rate_match", "nrldpc_rate_recover", "nrldpc_qpsk_awgn_llr", "nrldpc_host_alloc",
     "nrldpc_host_free", "nrldpc_launch_count", "nrldpc_version",
-    "nrldpc_modulate", "nrldpc_awgn", "nrldpc_demodulate", "nrldpc_mod_awgn_llr", "nrldpc_crc", "nrldpc_decode16",
+    "nrldpc_modulate", "nrldpc_awgn", "nrldpc_demodulate", "nrldpc_mod_awgn_llr", "nrldpc_crc", "nrldpc_decode16", "nrldpc_decode64",
 )
 
 
@@ -55,7 +57,7 @@ class CudaError(RuntimeError):
 
 class Cfg(C.Structure):
     _fields_ = [("bg", C.c_int32), ("Z", C.c_int32), ("max_iters", C.c_int32), ("early_term", C.c_int32),
-                ("alpha", C.c_float), ("device", C.c_int32), ("llr_dtype", C.c_int32), ("reserved", C.c_int32)]
+                ("alpha", C.c_float), ("device", C.c_int32), ("llr_dtype", C.c_int32), ("algorithm", C.c_int32)]
 
 
 class Dims(C.Structure):
@@ -92,6 +94,7 @@ def load():
     lib.nrldpc_base_graph.argtypes = [i32, i32, vp, vp, vp]
     lib.nrldpc_decode.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, i32, vp]
     lib.nrldpc_decode16.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, i32, vp]
+    lib.nrldpc_decode64.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, i32, vp]
     lib.nrldpc_encode.argtypes = [vp, vp, i64, vp, i32, vp]
     lib.nrldpc_rate_match.argtypes = [vp, vp, i64, C.POINTER(Rm), vp, i32, vp]
     lib.nrldpc_rate_recover.argtypes = [vp, vp, i64, C.POINTER(Rm), vp, vp, i32, vp]
@@ -162,11 +165,11 @@ class Handle:
     """Owner of one nrldpc_t: a (BG, Z) code with its iteration policy on one GPU."""
 
     def __init__(self, bg: int, Z: int, max_iters: int = 8, early_term: bool = False, alpha: float = 0.75,
-                 device: int = -1, llr_dtype: int = F32):
+                 device: int = -1, llr_dtype: int = F32, algorithm: int = ALG_NMS):
         self._lib = load()
         self._h = C.c_void_p()
         cfg = Cfg(bg=int(bg), Z=int(Z), max_iters=int(max_iters), early_term=int(bool(early_term)),
-                  alpha=float(alpha), device=int(device), llr_dtype=int(llr_dtype))
+                  alpha=float(alpha), device=int(device), llr_dtype=int(llr_dtype), algorithm=int(algorithm))
         rc = self._lib.nrldpc_create(C.byref(self._h), C.byref(cfg))
         if rc:
             _raise(rc, self._lib.nrldpc_last_error(None).decode())
@@ -208,6 +211,11 @@ class Handle:
         self._check(self._lib.nrldpc_decode16(self._h, _ptr(llr_f16), int(batch), int(n_rows), _ptr(hard), _ptr(soft),
                                               _ptr(iters), _ptr(ok), int(mem), stream))
 
+    def decode64_raw(self, llr_f64, batch, hard, soft=None, iters=None, ok=None, n_rows=0, mem=MEM_HOST, stream=None):
+        """nrldpc_decode64: LLRs (and app_soft) as float64, the reference's own type (NRLDPCDecoder.m:262)."""
+        self._check(self._lib.nrldpc_decode64(self._h, _ptr(llr_f64), int(batch), int(n_rows), _ptr(hard), _ptr(soft),
+                                              _ptr(iters), _ptr(ok), int(mem), stream))
+
     def encode_raw(self, info, batch, cw, mem=MEM_HOST, stream=None):
         self._check(self._lib.nrldpc_encode(self._h, _ptr(info), int(batch), _ptr(cw), int(mem), stream))
 
@@ -242,16 +250,18 @@ class Handle:
 
     # numpy conveniences (host memory, synchronous) ----------------------------------------------
     def decode(self, llr, n_rows=0, want_soft=False):
-        llr = np.ascontiguousarray(llr, dtype=np.float32)
+        """float32 (default) or float64 LLRs (numpy float64 input goes through nrldpc_decode64)."""
+        f64 = isinstance(llr, np.ndarray) and llr.dtype == np.float64
+        llr = np.ascontiguousarray(llr, dtype=np.float64 if f64 else np.float32)
         if llr.shape[-1] != self.n_cw:
             raise NRLDPCError(f"llr should have {self.n_cw} entries per codeword (cw_tilde layout).")
         llr2 = llr.reshape(-1, self.n_cw)
         B = llr2.shape[0]
         hard = np.zeros((B, self.K), np.uint8)
-        soft = np.zeros((B, self.n_cw), np.float32) if want_soft else None
+        soft = np.zeros((B, self.n_cw), llr2.dtype) if want_soft else None
         iters = np.zeros(B, np.int32)
         ok = np.zeros(B, np.uint8)
-        self.decode_raw(llr2, B, hard, soft, iters, ok, n_rows=n_rows)
+        (self.decode64_raw if f64 else self.decode_raw)(llr2, B, hard, soft, iters, ok, n_rows=n_rows)
         return dict(hard=hard, app=soft, iters=iters, parity_ok=ok)
 
     def encode(self, info):

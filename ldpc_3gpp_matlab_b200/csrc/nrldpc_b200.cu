@@ -18,6 +18,7 @@
 #include "chain_kernels.cuh"
 #include "decode_kernel.cuh"
 #include "decode_kernel_h2.cuh"
+#include "decode_kernel_bp.cuh"
 
 #define NRLDPC_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -42,6 +43,7 @@ __global__ void smem_base_probe(uint32_t *out) {
 namespace {
 
 constexpr int kNumPipe = 3;  // streams / staging sets for NRLDPC_MEM_HOST calls
+enum { kInF32 = 0, kInF16 = 1, kInF64 = 2 };   // element type of the LLR buffer handed to decode_impl
 
 thread_local char g_create_error[256] = "";
 
@@ -50,6 +52,10 @@ struct PipeSlot {
     cudaEvent_t done = nullptr;
     float *llr = nullptr;       // device staging
     uint16_t *llr16 = nullptr;  // fp16 transport staging (nrldpc_decode16)
+    double *llr64 = nullptr;    // float64 staging (nrldpc_decode64)
+    double *soft64 = nullptr;
+    double *rmsg = nullptr;     // sum-product check-to-variable messages (NRLDPC_ALG_BP)
+    size_t rmsg_cap = 0;
     uint8_t *hard = nullptr;
     float *soft = nullptr;
     int32_t *iters = nullptr;
@@ -86,8 +92,10 @@ struct nrldpc_handle {
     uint32_t smem_base = 0;          // shared-window address of dynamic shared memory (probed at create)
     nrldpc::DecArgs dec_args;
     cudaEvent_t dev_done = nullptr;  // last NRLDPC_MEM_DEVICE launch that used pipe[0]'s scratch
-    float *dev_widen = nullptr;      // float32 copy of device fp16 input (nrldpc_decode16, NRLDPC_MEM_DEVICE)
+    float *dev_widen = nullptr;      // float32 copy of device fp16 / fp64 input (nrldpc_decode16/64, NRLDPC_MEM_DEVICE)
     size_t dev_widen_cw = 0;
+    // sum-product kernel tables (decode_kernel_bp.cuh)
+    int *bp_shift = nullptr, *bp_colz = nullptr, *bp_col_start = nullptr, *bp_col_edge = nullptr;
 };
 
 namespace {
@@ -202,6 +210,41 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
     return 0;
 }
 
+// Enqueue one sum-product (reference algorithm) decode launch; T = element type of llr / soft.
+template <typename T>
+int launch_decode_bp(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const T *llr, int64_t batch, int n_rows,
+                     uint8_t *hard, T *soft, int32_t *iters, uint8_t *ok) {
+    const int Z = h->d.Z;
+    const size_t smem = (size_t)h->d.n_cw * sizeof(double);
+    const int threads = std::min(nrldpc::kBpThreads, (n_rows * Z + 31) / 32 * 32);
+    auto kern = nrldpc::decode_bp_kernel<T>;
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    occ = std::max(1, std::min(occ, 4));
+    const int grid = (int)std::min<int64_t>(batch, (int64_t)h->num_sms * occ);
+    const size_t stride = (size_t)h->d.edges * Z;
+    if (!s.counter) CUDA_TRY(h, cudaMalloc(&s.counter, sizeof(int)));
+    if ((size_t)grid * stride > s.rmsg_cap) {
+        cudaFree(s.rmsg);
+        s.rmsg = nullptr; s.rmsg_cap = 0;
+        CUDA_TRY(h, cudaMalloc(&s.rmsg, (size_t)grid * stride * sizeof(double)));
+        s.rmsg_cap = (size_t)grid * stride;
+    }
+    CUDA_TRY(h, cudaMemsetAsync(s.counter, 0, sizeof(int), stream));
+    nrldpc::BpArgs a{};
+    a.llr = llr; a.hard = hard; a.soft = soft; a.iters = iters; a.ok = ok; a.batch = batch;
+    a.Z = Z; a.ncols = h->d.cols; a.kcols = h->d.kcols; a.n_rows = n_rows; a.n_edges = h->h_row_start[n_rows];
+    a.max_iters = h->cfg.max_iters; a.early_term = h->cfg.early_term;
+    a.rmsg = s.rmsg; a.rmsg_stride = (long long)stride; a.work_counter = s.counter;
+    a.row_start = h->row_start; a.e_shift = h->bp_shift; a.e_colz = h->bp_colz;
+    a.col_start = h->bp_col_start; a.col_edge = h->bp_col_edge;
+    kern<<<grid, threads, smem, stream>>>(a);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
 int ensure_pipe(nrldpc_handle *h) {
     for (auto &s : h->pipe) {
         if (!s.stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -210,18 +253,22 @@ int ensure_pipe(nrldpc_handle *h) {
     return 0;
 }
 
-int ensure_decode_staging(nrldpc_handle *h, PipeSlot &s, size_t cw, bool soft, bool half_in) {
+int ensure_decode_staging(nrldpc_handle *h, PipeSlot &s, size_t cw, bool soft, int in_kind) {
     if (cw > s.cap_cw) {
         cudaFree(s.llr); cudaFree(s.hard); cudaFree(s.iters); cudaFree(s.ok); cudaFree(s.soft); cudaFree(s.llr16);
+        cudaFree(s.llr64); cudaFree(s.soft64);
         s.llr = nullptr; s.hard = nullptr; s.iters = nullptr; s.ok = nullptr; s.soft = nullptr; s.llr16 = nullptr; s.cap_cw = 0;
+        s.llr64 = nullptr; s.soft64 = nullptr;
         CUDA_TRY(h, cudaMalloc(&s.llr, cw * h->d.n_cw * sizeof(float)));
         CUDA_TRY(h, cudaMalloc(&s.hard, cw * h->d.K));
         CUDA_TRY(h, cudaMalloc(&s.iters, cw * sizeof(int32_t)));
         CUDA_TRY(h, cudaMalloc(&s.ok, cw));
         s.cap_cw = cw;
     }
-    if (soft && !s.soft) CUDA_TRY(h, cudaMalloc(&s.soft, s.cap_cw * h->d.n_cw * sizeof(float)));
-    if (half_in && !s.llr16) CUDA_TRY(h, cudaMalloc(&s.llr16, s.cap_cw * h->d.n_cw * sizeof(uint16_t)));
+    if (soft && in_kind != kInF64 && !s.soft) CUDA_TRY(h, cudaMalloc(&s.soft, s.cap_cw * h->d.n_cw * sizeof(float)));
+    if (in_kind == kInF16 && !s.llr16) CUDA_TRY(h, cudaMalloc(&s.llr16, s.cap_cw * h->d.n_cw * sizeof(uint16_t)));
+    if (in_kind == kInF64 && !s.llr64) CUDA_TRY(h, cudaMalloc(&s.llr64, s.cap_cw * h->d.n_cw * sizeof(double)));
+    if (in_kind == kInF64 && soft && !s.soft64) CUDA_TRY(h, cudaMalloc(&s.soft64, s.cap_cw * h->d.n_cw * sizeof(double)));
     return 0;
 }
 
@@ -408,6 +455,10 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
     if (cfg->max_iters < 1) return fail(nullptr, NRLDPC_EUNSUPPORTED, "MaximumIterationCount must be >= 1.");
     if (cfg->llr_dtype != NRLDPC_F32 && cfg->llr_dtype != NRLDPC_F16X2)
         return fail(nullptr, NRLDPC_EUNSUPPORTED, "llr_dtype must be NRLDPC_F32 or NRLDPC_F16X2.");
+    if (cfg->algorithm != NRLDPC_ALG_NMS && cfg->algorithm != NRLDPC_ALG_BP)
+        return fail(nullptr, NRLDPC_EUNSUPPORTED, "algorithm must be NRLDPC_ALG_NMS or NRLDPC_ALG_BP.");
+    if (cfg->algorithm == NRLDPC_ALG_BP && cfg->llr_dtype != NRLDPC_F32)
+        return fail(nullptr, NRLDPC_EUNSUPPORTED, "NRLDPC_ALG_BP computes in float64; llr_dtype must be NRLDPC_F32 (the default).");
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
     if (ce != cudaSuccess || ndev == 0)
@@ -464,8 +515,29 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
     if (nv != 3) { delete h; return fail(nullptr, NRLDPC_EUNSUPPORTED, "unexpected core parity structure"); }
     h->enc_delta = vals[0] == vals[1] ? vals[2] : (vals[0] == vals[2] ? vals[1] : vals[0]);
 
+    // tables of the sum-product kernel: per edge (shift, col*Z) and the column-major edge lists
+    std::vector<int> bp_shift(v.edges), bp_colz(v.edges), bp_col_start(v.cols + 1, 0), bp_col_edge(v.edges);
+    for (int e = 0; e < v.edges; ++e) {
+        bp_shift[e] = v.sh(ils, e) % Z;
+        bp_colz[e] = v.col[e] * Z;
+        bp_col_start[v.col[e] + 1] += 1;
+    }
+    for (int c = 0; c < v.cols; ++c) bp_col_start[c + 1] += bp_col_start[c];
+    {
+        std::vector<int> fill(bp_col_start.begin(), bp_col_start.end() - 1);
+        for (int e = 0; e < v.edges; ++e) bp_col_edge[fill[v.col[e]]++] = e;   // ascending e inside a column
+    }
+
     int rc = 0;
     auto up = [&]() -> int {
+        CUDA_TRY(h, cudaMalloc(&h->bp_shift, sizeof(int) * v.edges));
+        CUDA_TRY(h, cudaMalloc(&h->bp_colz, sizeof(int) * v.edges));
+        CUDA_TRY(h, cudaMalloc(&h->bp_col_start, sizeof(int) * (v.cols + 1)));
+        CUDA_TRY(h, cudaMalloc(&h->bp_col_edge, sizeof(int) * v.edges));
+        CUDA_TRY(h, cudaMemcpy(h->bp_shift, bp_shift.data(), sizeof(int) * v.edges, cudaMemcpyHostToDevice));
+        CUDA_TRY(h, cudaMemcpy(h->bp_colz, bp_colz.data(), sizeof(int) * v.edges, cudaMemcpyHostToDevice));
+        CUDA_TRY(h, cudaMemcpy(h->bp_col_start, bp_col_start.data(), sizeof(int) * (v.cols + 1), cudaMemcpyHostToDevice));
+        CUDA_TRY(h, cudaMemcpy(h->bp_col_edge, bp_col_edge.data(), sizeof(int) * v.edges, cudaMemcpyHostToDevice));
         CUDA_TRY(h, cudaMalloc(&h->edesc, ed.size() * sizeof(uint32_t)));
         CUDA_TRY(h, cudaMalloc(&h->row_start, sizeof(int) * (v.rows + 1)));
         CUDA_TRY(h, cudaMemcpy(h->edesc, ed.data(), ed.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -496,6 +568,7 @@ NRLDPC_EXPORT void nrldpc_destroy(nrldpc_t *h) {
         cudaFree(s.llr); cudaFree(s.hard); cudaFree(s.soft); cudaFree(s.iters); cudaFree(s.ok); cudaFree(s.llr16);
         cudaFree(s.bytes_in); cudaFree(s.bytes_out); cudaFree(s.f_in);
         cudaFree(s.c2v); cudaFree(s.counter);
+        cudaFree(s.llr64); cudaFree(s.soft64); cudaFree(s.rmsg);
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -503,6 +576,7 @@ NRLDPC_EXPORT void nrldpc_destroy(nrldpc_t *h) {
     cudaFree(h->dev_widen);
     cudaFree(h->edesc);
     cudaFree(h->row_start);
+    cudaFree(h->bp_shift); cudaFree(h->bp_colz); cudaFree(h->bp_col_start); cudaFree(h->bp_col_edge);
     delete h;
 }
 
@@ -529,17 +603,51 @@ int widen(nrldpc_handle *h, cudaStream_t st, const uint16_t *in, float *out, int
     return 0;
 }
 
-// llr: float32 (half_in = false) or IEEE binary16 (half_in = true) rows in cw layout
-int decode_impl(nrldpc_t *h, const void *llr, bool half_in, int64_t batch, int32_t n_rows, uint8_t *info_hard,
-                float *app_soft, int32_t *iters, uint8_t *parity_ok, int32_t mem, void *stream) {
+int narrow(nrldpc_handle *h, cudaStream_t st, const double *in, float *out, int64_t n_cw_total) {
+    const long long n = (long long)n_cw_total * h->d.n_cw;
+    nrldpc::narrow_f64_kernel<<<grid_for(h, n, 256), 256, 0, st>>>(in, out, n);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+// One decode launch (plus the conversion kernel the transport type needs) on device buffers.
+//   in_kind = kInF32: llr float32, soft float32;  kInF16: llr binary16, soft float32;  kInF64: llr float64, soft float64.
+//   f32_tmp: float32 scratch of batch*n_cw entries (needed when a conversion precedes the kernel)
+int launch_any(nrldpc_handle *h, PipeSlot &s, cudaStream_t st, const void *llr, int in_kind, float *f32_tmp, int64_t batch,
+               int n_rows, uint8_t *hard, void *soft, int32_t *iters, uint8_t *ok) {
+    const bool bp = h->cfg.algorithm == NRLDPC_ALG_BP;
+    if (in_kind == kInF64 && bp)   // the reference's arithmetic on the reference's own input type
+        return launch_decode_bp<double>(h, s, st, static_cast<const double *>(llr), batch, n_rows, hard,
+                                        static_cast<double *>(soft), iters, ok);
+    const float *src = static_cast<const float *>(llr);
+    if (in_kind == kInF16) {
+        if (int rc = widen(h, st, static_cast<const uint16_t *>(llr), f32_tmp, batch)) return rc;
+        src = f32_tmp;
+    } else if (in_kind == kInF64) {
+        if (int rc = narrow(h, st, static_cast<const double *>(llr), f32_tmp, batch)) return rc;
+        src = f32_tmp;
+    }
+    if (bp) return launch_decode_bp<float>(h, s, st, src, batch, n_rows, hard, static_cast<float *>(soft), iters, ok);
+    return launch_decode(h, s, st, src, batch, n_rows, hard, static_cast<float *>(soft), iters, ok);
+}
+
+// llr: float32 / IEEE binary16 / float64 rows in cw layout (in_kind)
+int decode_impl(nrldpc_t *h, const void *llr, int in_kind, int64_t batch, int32_t n_rows, uint8_t *info_hard,
+                void *app_soft, int32_t *iters, uint8_t *parity_ok, int32_t mem, void *stream) {
     if (!h) return NRLDPC_ESHAPE;
     if (batch < 0) return fail(h, NRLDPC_ESHAPE, "batch must be >= 0");
     if (batch == 0) return 0;
     if (!llr || !info_hard) return fail(h, NRLDPC_ESHAPE, "llr and info_hard must not be NULL");
     if (n_rows == 0) n_rows = h->d.rows;
     if (n_rows < 4 || n_rows > h->d.rows) return fail(h, NRLDPC_EUNSUPPORTED, "n_rows must be 0 or in [4, %d]", h->d.rows);
+    const bool bp = h->cfg.algorithm == NRLDPC_ALG_BP;
+    if (in_kind == kInF64 && !bp && app_soft)
+        return fail(h, NRLDPC_EUNSUPPORTED, "nrldpc_decode64 returns app_soft only with NRLDPC_ALG_BP (the min-sum kernels compute in float32)");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    const size_t in_elt = half_in ? sizeof(uint16_t) : sizeof(float);
+    const size_t in_elt = in_kind == kInF16 ? sizeof(uint16_t) : in_kind == kInF64 ? sizeof(double) : sizeof(float);
+    const size_t soft_elt = in_kind == kInF64 ? sizeof(double) : sizeof(float);
+    const bool convert = in_kind == kInF16 || (in_kind == kInF64 && !bp);
     if (mem == NRLDPC_MEM_DEVICE) {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         if ((reinterpret_cast<uintptr_t>(llr) & 15) || (app_soft && (reinterpret_cast<uintptr_t>(app_soft) & 15)))
@@ -547,19 +655,15 @@ int decode_impl(nrldpc_t *h, const void *llr, bool half_in, int64_t batch, int32
         if (reinterpret_cast<uintptr_t>(info_hard) & 3)
             return fail(h, NRLDPC_ESHAPE, "device info_hard pointer must be 4-byte aligned");
         if (!h->dev_done) CUDA_TRY(h, cudaEventCreateWithFlags(&h->dev_done, cudaEventDisableTiming));
-        const float *src = static_cast<const float *>(llr);
-        if (half_in) {
-            if ((size_t)batch > h->dev_widen_cw) {
-                CUDA_TRY(h, cudaStreamSynchronize(st));
-                cudaFree(h->dev_widen);
-                h->dev_widen = nullptr; h->dev_widen_cw = 0;
-                CUDA_TRY(h, cudaMalloc(&h->dev_widen, (size_t)batch * h->d.n_cw * sizeof(float)));
-                h->dev_widen_cw = (size_t)batch;
-            }
-            if (int rc = widen(h, st, static_cast<const uint16_t *>(llr), h->dev_widen, batch)) return rc;
-            src = h->dev_widen;
+        if (convert && (size_t)batch > h->dev_widen_cw) {
+            CUDA_TRY(h, cudaStreamSynchronize(st));
+            cudaFree(h->dev_widen);
+            h->dev_widen = nullptr; h->dev_widen_cw = 0;
+            CUDA_TRY(h, cudaMalloc(&h->dev_widen, (size_t)batch * h->d.n_cw * sizeof(float)));
+            h->dev_widen_cw = (size_t)batch;
         }
-        if (int rc = launch_decode(h, h->pipe[0], st, src, batch, n_rows, info_hard, app_soft, iters, parity_ok)) return rc;
+        if (int rc = launch_any(h, h->pipe[0], st, llr, in_kind, h->dev_widen, batch, n_rows, info_hard, app_soft, iters, parity_ok))
+            return rc;
         CUDA_TRY(h, cudaEventRecord(h->dev_done, st));
         return 0;
     }
@@ -570,29 +674,31 @@ int decode_impl(nrldpc_t *h, const void *llr, bool half_in, int64_t batch, int32
     if (int rc = ensure_pipe(h)) return rc;
     if (h->dev_done) CUDA_TRY(h, cudaStreamWaitEvent(h->pipe[0].stream, h->dev_done, 0));
     const int cwpc = decode_cwpc(h->d.Z);
-    const int64_t wave = (int64_t)h->num_sms * nrldpc::kDecCtasPerSm * cwpc *
-                         (h->cfg.llr_dtype == NRLDPC_F16X2 ? 2 : 1);  // codewords per full grid
+    const int64_t wave = bp ? (int64_t)h->num_sms
+                            : (int64_t)h->num_sms * nrldpc::kDecCtasPerSm * cwpc *
+                                  (h->cfg.llr_dtype == NRLDPC_F16X2 ? 2 : 1);  // codewords per full grid
     int64_t chunk = wave;
     while (chunk * 2 * h->d.n_cw * 4 <= (int64_t)40 << 20 && chunk * 2 * kNumPipe <= batch) chunk *= 2;
     chunk = std::min<int64_t>(chunk, batch);
     for (auto &s : h->pipe)
-        if (int rc = ensure_decode_staging(h, s, (size_t)chunk, app_soft != nullptr, half_in)) return rc;
+        if (int rc = ensure_decode_staging(h, s, (size_t)chunk, app_soft != nullptr, in_kind)) return rc;
     int k = 0;
     const unsigned char *llr_b = static_cast<const unsigned char *>(llr);
+    unsigned char *soft_b = static_cast<unsigned char *>(app_soft);
     for (int64_t off = 0; off < batch; off += chunk, k = (k + 1) % kNumPipe) {
         PipeSlot &s = h->pipe[k];
         const int64_t n = std::min<int64_t>(chunk, batch - off);
-        CUDA_TRY(h, cudaMemcpyAsync(half_in ? static_cast<void *>(s.llr16) : static_cast<void *>(s.llr),
-                                    llr_b + (size_t)off * h->d.n_cw * in_elt, (size_t)n * h->d.n_cw * in_elt,
+        void *d_in = in_kind == kInF16 ? static_cast<void *>(s.llr16) : in_kind == kInF64 ? static_cast<void *>(s.llr64)
+                                                                                         : static_cast<void *>(s.llr);
+        void *d_soft = !app_soft ? nullptr : in_kind == kInF64 ? static_cast<void *>(s.soft64) : static_cast<void *>(s.soft);
+        CUDA_TRY(h, cudaMemcpyAsync(d_in, llr_b + (size_t)off * h->d.n_cw * in_elt, (size_t)n * h->d.n_cw * in_elt,
                                     cudaMemcpyHostToDevice, s.stream));
-        if (half_in)
-            if (int rc = widen(h, s.stream, s.llr16, s.llr, n)) return rc;
-        if (int rc = launch_decode(h, s, s.stream, s.llr, n, n_rows, s.hard, app_soft ? s.soft : nullptr,
-                                   iters ? s.iters : nullptr, parity_ok ? s.ok : nullptr))
+        if (int rc = launch_any(h, s, s.stream, d_in, in_kind, s.llr, n, n_rows, s.hard, d_soft, iters ? s.iters : nullptr,
+                                parity_ok ? s.ok : nullptr))
             return rc;
         CUDA_TRY(h, cudaMemcpyAsync(info_hard + off * h->d.K, s.hard, (size_t)n * h->d.K, cudaMemcpyDeviceToHost, s.stream));
         if (app_soft)
-            CUDA_TRY(h, cudaMemcpyAsync(app_soft + off * h->d.n_cw, s.soft, (size_t)n * h->d.n_cw * sizeof(float),
+            CUDA_TRY(h, cudaMemcpyAsync(soft_b + (size_t)off * h->d.n_cw * soft_elt, d_soft, (size_t)n * h->d.n_cw * soft_elt,
                                         cudaMemcpyDeviceToHost, s.stream));
         if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters + off, s.iters, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
         if (parity_ok) CUDA_TRY(h, cudaMemcpyAsync(parity_ok + off, s.ok, (size_t)n, cudaMemcpyDeviceToHost, s.stream));
@@ -604,12 +710,17 @@ int decode_impl(nrldpc_t *h, const void *llr, bool half_in, int64_t batch, int32
 
 NRLDPC_EXPORT int nrldpc_decode(nrldpc_t *h, const float *llr, int64_t batch, int32_t n_rows, uint8_t *info_hard,
                                 float *app_soft, int32_t *iters, uint8_t *parity_ok, int32_t mem, void *stream) {
-    return decode_impl(h, llr, false, batch, n_rows, info_hard, app_soft, iters, parity_ok, mem, stream);
+    return decode_impl(h, llr, kInF32, batch, n_rows, info_hard, app_soft, iters, parity_ok, mem, stream);
 }
 
 NRLDPC_EXPORT int nrldpc_decode16(nrldpc_t *h, const uint16_t *llr_f16, int64_t batch, int32_t n_rows, uint8_t *info_hard,
                                   float *app_soft, int32_t *iters, uint8_t *parity_ok, int32_t mem, void *stream) {
-    return decode_impl(h, llr_f16, true, batch, n_rows, info_hard, app_soft, iters, parity_ok, mem, stream);
+    return decode_impl(h, llr_f16, kInF16, batch, n_rows, info_hard, app_soft, iters, parity_ok, mem, stream);
+}
+
+NRLDPC_EXPORT int nrldpc_decode64(nrldpc_t *h, const double *llr_f64, int64_t batch, int32_t n_rows, uint8_t *info_hard,
+                                  double *app_soft, int32_t *iters, uint8_t *parity_ok, int32_t mem, void *stream) {
+    return decode_impl(h, llr_f64, kInF64, batch, n_rows, info_hard, app_soft, iters, parity_ok, mem, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -291,10 +291,14 @@ class NRLDPCDecoder(NRLDPC):
     transport-block CRC or any code-block CRC fails (:337-339).
 
     Engine-specific properties (not in the reference): ``early_termination`` (default True = the
-    reference's 'Parity check satisfied', NRLDPCDecoder.m:120), ``alpha`` (min-sum normalisation)
-    and ``trim_rows`` (skip base rows whose parity bits were never received)."""
+    reference's 'Parity check satisfied', NRLDPCDecoder.m:120), ``alpha`` (min-sum normalisation),
+    ``trim_rows`` (skip base rows whose parity bits were never received) and ``algorithm``:
+    ``'Layered normalized min-sum'`` (default, the fast path) or ``'Sum-product'`` = the reference's own
+    flooding sum-product in float64 on the whole H, as comm.LDPCDecoder runs it at :120,:265 (rows are never
+    trimmed in this mode: the reference always passes the full matrix)."""
 
-    _extra_props = ("I_HARQ", "iterations", "early_termination", "alpha", "trim_rows")
+    _extra_props = ("I_HARQ", "iterations", "early_termination", "alpha", "trim_rows", "algorithm")
+    ALGORITHMS = {"Layered normalized min-sum": capi.ALG_NMS, "Sum-product": capi.ALG_BP}
     _extra_nontunable = ("I_HARQ",)
 
     def __init__(self, **kw):
@@ -302,12 +306,16 @@ class NRLDPCDecoder(NRLDPC):
         self.I_HARQ = 0                   # NRLDPCDecoder.m:34
         self.iterations = 50              # :41
         self.early_termination, self.alpha, self.trim_rows = True, 0.75, True
+        self.algorithm = "Layered normalized min-sum"
         super().__init__(**kw)
 
     def _setup(self):                     # NRLDPCDecoder.m:107-130
         # `iterations` is read here only, as in the reference (:120): changing it later has no effect
+        if self.algorithm not in self.ALGORITHMS:
+            raise UnsupportedParameters("Valid values of algorithm are 'Layered normalized min-sum' and 'Sum-product'.")
         object.__setattr__(self, "_h", capi.Handle(self.BG, self.Z_c, int(self.iterations),
-                                                   bool(self.early_termination), float(self.alpha)))
+                                                   bool(self.early_termination), float(self.alpha),
+                                                   algorithm=self.ALGORITHMS[self.algorithm]))
         self._reset()
 
     def _reset(self):                     # resetImpl, :343-356
@@ -327,7 +335,7 @@ class NRLDPCDecoder(NRLDPC):
         has a zero LLR on a degree-1 variable and sends zero messages for ever."""
         Z, kcols = self.Z_c, 22 if self.BG == 1 else 10
         rows_all = 46 if self.BG == 1 else 42
-        if not self.trim_rows:
+        if not self.trim_rows or self.algorithm == "Sum-product":
             return rows_all
         nfill = self.K - max(self.K_prime, 2 * Z) if self.K > max(self.K_prime, 2 * Z) else 0
         span = self.k_0 + E_max + nfill  # last circular-buffer index touched (filler is skipped)

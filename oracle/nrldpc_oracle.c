@@ -512,8 +512,8 @@ ORC_API int orc_decode_nms_f16(int bg, int Z, int n_rows, int max_iters, int ear
  * argument is clipped to +-(1 - 2^-53) so that +inf filler LLRs cannot produce inf - inf.
  * Uses the whole H (the reference always passes the full matrix), n_rows <= 0 => all rows.
  * ---------------------------------------------------------------------------------------- */
-static int decode_bp_one(int bg, int Z, int ils, int n_rows, int max_iters, const int *vidx, const double *llr,
-                         uint8_t *hard_info, uint8_t *parity_ok) {
+static int decode_bp_one(int bg, int Z, int ils, int n_rows, int max_iters, int early_term, const int *vidx,
+                         const double *llr, uint8_t *hard_info, double *app_out, uint8_t *parity_ok) {
     int R, C, Kc, E;
     bg_dims(bg, &R, &C, &Kc, &E);
     const unsigned char *er = bg_row(bg);
@@ -554,10 +554,11 @@ static int decode_bp_one(int bg, int Z, int ils, int n_rows, int max_iters, cons
                     par ^= Q[vidx[(size_t)e * Z + z]] < 0.0;
                 if (par) { ok = 0; break; }
             }
-        if (ok) break;
+        if (ok && early_term) break;   /* early_term = 1 is the reference's setting (NRLDPCDecoder.m:120) */
     }
     if (it == 0) for (int i = 0; i < nV; ++i) Q[i] = llr[i];
     for (int k = 0; k < Kc * Z; ++k) hard_info[k] = Q[k] < 0.0;
+    if (app_out) memcpy(app_out, Q, sizeof(double) * nV);
     if (parity_ok) *parity_ok = (uint8_t)ok;
     free(q); free(rm); free(Q);
     return it;
@@ -574,8 +575,29 @@ ORC_API int orc_decode_bp(int bg, int Z, int n_rows, int max_iters, const double
     int *vidx = build_vidx(bg, Z, ils);
 #pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
     for (long b = 0; b < batch; ++b) {
-        int it = decode_bp_one(bg, Z, ils, n_rows, max_iters, vidx, llr + b * nV, hard_info + b * K,
+        int it = decode_bp_one(bg, Z, ils, n_rows, max_iters, 1, vidx, llr + b * nV, hard_info + b * K, NULL,
                                parity_ok ? parity_ok + b : NULL);
+        if (iters_out) iters_out[b] = it;
+    }
+    free(vidx);
+    return 0;
+}
+
+/* Same with the termination rule selectable (early_term = 0: 'Maximum iteration count') and the a-posteriori
+ * values returned: the checker of the device's NRLDPC_ALG_BP kernel (tests/test_gpu_parity.py). */
+ORC_API int orc_decode_bp_ex(int bg, int Z, int n_rows, int max_iters, int early_term, const double *llr, long batch,
+                             uint8_t *hard_info, double *app_out, int32_t *iters_out, uint8_t *parity_ok, int n_threads) {
+    int R, C, Kc, E, ils = orc_set_index(Z);
+    if ((bg != 1 && bg != 2) || ils < 0 || max_iters < 1) return -1;
+    bg_dims(bg, &R, &C, &Kc, &E);
+    if (n_rows <= 0 || n_rows > R) n_rows = R;
+    if (n_threads < 1) n_threads = 1;
+    const long nV = (long)C * Z, K = (long)Kc * Z;
+    int *vidx = build_vidx(bg, Z, ils);
+#pragma omp parallel for schedule(dynamic, 1) num_threads(n_threads)
+    for (long b = 0; b < batch; ++b) {
+        int it = decode_bp_one(bg, Z, ils, n_rows, max_iters, early_term, vidx, llr + b * nV, hard_info + b * K,
+                               app_out ? app_out + b * nV : NULL, parity_ok ? parity_ok + b : NULL);
         if (iters_out) iters_out[b] = it;
     }
     free(vidx);
@@ -596,7 +618,7 @@ ORC_API int orc_decode_bp_f32(int bg, int Z, int n_rows, int max_iters, const fl
     for (long b = 0; b < batch; ++b) {
         double *d = (double *)malloc(sizeof(double) * nV);
         for (long i = 0; i < nV; ++i) d[i] = llr[b * nV + i];
-        int it = decode_bp_one(bg, Z, ils, n_rows, max_iters, vidx, d, hard_info + b * K,
+        int it = decode_bp_one(bg, Z, ils, n_rows, max_iters, 1, vidx, d, hard_info + b * K, NULL,
                                parity_ok ? parity_ok + b : NULL);
         if (iters_out) iters_out[b] = it;
         free(d);

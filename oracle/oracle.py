@@ -141,8 +141,9 @@ def f16_widen(h):
     return out
 
 
-def decode_bp(bg, Z, llr, max_iters=8, n_rows=0, n_threads=None):
-    """Oracle B (flooding sum-product, f64, parity-check termination)."""
+def decode_bp(bg, Z, llr, max_iters=8, n_rows=0, n_threads=None, early_term=True, want_app=False):
+    """Oracle B (flooding sum-product, f64; early_term=True is the reference's parity-check termination).
+    float32 input is widened exactly to float64, as the GPU boundary does."""
     d = dims(bg, Z)
     nt = n_threads or os.cpu_count() or 1
     llr = np.ascontiguousarray(llr)
@@ -151,16 +152,19 @@ def decode_bp(bg, Z, llr, max_iters=8, n_rows=0, n_threads=None):
     hard = np.zeros((B, d["K"]), dtype=np.uint8)
     iters = np.zeros(B, dtype=np.int32)
     ok = np.zeros(B, dtype=np.uint8)
-    if llr2.dtype == np.float32:
+    app = None
+    if llr2.dtype == np.float32 and early_term and not want_app:
         rc = lib().orc_decode_bp_f32(bg, Z, n_rows, max_iters, _p(llr2, C.c_float), C.c_long(B),
                                      _p(hard, C.c_uint8), _p(iters, C.c_int32), _p(ok, C.c_uint8), nt)
     else:
         llr2 = np.ascontiguousarray(llr2, dtype=np.float64)
-        rc = lib().orc_decode_bp(bg, Z, n_rows, max_iters, _p(llr2, C.c_double), C.c_long(B),
-                                 _p(hard, C.c_uint8), _p(iters, C.c_int32), _p(ok, C.c_uint8), nt)
+        app = np.zeros((B, d["ncw"]), dtype=np.float64) if want_app else None
+        rc = lib().orc_decode_bp_ex(bg, Z, n_rows, max_iters, int(bool(early_term)), _p(llr2, C.c_double), C.c_long(B),
+                                    _p(hard, C.c_uint8), _p(app, C.c_double) if want_app else None,
+                                    _p(iters, C.c_int32), _p(ok, C.c_uint8), nt)
     if rc:
         raise RuntimeError(f"oracle decode_bp rc={rc}")
-    return dict(hard=hard, iters=iters, parity_ok=ok)
+    return dict(hard=hard, app=app, iters=iters, parity_ok=ok)
 
 
 FILL = 0xFF

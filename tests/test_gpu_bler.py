@@ -113,3 +113,51 @@ def test_device_crc_matches_oracle_and_bler_criterion(O):
         assert ca[0] == cb[0] == 256 and ca[1] == cb[1], (esn0, ca, cb)     # symmetric decoder: same noise, same failures
     assert 0 < ca[1] + cb[1]
     a.close(); b.close()
+
+
+def test_bler_reference_algorithm_mode_matches_oracle_b(O):
+    """algorithm = NRLDPC_ALG_BP through the device loop: on the LLRs the loop generated, block decisions and
+    iteration counts equal the CPU restatement of the reference's decoder (flooding sum-product, float64, whole H),
+    so the BLER curve of this mode IS the reference algorithm's curve (0 dB apart), for BASELINE configs 1 and 3."""
+    from ldpc_3gpp_matlab_b200 import capi
+    from ldpc_3gpp_matlab_b200.bler import BlerSimulator
+    for (A, R, BG, esn0s, Z, rows) in ((20, 0.2, 2, (0.0, 1.5, 3.0), 6, 42), (400, 0.2, 2, (-3.0, -2.4), 52, 42)):
+        sim = BlerSimulator(A, R, BG, iterations=8, early_termination=True, batch=512, seed=11, algorithm=capi.ALG_BP)
+        assert (sim.Z, sim.n_rows) == (Z, rows)
+        seen_err = seen_ok = False
+        for esn0 in esn0s:
+            c, _ = sim.run_batch(esn0)
+            llr, hard, iters = sim.llr.cpu().numpy(), sim.hard.cpu().numpy(), sim.iters.cpu().numpy()
+            ref = O.decode_bp(BG, Z, llr, 8)
+            assert (ref["hard"] == hard).all() and (ref["iters"] == iters).all(), (A, esn0)
+            seen_err |= c[1] > 0
+            seen_ok |= c[1] < c[0]
+        assert seen_err and seen_ok
+        sim.close()
+
+
+def test_host_mirror_sum_product_option(O):
+    """NRLDPCDecoder(algorithm='Sum-product'): same step()/reset() API, the reference's algorithm underneath."""
+    from ldpc_3gpp_matlab_b200 import capi
+    from ldpc_3gpp_matlab_b200.nrldpc import NRLDPCDecoder, NRLDPCEncoder
+    rng = np.random.default_rng(21)
+    enc = NRLDPCEncoder(BG=2, A=400, G=2000)
+    dec = NRLDPCDecoder(BG=2, A=400, G=2000, iterations=8, algorithm="Sum-product")
+    nms = NRLDPCDecoder(BG=2, A=400, G=2000, iterations=8)
+    n_ok = 0
+    for _ in range(6):
+        a = rng.integers(0, 2, 400).astype(np.float64)
+        g = enc.step(a)
+        s2 = 10 ** (2.0 / 10)
+        y = (1 - 2 * g) + rng.normal(0, np.sqrt(s2 / 2), g.shape)     # -2 dB: both decoders succeed most of the time
+        g_tilde = 4 * y / s2
+        a_hat = dec.step(g_tilde)
+        assert a_hat.size in (0, 400)
+        if a_hat.size:
+            assert (a_hat == a).all()
+            n_ok += 1
+        nms.step(g_tilde)
+    assert n_ok >= 3 and dec._active_rows(2000) == 42 and nms._active_rows(2000) == 33
+    with pytest.raises(capi.UnsupportedParameters):
+        NRLDPCDecoder(BG=2, A=400, G=2000, algorithm="bogus").step(g_tilde)
+    enc.release(); dec.release(); nms.release()

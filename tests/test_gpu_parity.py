@@ -444,3 +444,127 @@ def test_decode16_half_transport(capi, O):
             torch.cuda.synchronize()
             assert (dh.cpu().numpy() == hard).all()
             h.close()
+
+
+# ---- NRLDPC_ALG_BP: the reference's own algorithm (flooding sum-product, float64) on the device -------------
+# Checker: oracle B (oracle/nrldpc_oracle.c, decode_bp_one), the restatement of MathWorks' documented comm.LDPCDecoder
+# algorithm as configured at NRLDPCDecoder.m:120.  Kernel and oracle perform every +, -, * in the same order; they
+# differ only in the tanh / atanh library (CUDA vs glibc, ~1 ulp each).  Stated bar: hard decisions, iteration counts
+# and parity flags IDENTICAL; a-posteriori values within 1e-9 relative (float64 path) / float32 rounding of that.
+BP_RTOL = 1e-9
+
+
+def _bp_close(app, ref, rtol):
+    fin = np.isfinite(ref)
+    assert (np.isfinite(app) == fin).all()
+    assert (app[~fin] == ref[~fin]).all()            # +-inf fillers stay +-inf
+    return bool((np.abs(app[fin] - ref[fin]) <= rtol * np.maximum(1.0, np.abs(ref[fin]))).all())
+
+
+@pytest.mark.parametrize("bg", [1, 2])
+def test_decode_bp_matches_reference_algorithm_all_set_indices(capi, O, bg):
+    """One lifting size per set index (plus the smallest and the largest), ragged batches, filler (+inf), punctured
+    zeros, both termination rules; float64 buffers (nrldpc_decode64) as the reference passes them."""
+    rng = np.random.default_rng(900 + bg)
+    for Z in (2, 3, 5, 7, 9, 11, 13, 15, 36, 52, 96, 208, 384):
+        d = O.dims(bg, Z)
+        B = 5 if Z > 100 else 9
+        E = int(d["N"] * rng.uniform(0.4, 1.0)) // 2 * 2
+        filler = int(rng.integers(0, 3)) * (Z // 2)
+        info, llr = make_llr(O, bg, Z, B, E, rng.uniform(0.0, 3.0), rng, filler=filler)
+        llr64 = llr.astype(np.float64) * 1.000000001   # genuinely double-valued inputs
+        for et in (True, False):
+            ref = O.decode_bp(bg, Z, llr64, 6, early_term=et, want_app=True)
+            h = capi.Handle(bg, Z, 6, et, algorithm=capi.ALG_BP)
+            out = h.decode(llr64, want_soft=True)
+            h.close()
+            assert out["app"].dtype == np.float64
+            assert (out["hard"] == ref["hard"]).all(), (bg, Z, et)
+            assert (out["iters"] == ref["iters"]).all(), (bg, Z, et, out["iters"], ref["iters"])
+            assert (out["parity_ok"] == ref["parity_ok"]).all(), (bg, Z, et)
+            assert _bp_close(out["app"], ref["app"], BP_RTOL), (bg, Z, et)
+
+
+@pytest.mark.parametrize("bg,Z,rows", [(1, 384, 46), (1, 384, 5), (2, 52, 33), (2, 6, 13), (1, 30, 4)])
+def test_decode_bp_float32_buffers_special_values_and_row_trimming(capi, O, bg, Z, rows):
+    """nrldpc_decode (float32 buffers) in BP mode: inputs are widened exactly; NaN and +inf mark filler, -inf, zeros,
+    -0.0 and huge magnitudes go through the same arithmetic as in the restatement."""
+    rng = np.random.default_rng(Z + rows + 5)
+    d = O.dims(bg, Z)
+    B = 6
+    llr = (rng.normal(1.0, 3, (B, d["ncw"]))).astype(np.float32)
+    llr[:, :2 * Z] = 0
+    llr[:, (d["kcols"] + rows) * Z:] = 0
+    llr[0, 3 * Z:3 * Z + Z // 2] = np.inf
+    llr[1, 3 * Z:3 * Z + Z // 2] = np.nan
+    llr[2, 5 * Z] = -np.inf
+    llr[3, ::7] = 0.0
+    llr[3, 1::11] = -0.0
+    llr[4, 2 * Z::5] *= 1e20
+    llr[5] *= 100.0
+    ref_in = llr.astype(np.float64)
+    ref_in[np.isnan(ref_in)] = np.inf     # NRLDPCDecoder.m:264
+    for et in (True, False):
+        ref = O.decode_bp(bg, Z, ref_in, 5, n_rows=rows, early_term=et, want_app=True)
+        h = capi.Handle(bg, Z, 5, et, algorithm=capi.ALG_BP)
+        out = h.decode(llr, n_rows=rows, want_soft=True)
+        h.close()
+        assert (out["hard"] == ref["hard"]).all() and (out["iters"] == ref["iters"]).all()
+        assert (out["parity_ok"] == ref["parity_ok"]).all()
+        assert out["app"].dtype == np.float32
+        with np.errstate(over="ignore"):
+            ref32 = ref["app"].astype(np.float32)
+        assert _bp_close(out["app"].astype(np.float64), ref32.astype(np.float64), 1e-6)
+
+
+def test_decode_bp_headline_code_and_device_buffers(capi, O):
+    """BG1 Z=384 rate 1/3 near its waterfall through device pointers (torch tensors): identical block decisions and
+    iteration counts to the restatement of the reference's decoder; then the same call on binary16 and float64
+    device buffers (transport conversions in front of the same kernel)."""
+    import torch
+    rng = np.random.default_rng(4242)
+    info, llr = make_llr(O, 1, 384, 24, 25272, -0.6, rng)
+    ref = O.decode_bp(1, 384, llr, 12, early_term=True)
+    h = capi.Handle(1, 384, 12, True, algorithm=capi.ALG_BP)
+    dev = torch.device("cuda:0")
+    t_llr = torch.from_numpy(llr).to(dev)
+    hard = torch.zeros((24, h.K), dtype=torch.uint8, device=dev)
+    iters = torch.zeros(24, dtype=torch.int32, device=dev)
+    ok = torch.zeros(24, dtype=torch.uint8, device=dev)
+    h.decode_raw(t_llr, 24, hard, None, iters, ok, mem=capi.MEM_DEVICE, stream=None)
+    h.synchronize()
+    assert (hard.cpu().numpy() == ref["hard"]).all()
+    assert (iters.cpu().numpy() == ref["iters"]).all() and (ok.cpu().numpy() == ref["parity_ok"]).all()
+    assert ref["iters"].min() < 12 and ref["iters"].max() >= 8    # the operating point exercises early stopping
+    # float64 device buffers
+    t64 = t_llr.double()
+    hard2 = torch.zeros_like(hard)
+    h.decode64_raw(t64, 24, hard2, None, iters, ok, mem=capi.MEM_DEVICE, stream=None)
+    h.synchronize()
+    assert (hard2.cpu().numpy() == ref["hard"]).all() and (iters.cpu().numpy() == ref["iters"]).all()
+    # binary16 transport: the restatement sees the same rounded values
+    l16 = llr.astype(np.float16)
+    ref16 = O.decode_bp(1, 384, l16.astype(np.float32), 12, early_term=True)
+    h.decode16_raw(torch.from_numpy(l16).to(dev), 24, hard2, None, iters, ok, mem=capi.MEM_DEVICE, stream=None)
+    h.synchronize()
+    assert (hard2.cpu().numpy() == ref16["hard"]).all() and (iters.cpu().numpy() == ref16["iters"]).all()
+    h.close()
+
+
+def test_decode64_with_default_algorithm_rounds_to_float32(capi, O):
+    """nrldpc_decode64 in front of the min-sum kernel: doubles are rounded to float32 on the device; app_soft in
+    float64 is refused (UnsupportedParameters), BP + packed-half is refused at create."""
+    rng = np.random.default_rng(5)
+    info, llr = make_llr(O, 2, 52, 11, 2000, 1.0, rng, filler=104)
+    llr64 = llr.astype(np.float64) * (1 + 1e-12)
+    ref = O.decode_nms(2, 52, llr64.astype(np.float32), 8, early_term=True)
+    h = capi.Handle(2, 52, 8, True)
+    out = h.decode(llr64)
+    assert (out["hard"] == ref["hard"]).all() and (out["iters"] == ref["iters"]).all()
+    with pytest.raises(capi.UnsupportedParameters):
+        h.decode(llr64, want_soft=True)
+    h.close()
+    with pytest.raises(capi.UnsupportedParameters):
+        capi.Handle(2, 52, 8, True, llr_dtype=capi.F16X2, algorithm=capi.ALG_BP)
+    with pytest.raises(capi.UnsupportedParameters):
+        capi.Handle(2, 52, 8, True, algorithm=7)

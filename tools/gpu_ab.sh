@@ -1,0 +1,6 @@
+#!/bin/bash
+# A/B helper: parity tests, then the headline bench twice per arithmetic mode.
+python -m pytest tests -x -q -m gpu 2>&1 | tail -3
+for dt in f32 f16x2; do for i in 1 2; do
+python bench.py --steps 100 --warmup 3 --no-cpu-baseline --no-e2e --no-alt --llr-dtype $dt 2>&1 | tail -1 | python -c "import json,sys;d=json.loads(sys.stdin.read());print('$dt',round(d['value'],3),round(d['ms_per_step'],4))"
+done; done
