@@ -172,9 +172,10 @@ __device__ __forceinline__ uint32_t edge_addr(const Lane &l, const uint2 d, cons
 }
 
 // One check row of degree DEG for check z.  (om1, om2, ometa) is the compressed message record
-// written for this check in the previous iteration: om1/om2 = alpha*min1, alpha*min2 (their sign
-// bits are ignored), ometa = arg-min index in bits 0..4 and the messages' sign bits MSB-first above
-// it (edge e at bit 5 + DEG-1-e).
+// written for this check in the previous iteration: om1/om2 = alpha*min1, alpha*min2 with the row's
+// sign product sg in their sign bit, ometa = arg-min index in bits 0..4 and the sign bits of the
+// row's t values MSB-first above it (edge e at bit 5 + DEG-1-e): message e = (e == arg ? om2 : om1)
+// with its sign bit flipped by sign(t_e), i.e. sign(c_e) = sg ^ sign(t_e).
 // In the first iteration the record is all zeros (previous messages +0: x - (+0) = x exactly).
 // IDENT_LAST: the row's last edge is an identity circulant (extension parity column, shift 0 for
 // every lifting-size set: TS 38.212 tables) -> no wrap.
@@ -193,8 +194,8 @@ __device__ __forceinline__ uint4 process_row(const Lane &l, const uint2 *__restr
         addr[e] = a;
         const float x = lds_f32(a);
         const uint32_t mag = (oarg == (uint32_t)e) ? om2 : om1;
-        // magnitude bits of the stored minimum, sign bit of edge e (meta bit 5 + DEG-1-e -> bit 31)
-        const uint32_t c = bitselect(mag, ometa << (26 - (DEG - 1 - e)), 0x80000000u);
+        // stored minimum (carries sg) with its sign bit flipped by sign(t_e) (meta bit 5 + DEG-1-e -> bit 31): one LOP3
+        const uint32_t c = mag ^ ((ometa << (26 - (DEG - 1 - e))) & 0x80000000u);
         const float tt = __fsub_rn(x, __uint_as_float(c));
         t[e] = tt;
         const float ab = fabsf(tt);
@@ -210,10 +211,11 @@ __device__ __forceinline__ uint4 process_row(const Lane &l, const uint2 *__restr
         sx ^= __float_as_uint(tt);
         ts = __funnelshift_l(__float_as_uint(tt), ts, 1);  // ts = ts << 1 | signbit(tt)
     }
-    const uint32_t sg = sx & 0x80000000u;
-    // both candidate magnitudes with the row's sign product folded in
-    uint32_t m1ss = __float_as_uint(__fmul_rn(alpha, m1)) | sg;
-    uint32_t m2ss = __float_as_uint(__fmul_rn(alpha, m2)) | sg;
+    // both candidate magnitudes with the row's sign product folded in: multiply by alpha carrying the sign
+    // (m >= 0, so the product's sign bit is sg also when m = 0: bit-identical to (alpha*m) | sg)
+    const float alpha_s = __uint_as_float(bitselect(__float_as_uint(alpha), sx, 0x80000000u));
+    uint32_t m1ss = __float_as_uint(__fmul_rn(alpha_s, m1));
+    uint32_t m2ss = __float_as_uint(__fmul_rn(alpha_s, m2));
     asm volatile("" : "+r"(m1ss), "+r"(m2ss));  // keep the sign folded per row, not re-derived per edge
     uint32_t arg = 0;
 #pragma unroll
@@ -225,9 +227,7 @@ __device__ __forceinline__ uint4 process_row(const Lane &l, const uint2 *__restr
         const float c = __uint_as_float(sel ^ (__float_as_uint(t[e]) & 0x80000000u));
         sts_f32(addr[e], __fadd_rn(t[e], c));
     }
-    // sign of message e = sg ^ sign(t_e)
-    const uint32_t csg = sg ? (ts ^ ((1u << DEG) - 1u)) : ts;
-    return make_uint4(m1ss, m2ss, arg | (csg << 5), 0u);
+    return make_uint4(m1ss, m2ss, arg | (ts << 5), 0u);
 }
 
 // ---- pieces shared by all kernel variants --------------------------------------------------------
@@ -334,37 +334,38 @@ __device__ __forceinline__ void iteration_looped(const DecArgs &a, DecCtx &c, co
 // ---- one full iteration over the layers: fully unrolled for base graph BG -----------------------
 // One instantiation serves every iteration: the unrolled layer code of BG1 is ~100 KB of SASS and
 // has to stay resident in the SM's instruction cache (per-iteration specialisations were measured
-// to thrash it).  ld_from / ld_to: the next layer's record is prefetched while processing layer R
-// iff ld_from <= R < ld_to (first iteration: only across the iteration boundary; last: never across).
+// to thrash it).  The next layer's record is prefetched unconditionally while processing layer R: the
+// records of a codeword are zeroed before its first iteration (zero record = previous messages +0), and
+// the one prefetch across the end of the last iteration reads a stale record that is never used -- no
+// per-layer "is this the first / last iteration" tests on the ALU pipe.
 // FULL: every thread of the CTA owns a check for the whole decode (one codeword per CTA, Z a
 // multiple of 32): no per-thread activity test.
 template <int BG, int R, bool FULL>
 struct UnrolledRows {
-    static __device__ __forceinline__ void run(const DecArgs &a, DecCtx &c, const int ld_from, const int ld_to, const bool store_rec) {
-        if (R >= a.n_rows) return;
+    static __device__ __forceinline__ void run(const DecArgs &a, DecCtx &c, const bool store_rec) {
+        if (R >= 4 && R >= a.n_rows) return;   // n_rows >= 4 is validated by the host
         constexpr int DEG = BgShape<BG>::deg(R);
         constexpr int E0 = BgShape<BG>::start(R);
         if (FULL || !c.done) {
             // slot R+1; slot n_rows holds layer 0
-            uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
-            if (R >= ld_from && R < ld_to) nxt = ld_rec(c.my_rec, R + 1, c.pol);
+            const uint4 nxt = ld_rec(c.my_rec, R + 1, c.pol);
             const uint4 rec = process_row<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur.x, c.cur.y, c.cur.z, a.alpha);
             if (store_rec) st_rec(c.my_rec, R == 0 ? a.n_rows : R, rec, c.pol);
             c.cur = nxt;
         }
         __syncthreads();
-        UnrolledRows<BG, R + 1, FULL>::run(a, c, ld_from, ld_to, store_rec);
+        UnrolledRows<BG, R + 1, FULL>::run(a, c, store_rec);
     }
 };
 template <int BG, bool FULL>
 struct UnrolledRows<BG, BgShape<BG>::kRows, FULL> {
-    static __device__ __forceinline__ void run(const DecArgs &, DecCtx &, int, int, bool) {}
+    static __device__ __forceinline__ void run(const DecArgs &, DecCtx &, bool) {}
 };
 
 template <int BG, bool FULL>
 __device__ __forceinline__ void iteration_unrolled(const DecArgs &a, DecCtx &c, const int it) {
-    const bool first = it == 0, last = it + 1 == a.max_iters;
-    UnrolledRows<BG, 0, FULL>::run(a, c, first ? a.n_rows - 1 : 0, last ? a.n_rows - 1 : a.n_rows, !last);
+    const bool last = it + 1 == a.max_iters;
+    UnrolledRows<BG, 0, FULL>::run(a, c, !last);
 }
 
 // BG = 0: generic looped variant; BG = 1 / 2: layer loop unrolled for that base graph.
@@ -417,6 +418,9 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
         const bool active = lane_ok && slot < n_here;
         c.done = !active;
         c.cur = make_uint4(0u, 0u, 0u, 0u);
+        if (BG != 0 && active) {   // unrolled kernels prefetch unconditionally: iteration 1 must read zero records
+            for (int sl = 1; sl <= a.n_rows; ++sl) st_rec(c.my_rec, sl, make_uint4(0u, 0u, 0u, 0u), c.pol);
+        }
         int my_iters = 0;
         int my_ok = 0;
 

@@ -42,8 +42,8 @@ __device__ __forceinline__ float clamp_llr_h2(float x) { return __fadd_rn(fmaxf(
 
 // One check row of degree DEG for check z of a codeword pair.  Record layout (uint4; three words
 // when DEG <= 11, i.e. every layer but the four degree-19 ones of base graph 1):
-//   x, y : alpha*min1, alpha*min2 of both codewords (packed fp16; sign bits ignored on read)
-//   z    : sign bits of the messages on edges 0..min(DEG,16)-1: edge e at bit 15-(n0-1-e) of each half;
+//   x, y : alpha*min1, alpha*min2 of both codewords (packed fp16) with the row's sign product in their sign bits
+//   z    : sign bits of the row's t values (message sign = row sign ^ sign(t_e)) on edges 0..min(DEG,16)-1: edge e at bit 15-(n0-1-e) of each half;
 //          DEG <= 11: also the arg-min edge index of each codeword in bits 0..3 / 16..19
 //   w    : DEG > 11 only: arg-min edge indices in bits 0..4 / 16..20 and, for DEG > 16, the sign bits of
 //          edges 16..DEG-1 at the top of each half
@@ -69,7 +69,7 @@ __device__ __forceinline__ uint4 process_row_h2(const Lane &l, const uint2 *__re
         const uint32_t is_arg = __heq2_mask(as_h2(oargs), as_h2(e2));
         const uint32_t mag = bitselect(rec.x, rec.y, is_arg);
         const uint32_t sw = e < 16 ? rec.z << (N0 - 1 - e) : rec.w << (DEG - 1 - e);
-        const uint32_t c = bitselect(mag, sw, kH2Sign);
+        const uint32_t c = mag ^ (sw & kH2Sign);
         const __half2 tt = __hsub2(as_h2(x), as_h2(c));
         t[e] = as_u32(tt);
         const __half2 ab = __habs2(tt);
@@ -90,9 +90,10 @@ __device__ __forceinline__ uint4 process_row_h2(const Lane &l, const uint2 *__re
     const __half2 m1raw = m1;
     m1 = __hmin2(m1, as_h2(kH2MsgCap));
     m2 = __hmin2(m2, as_h2(kH2MsgCap));
-    const uint32_t sg = sx & kH2Sign;
-    uint32_t m1ss = as_u32(__hmul2(as_h2(alpha2), m1)) | sg;
-    uint32_t m2ss = as_u32(__hmul2(as_h2(alpha2), m2)) | sg;
+    // multiply by alpha carrying the row's sign product (m >= 0: bit-identical to (alpha*m) | sg, also for m = 0)
+    const uint32_t alpha_s = bitselect(alpha2, sx, kH2Sign);
+    uint32_t m1ss = as_u32(__hmul2(as_h2(alpha_s), m1));
+    uint32_t m2ss = as_u32(__hmul2(as_h2(alpha_s), m2));
     asm volatile("" : "+r"(m1ss), "+r"(m2ss));
     uint32_t args = 0;
 #pragma unroll
@@ -104,12 +105,10 @@ __device__ __forceinline__ uint4 process_row_h2(const Lane &l, const uint2 *__re
         const uint32_t c = sel ^ (t[e] & kH2Sign);
         sts_u32(addr[e], as_u32(__hadd2(as_h2(t[e]), as_h2(c))));
     }
-    // sign of message e = row sign ^ sign(t_e), per codeword
-    const uint32_t flip = ((sx >> 15) & 0x00010001u) * 0xffffu;
     constexpr uint32_t F0 = (((1u << N0) - 1u) << (16 - N0)) * 0x00010001u;
     constexpr uint32_t F1 = N1 > 0 ? (((1u << N1) - 1u) << (16 - N1)) * 0x00010001u : 0u;
-    const uint32_t z = (s0 ^ (flip & F0)) | (W3 ? args : 0u);
-    const uint32_t w = W3 ? 0u : (((s1 ^ flip) & F1) | args);
+    const uint32_t z = (s0 & F0) | (W3 ? args : 0u);
+    const uint32_t w = W3 ? 0u : ((s1 & F1) | args);
     return make_uint4(m1ss, m2ss, z, w);
 }
 

@@ -15,6 +15,8 @@ classdef B200LDPCDecoder < matlab.System
         IterationTerminationCondition = 'Maximum iteration count';
         Alpha = 0.75;          % min-sum normalisation (engine-specific)
         ActiveRows = 0;        % 0 = all base rows (engine-specific)
+        Algorithm = 'Layered normalized min-sum';  % or 'Sum-product': comm.LDPCDecoder's own flooding sum-product in
+                                                   % float64 (same BLER curve and iteration counts as the reference)
     end
     properties (Access = private)
         handle = uint64(0);
@@ -41,7 +43,8 @@ classdef B200LDPCDecoder < matlab.System
                 error('ldpc_3gpp_matlab:UnsupportedParameters','H does not match TS 38.212 for BG%d, Z=%d.', BG, Z);
             end
             early = strcmp(obj.IterationTerminationCondition, 'Parity check satisfied');
-            obj.handle = nrldpc_mex('create', BG, Z, obj.MaximumIterationCount, double(early), obj.Alpha);
+            alg = double(strcmp(obj.Algorithm, 'Sum-product'));
+            obj.handle = nrldpc_mex('create', BG, Z, obj.MaximumIterationCount, double(early), obj.Alpha, 0, alg);
         end
         function c_hat = stepImpl(obj, cw_tilde)
             c_hat = nrldpc_mex('decode', obj.handle, double(cw_tilde), obj.ActiveRows);

@@ -6,7 +6,8 @@
 //     mex -I../include nrldpc_mex.cpp -L../ldpc_3gpp_matlab_b200 -lnrldpc_b200
 //
 // Usage from MATLAB (see B200LDPCDecoder.m / B200LDPCEncoder.m):
-//     h     = nrldpc_mex('create', BG, Z, max_iters, early_term, alpha);
+//     h     = nrldpc_mex('create', BG, Z, max_iters, early_term, alpha, llr_dtype, algorithm);
+//             algorithm: 0 = layered normalized min-sum (default), 1 = the reference's flooding sum-product in float64
 //     c_hat = nrldpc_mex('decode', h, cw_tilde, n_rows);   % cw_tilde: (68Z or 52Z) x batch double, +inf = filler
 //     cw    = nrldpc_mex('encode', h, c);                  % c: K x batch, values 0/1
 //     nrldpc_mex('destroy', h);
@@ -47,6 +48,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         cfg.alpha = nrhs > 5 ? (float)mxGetScalar(prhs[5]) : 0.75f;
         cfg.device = -1;
         cfg.llr_dtype = nrhs > 6 ? (int32_t)mxGetScalar(prhs[6]) : NRLDPC_F32;   /* NRLDPC_F16X2 = packed-half decoder */
+        cfg.algorithm = nrhs > 7 ? (int32_t)mxGetScalar(prhs[7]) : NRLDPC_ALG_NMS; /* NRLDPC_ALG_BP = comm.LDPCDecoder's own algorithm */
         nrldpc_t *h = nullptr;
         check(nrldpc_create(&h, &cfg), nullptr);
         plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
@@ -69,11 +71,11 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
             mexErrMsgIdAndTxt("ldpc_3gpp_matlab:Error", "cw_tilde should have %d rows.", d.n_cw);
         const int64_t batch = (int64_t)mxGetN(in);
         const int n_rows = nrhs > 3 ? (int)mxGetScalar(prhs[3]) : 0;
-        const double *x = mxGetPr(in);
-        std::vector<float> llr((size_t)batch * d.n_cw);
-        for (size_t i = 0; i < llr.size(); ++i) llr[i] = (float)x[i];  // +inf stays +inf; NaN = filler too
+        // the doubles go to the library as they are (nrldpc_decode64): the sum-product mode computes on them in
+        // float64 like comm.LDPCDecoder, the min-sum mode rounds them to float32 on the device (+inf stays +inf,
+        // NaN = filler too) -- no conversion loop on the MATLAB thread
         std::vector<uint8_t> hard((size_t)batch * d.K);
-        check(nrldpc_decode(h, llr.data(), batch, n_rows, hard.data(), nullptr, nullptr, nullptr, NRLDPC_MEM_HOST, nullptr), h);
+        check(nrldpc_decode64(h, mxGetPr(in), batch, n_rows, hard.data(), nullptr, nullptr, nullptr, NRLDPC_MEM_HOST, nullptr), h);
         plhs[0] = mxCreateLogicalMatrix(d.K, batch);  // comm.LDPCDecoder returns logical K x 1 (NRLDPCDecoder.m:265)
         mxLogical *o = mxGetLogicals(plhs[0]);
         for (size_t i = 0; i < hard.size(); ++i) o[i] = hard[i] != 0;
