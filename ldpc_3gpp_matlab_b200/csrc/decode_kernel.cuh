@@ -78,12 +78,33 @@ template <> struct BgShape<1> {
     static constexpr int kRows = NRLDPC_BG1_ROWS;
     static __host__ __device__ constexpr int deg(int r) { return nrldpc_bg1_deg[r]; }
     static __host__ __device__ constexpr int start(int r) { return nrldpc_bg1_start[r]; }
+    static __host__ __device__ constexpr int col(int e) { return nrldpc_bg1_col[e]; }
 };
 template <> struct BgShape<2> {
     static constexpr int kRows = NRLDPC_BG2_ROWS;
     static __host__ __device__ constexpr int deg(int r) { return nrldpc_bg2_deg[r]; }
     static __host__ __device__ constexpr int start(int r) { return nrldpc_bg2_start[r]; }
+    static __host__ __device__ constexpr int col(int e) { return nrldpc_bg2_col[e]; }
 };
+
+// Row orthogonality of the TS 38.212 base graphs: from row 20 on (and for a few earlier rows) consecutive base rows
+// touch DISJOINT block columns, so the two layers update disjoint variables and may run as one layer with a single
+// barrier -- the result is bit-identical to running them one after the other.  Pairs are formed greedily in row
+// order: BG1 (16,17), (20,21), (22,23) ... (44,45): 46 layers -> 32 barriers; BG2 (11,12), (17,18), (20,21) ... : 42 -> 29.
+template <int BG>
+__host__ __device__ constexpr bool rows_disjoint(int r) {   // rows r and r + 1
+    if (r < 0 || r + 1 >= BgShape<BG>::kRows) return false;
+    for (int i = BgShape<BG>::start(r); i < BgShape<BG>::start(r + 1); ++i)
+        for (int j = BgShape<BG>::start(r + 1); j < BgShape<BG>::start(r + 2); ++j)
+            if (BgShape<BG>::col(i) == BgShape<BG>::col(j)) return false;
+    return true;
+}
+template <int BG>
+__host__ __device__ constexpr bool pair_first(int r) {      // row r opens a pair (r, r + 1)
+    bool first = false;
+    for (int q = 0; q <= r; ++q) first = !first && rows_disjoint<BG>(q);   // first(q) = !first(q-1) && disjoint(q)
+    return first;
+}
 
 __device__ __forceinline__ float clamp_llr(float x) {
     // NaN marks filler upstream (NRLDPCDecoder.m:224,264): fminf(NaN, M) = M.  The final + 0 turns -0 into +0:
@@ -179,11 +200,18 @@ __device__ __forceinline__ uint32_t edge_addr(const Lane &l, const uint2 d, cons
 // In the first iteration the record is all zeros (previous messages +0: x - (+0) = x exactly).
 // IDENT_LAST: the row's last edge is an identity circulant (extension parity column, shift 0 for
 // every lifting-size set: TS 38.212 tables) -> no wrap.
-template <int DEG, bool IDENT_LAST, bool ONE_CW>
-__device__ __forceinline__ uint4 process_row(const Lane &l, const uint2 *__restrict__ ed, const uint32_t om1,
-                                             const uint32_t om2, const uint32_t ometa, const float alpha) {
+template <int DEG>
+struct RowState {
     float t[DEG];
     uint32_t addr[DEG];
+    float m1, m2;
+    uint32_t sx, ts;
+};
+
+// first half of a row update: addresses, loads, t_e = app - c_e, the two minima and the sign bits
+template <int DEG, bool IDENT_LAST, bool ONE_CW>
+__device__ __forceinline__ void row_gather(const Lane &l, const uint2 *__restrict__ ed, const uint32_t om1,
+                                           const uint32_t om2, const uint32_t ometa, RowState<DEG> &s) {
     float m1 = 0.f, m2 = 0.f;
     uint32_t sx = 0, ts = 0;
     const uint32_t oarg = ometa & 31u;
@@ -191,13 +219,13 @@ __device__ __forceinline__ uint4 process_row(const Lane &l, const uint2 *__restr
     for (int e = 0; e < DEG; ++e) {
         const uint2 d = ed[e];
         const uint32_t a = edge_addr<ONE_CW>(l, d, IDENT_LAST && e == DEG - 1);
-        addr[e] = a;
+        s.addr[e] = a;
         const float x = lds_f32(a);
         const uint32_t mag = (oarg == (uint32_t)e) ? om2 : om1;
         // stored minimum (carries sg) with its sign bit flipped by sign(t_e) (meta bit 5 + DEG-1-e -> bit 31): one LOP3
         const uint32_t c = mag ^ ((ometa << (26 - (DEG - 1 - e))) & 0x80000000u);
         const float tt = __fsub_rn(x, __uint_as_float(c));
-        t[e] = tt;
+        s.t[e] = tt;
         const float ab = fabsf(tt);
         if (e == 0) {
             m1 = ab;
@@ -211,23 +239,37 @@ __device__ __forceinline__ uint4 process_row(const Lane &l, const uint2 *__restr
         sx ^= __float_as_uint(tt);
         ts = __funnelshift_l(__float_as_uint(tt), ts, 1);  // ts = ts << 1 | signbit(tt)
     }
+    s.m1 = m1; s.m2 = m2; s.sx = sx; s.ts = ts;
+}
+
+// second half: new messages, APP write-back, the row's new record
+template <int DEG>
+__device__ __forceinline__ uint4 row_scatter(const RowState<DEG> &s, const float alpha) {
     // both candidate magnitudes with the row's sign product folded in: multiply by alpha carrying the sign
     // (m >= 0, so the product's sign bit is sg also when m = 0: bit-identical to (alpha*m) | sg)
-    const float alpha_s = __uint_as_float(bitselect(__float_as_uint(alpha), sx, 0x80000000u));
-    uint32_t m1ss = __float_as_uint(__fmul_rn(alpha_s, m1));
-    uint32_t m2ss = __float_as_uint(__fmul_rn(alpha_s, m2));
+    const float alpha_s = __uint_as_float(bitselect(__float_as_uint(alpha), s.sx, 0x80000000u));
+    uint32_t m1ss = __float_as_uint(__fmul_rn(alpha_s, s.m1));
+    uint32_t m2ss = __float_as_uint(__fmul_rn(alpha_s, s.m2));
     asm volatile("" : "+r"(m1ss), "+r"(m2ss));  // keep the sign folded per row, not re-derived per edge
     uint32_t arg = 0;
 #pragma unroll
     for (int e = 0; e < DEG; ++e) {
         // the arg-min edge is found by value: on a tie min2 == min1, so every tied edge gets the same message
-        const bool is_min = fabsf(t[e]) == m1;
+        const bool is_min = fabsf(s.t[e]) == s.m1;
         const uint32_t sel = is_min ? m2ss : m1ss;
         arg = is_min ? (uint32_t)e : arg;
-        const float c = __uint_as_float(sel ^ (__float_as_uint(t[e]) & 0x80000000u));
-        sts_f32(addr[e], __fadd_rn(t[e], c));
+        const float c = __uint_as_float(sel ^ (__float_as_uint(s.t[e]) & 0x80000000u));
+        sts_f32(s.addr[e], __fadd_rn(s.t[e], c));
     }
-    return make_uint4(m1ss, m2ss, arg | (ts << 5), 0u);
+    return make_uint4(m1ss, m2ss, arg | (s.ts << 5), 0u);
+}
+
+template <int DEG, bool IDENT_LAST, bool ONE_CW>
+__device__ __forceinline__ uint4 process_row(const Lane &l, const uint2 *__restrict__ ed, const uint32_t om1,
+                                             const uint32_t om2, const uint32_t ometa, const float alpha) {
+    RowState<DEG> s;
+    row_gather<DEG, IDENT_LAST, ONE_CW>(l, ed, om1, om2, ometa, s);
+    return row_scatter<DEG>(s, alpha);
 }
 
 // ---- pieces shared by all kernel variants --------------------------------------------------------
@@ -235,7 +277,7 @@ struct DecCtx {
     Lane l;
     uint32_t *my_rec;   // word 0 of this thread's record column
     uint64_t pol;
-    uint4 cur;
+    uint4 cur, cur2; // prefetched records of the next layer (and of its partner when the next layer is a pair)
     bool done;       // this thread does no row work (inactive lane, or its codeword has converged)
 };
 
@@ -346,15 +388,44 @@ struct UnrolledRows {
         if (R >= 4 && R >= a.n_rows) return;   // n_rows >= 4 is validated by the host
         constexpr int DEG = BgShape<BG>::deg(R);
         constexpr int E0 = BgShape<BG>::start(R);
-        if (FULL || !c.done) {
-            // slot R+1; slot n_rows holds layer 0
-            const uint4 nxt = ld_rec(c.my_rec, R + 1, c.pol);
-            const uint4 rec = process_row<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur.x, c.cur.y, c.cur.z, a.alpha);
-            if (store_rec) st_rec(c.my_rec, R == 0 ? a.n_rows : R, rec, c.pol);
-            c.cur = nxt;
+        constexpr bool PAIR = pair_first<BG>(R);
+        if (PAIR && R + 1 < a.n_rows) {
+            // rows R and R+1 touch disjoint block columns: one layer, one barrier
+            constexpr int DEG2 = BgShape<BG>::deg(PAIR ? R + 1 : R);
+            constexpr int E1 = BgShape<BG>::start(PAIR ? R + 1 : R);
+            if (FULL || !c.done) {
+                const uint4 nxt = ld_rec(c.my_rec, R + 2, c.pol);   // slot R+2 (slot n_rows holds layer 0)
+                uint4 nxt2 = nxt;
+                if (pair_first<BG>(R + 2)) nxt2 = ld_rec(c.my_rec, R + 3, c.pol);
+                RowState<DEG> s0;
+                RowState<DEG2> s1;
+                row_gather<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur.x, c.cur.y, c.cur.z, s0);
+                row_gather<DEG2, (R >= 4), FULL>(c.l, a.ed + E1, c.cur2.x, c.cur2.y, c.cur2.z, s1);
+                const uint4 rec0 = row_scatter<DEG>(s0, a.alpha);
+                const uint4 rec1 = row_scatter<DEG2>(s1, a.alpha);
+                if (store_rec) {
+                    st_rec(c.my_rec, R == 0 ? a.n_rows : R, rec0, c.pol);
+                    st_rec(c.my_rec, R + 1, rec1, c.pol);
+                }
+                c.cur = nxt;
+                c.cur2 = nxt2;
+            }
+            __syncthreads();
+            UnrolledRows<BG, (PAIR ? R + 2 : BgShape<BG>::kRows), FULL>::run(a, c, store_rec);
+        } else {
+            if (FULL || !c.done) {
+                const uint4 nxt = ld_rec(c.my_rec, R + 1, c.pol);   // slot R+1; slot n_rows holds layer 0
+                uint4 nxt2 = nxt;
+                if (!PAIR && pair_first<BG>(R + 1)) nxt2 = ld_rec(c.my_rec, R + 2, c.pol);
+                const uint4 rec = process_row<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur.x, c.cur.y, c.cur.z, a.alpha);
+                if (store_rec) st_rec(c.my_rec, R == 0 ? a.n_rows : R, rec, c.pol);
+                c.cur = nxt;
+                c.cur2 = nxt2;
+            }
+            __syncthreads();
+            // a pair opener running alone means R + 1 == n_rows: the iteration ends here
+            if (!PAIR) UnrolledRows<BG, R + 1, FULL>::run(a, c, store_rec);
         }
-        __syncthreads();
-        UnrolledRows<BG, R + 1, FULL>::run(a, c, store_rec);
     }
 };
 template <int BG, bool FULL>
@@ -418,6 +489,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
         const bool active = lane_ok && slot < n_here;
         c.done = !active;
         c.cur = make_uint4(0u, 0u, 0u, 0u);
+        c.cur2 = c.cur;
         if (BG != 0 && active) {   // unrolled kernels prefetch unconditionally: iteration 1 must read zero records
             for (int sl = 1; sl <= a.n_rows; ++sl) st_rec(c.my_rec, sl, make_uint4(0u, 0u, 0u, 0u), c.pol);
         }
