@@ -48,13 +48,18 @@ __device__ __forceinline__ float clamp_llr_h2(float x) { return __fadd_rn(fmaxf(
 //   w    : DEG > 11 only: arg-min edge indices in bits 0..4 / 16..20 and, for DEG > 16, the sign bits of
 //          edges 16..DEG-1 at the top of each half
 // Arg-min indices are compared as fp16 bit patterns (HSET2 without flush-to-zero).
-template <int DEG, bool IDENT_LAST, bool ONE_CW>
-__device__ __forceinline__ uint4 process_row_h2(const Lane &l, const uint2 *__restrict__ ed, const uint4 rec,
-                                                const uint32_t alpha2) {
-    constexpr int N0 = DEG < 16 ? DEG : 16;
-    constexpr int N1 = DEG - N0;
+template <int DEG>
+struct RowStateH2 {
     uint32_t t[DEG];
     uint32_t addr[DEG];
+    __half2 m1, m2;
+    uint32_t sx, s0, s1;
+};
+
+// first half of a row update (see row_gather in decode_kernel.cuh)
+template <int DEG, bool IDENT_LAST, bool ONE_CW>
+__device__ __forceinline__ void row_gather_h2(const Lane &l, const uint2 *__restrict__ ed, const uint4 rec, RowStateH2<DEG> &s) {
+    constexpr int N0 = DEG < 16 ? DEG : 16;
     __half2 m1 = as_h2(0u), m2 = as_h2(0u);
     uint32_t sx = 0, s0 = 0, s1 = 0;
     constexpr bool W3 = DEG <= 11;   // three-word record
@@ -63,7 +68,7 @@ __device__ __forceinline__ uint4 process_row_h2(const Lane &l, const uint2 *__re
     for (int e = 0; e < DEG; ++e) {
         const uint2 d = ed[e];
         const uint32_t a = edge_addr<ONE_CW>(l, d, IDENT_LAST && e == DEG - 1);
-        addr[e] = a;
+        s.addr[e] = a;
         const uint32_t x = lds_u32(a);
         const uint32_t e2 = (uint32_t)e * 0x00010001u;
         const uint32_t is_arg = __heq2_mask(as_h2(oargs), as_h2(e2));
@@ -71,7 +76,7 @@ __device__ __forceinline__ uint4 process_row_h2(const Lane &l, const uint2 *__re
         const uint32_t sw = e < 16 ? rec.z << (N0 - 1 - e) : rec.w << (DEG - 1 - e);
         const uint32_t c = mag ^ (sw & kH2Sign);
         const __half2 tt = __hsub2(as_h2(x), as_h2(c));
-        t[e] = as_u32(tt);
+        s.t[e] = as_u32(tt);
         const __half2 ab = __habs2(tt);
         if (e == 0) {
             m1 = ab;
@@ -87,11 +92,20 @@ __device__ __forceinline__ uint4 process_row_h2(const Lane &l, const uint2 *__re
         if (e < 16) s0 = bitselect(s0 >> 1, as_u32(tt), kH2Sign);
         else s1 = bitselect(s1 >> 1, as_u32(tt), kH2Sign);
     }
-    const __half2 m1raw = m1;
-    m1 = __hmin2(m1, as_h2(kH2MsgCap));
-    m2 = __hmin2(m2, as_h2(kH2MsgCap));
+    s.m1 = m1; s.m2 = m2; s.sx = sx; s.s0 = s0; s.s1 = s1;
+}
+
+// second half: new messages, APP write-back, the row's new record
+template <int DEG>
+__device__ __forceinline__ uint4 row_scatter_h2(const RowStateH2<DEG> &s, const uint32_t alpha2) {
+    constexpr int N0 = DEG < 16 ? DEG : 16;
+    constexpr int N1 = DEG - N0;
+    constexpr bool W3 = DEG <= 11;
+    const __half2 m1raw = s.m1;
+    const __half2 m1 = __hmin2(s.m1, as_h2(kH2MsgCap));
+    const __half2 m2 = __hmin2(s.m2, as_h2(kH2MsgCap));
     // multiply by alpha carrying the row's sign product (m >= 0: bit-identical to (alpha*m) | sg, also for m = 0)
-    const uint32_t alpha_s = bitselect(alpha2, sx, kH2Sign);
+    const uint32_t alpha_s = bitselect(alpha2, s.sx, kH2Sign);
     uint32_t m1ss = as_u32(__hmul2(as_h2(alpha_s), m1));
     uint32_t m2ss = as_u32(__hmul2(as_h2(alpha_s), m2));
     asm volatile("" : "+r"(m1ss), "+r"(m2ss));
@@ -99,17 +113,25 @@ __device__ __forceinline__ uint4 process_row_h2(const Lane &l, const uint2 *__re
 #pragma unroll
     for (int e = 0; e < DEG; ++e) {
         // arg-min edges found by value (ties: min2 == min1, every tied edge gets the same message)
-        const uint32_t is_min = __heq2_mask(__habs2(as_h2(t[e])), m1raw);
+        const uint32_t is_min = __heq2_mask(__habs2(as_h2(s.t[e])), m1raw);
         const uint32_t sel = bitselect(m1ss, m2ss, is_min);
         args = bitselect(args, (uint32_t)e * 0x00010001u, is_min);
-        const uint32_t c = sel ^ (t[e] & kH2Sign);
-        sts_u32(addr[e], as_u32(__hadd2(as_h2(t[e]), as_h2(c))));
+        const uint32_t c = sel ^ (s.t[e] & kH2Sign);
+        sts_u32(s.addr[e], as_u32(__hadd2(as_h2(s.t[e]), as_h2(c))));
     }
     constexpr uint32_t F0 = (((1u << N0) - 1u) << (16 - N0)) * 0x00010001u;
     constexpr uint32_t F1 = N1 > 0 ? (((1u << N1) - 1u) << (16 - N1)) * 0x00010001u : 0u;
-    const uint32_t z = (s0 & F0) | (W3 ? args : 0u);
-    const uint32_t w = W3 ? 0u : ((s1 & F1) | args);
+    const uint32_t z = (s.s0 & F0) | (W3 ? args : 0u);
+    const uint32_t w = W3 ? 0u : ((s.s1 & F1) | args);
     return make_uint4(m1ss, m2ss, z, w);
+}
+
+template <int DEG, bool IDENT_LAST, bool ONE_CW>
+__device__ __forceinline__ uint4 process_row_h2(const Lane &l, const uint2 *__restrict__ ed, const uint4 rec,
+                                                const uint32_t alpha2) {
+    RowStateH2<DEG> s;
+    row_gather_h2<DEG, IDENT_LAST, ONE_CW>(l, ed, rec, s);
+    return row_scatter_h2<DEG>(s, alpha2);
 }
 
 // ---- pieces of the pair kernel ---------------------------------------------------------------------
@@ -117,7 +139,7 @@ struct DecCtxH2 {
     Lane l;
     uint32_t *my_rec;
     uint64_t pol;
-    uint4 cur;
+    uint4 cur, cur2;   // prefetched records of the next layer (and of its partner when the next layer is a row pair)
     bool done;   // this thread does no row work (inactive lane, or both codewords of its pair are finished)
 };
 
@@ -175,32 +197,64 @@ __device__ __forceinline__ uint32_t syndrome_fail_h2(const DecArgs &a, const Dec
     return fail & kH2Sign;
 }
 
+// Layer loop, unrolled per base graph.  As in decode_kernel.cuh: ld_from / ld_to gate the prefetch of the next
+// layer's record, and two consecutive base rows that touch disjoint block columns (pair_first<BG>) run as one layer
+// with one barrier.  Row pairs only occur among rows of degree <= 11, i.e. with three-word records.
 template <int BG, int R, bool FULL>
 struct UnrolledRowsH2 {
     static __device__ __forceinline__ void run(const DecArgs &a, DecCtxH2 &c, const int ld_from, const int ld_to, const bool store_rec) {
-        if (R >= a.n_rows) return;
+        if (R >= 4 && R >= a.n_rows) return;   // n_rows >= 4 is validated by the host
         constexpr int DEG = BgShape<BG>::deg(R);
         constexpr int E0 = BgShape<BG>::start(R);
-        if (FULL || !c.done) {
-            constexpr bool kW4 = DEG > 11;                                                  // this layer has a 4th word
-            constexpr bool kNextW4 = R + 1 < BgShape<BG>::kRows && BgShape<BG>::deg(R + 1 < BgShape<BG>::kRows ? R + 1 : R) > 11;
-            uint32_t *w4 = c.my_rec + kRecSlots * 3 * kRecStride;                           // [layer 0..3][kRecStride]
-            uint4 nxt = make_uint4(0u, 0u, 0u, 0u);
-            if (R >= ld_from && R < ld_to) {
-                nxt = ld_rec(c.my_rec, R + 1, c.pol);
-                if (kNextW4) nxt.w = ld_word(w4 + (R + 1) * kRecStride, c.pol);
+        constexpr bool kW4 = DEG > 11;                                                  // this layer has a 4th word
+        constexpr bool PAIR = pair_first<BG>(R) && !kW4 && BgShape<BG>::deg(R + 1 < BgShape<BG>::kRows ? R + 1 : R) <= 11;
+        uint32_t *w4 = c.my_rec + kRecSlots * 3 * kRecStride;                           // [layer 0..3][kRecStride]
+        if (PAIR && R + 1 < a.n_rows) {
+            constexpr int DEG2 = BgShape<BG>::deg(PAIR ? R + 1 : R);
+            constexpr int E1 = BgShape<BG>::start(PAIR ? R + 1 : R);
+            if (FULL || !c.done) {
+                uint4 nxt = make_uint4(0u, 0u, 0u, 0u), nxt2 = nxt;
+                if ((R + 1 >= ld_from && R + 1 < ld_to)) {
+                    nxt = ld_rec(c.my_rec, R + 2, c.pol);   // no 4th word: layers >= 4 have degree <= 11
+                    if (pair_first<BG>(R + 2)) nxt2 = ld_rec(c.my_rec, R + 3, c.pol);
+                }
+                RowStateH2<DEG> s0;
+                RowStateH2<DEG2> s1;
+                row_gather_h2<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur, s0);
+                row_gather_h2<DEG2, (R >= 4), FULL>(c.l, a.ed + E1, c.cur2, s1);
+                const uint4 rec0 = row_scatter_h2<DEG>(s0, a.alpha_h2);
+                const uint4 rec1 = row_scatter_h2<DEG2>(s1, a.alpha_h2);
+                if (store_rec) {
+                    st_rec(c.my_rec, R, rec0, c.pol);
+                    st_rec(c.my_rec, R + 1, rec1, c.pol);
+                }
+                c.cur = nxt;
+                c.cur2 = nxt2;
             }
-            // layer 0's 4th word is not prefetched across the iteration boundary: fetch it on entry
-            if (R == 0 && kW4 && ld_from == 0) c.cur.w = ld_word(w4, c.pol);
-            const uint4 rec = process_row_h2<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur, a.alpha_h2);
-            if (store_rec) {
-                st_rec(c.my_rec, R == 0 ? a.n_rows : R, rec, c.pol);
-                if (kW4) st_word(w4 + R * kRecStride, rec.w, c.pol);
+            __syncthreads();
+            UnrolledRowsH2<BG, (PAIR ? R + 2 : BgShape<BG>::kRows), FULL>::run(a, c, ld_from, ld_to, store_rec);
+        } else {
+            if (FULL || !c.done) {
+                constexpr bool kNextW4 = R + 1 < BgShape<BG>::kRows && BgShape<BG>::deg(R + 1 < BgShape<BG>::kRows ? R + 1 : R) > 11;
+                uint4 nxt = make_uint4(0u, 0u, 0u, 0u), nxt2 = nxt;
+                if ((R >= ld_from && R < ld_to)) {
+                    nxt = ld_rec(c.my_rec, R + 1, c.pol);
+                    if (kNextW4) nxt.w = ld_word(w4 + (R + 1) * kRecStride, c.pol);
+                    if (!PAIR && pair_first<BG>(R + 1)) nxt2 = ld_rec(c.my_rec, R + 2, c.pol);
+                }
+                // layer 0's 4th word is not prefetched across the iteration boundary: fetch it on entry
+                if (R == 0 && kW4 && (ld_from == 0)) c.cur.w = ld_word(w4, c.pol);
+                const uint4 rec = process_row_h2<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur, a.alpha_h2);
+                if (store_rec) {
+                    st_rec(c.my_rec, R == 0 ? a.n_rows : R, rec, c.pol);
+                    if (kW4) st_word(w4 + R * kRecStride, rec.w, c.pol);
+                }
+                c.cur = nxt;
+                c.cur2 = nxt2;
             }
-            c.cur = nxt;
+            __syncthreads();
+            if (!PAIR) UnrolledRowsH2<BG, R + 1, FULL>::run(a, c, ld_from, ld_to, store_rec);
         }
-        __syncthreads();
-        UnrolledRowsH2<BG, R + 1, FULL>::run(a, c, ld_from, ld_to, store_rec);
     }
 };
 template <int BG, bool FULL>
@@ -256,6 +310,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
         bool fin_a = !active, fin_b = !has_b;   // finished (converged and already written out, or absent)
         c.done = !active;
         c.cur = make_uint4(0u, 0u, 0u, 0u);
+        c.cur2 = c.cur;
         int it_a = 0, it_b = 0, ok_a = 0, ok_b = 0;
 
         for (int it = 0; it < a.max_iters; ++it) {

@@ -201,3 +201,23 @@ def test_demodulator_oracle_properties(O):
             ref = np.stack([rx.real, rx.imag], axis=1).ravel() * 2 * np.sqrt(2) / var
             assert np.allclose(llr, ref, rtol=1e-6, atol=1e-6)
             assert np.allclose(llr, O.qpsk_demod(rx.real.astype(np.float32), rx.imag.astype(np.float32), var), rtol=1e-5, atol=1e-5)
+
+
+def test_oracle_b_variants_agree(O):
+    """Oracle B: the float32-input export, the float64 export and the _ex export (termination selectable, APP returned)
+    are the same decoder; with termination off it runs exactly max_iters flooding iterations; a noiseless word is returned."""
+    rng = np.random.default_rng(12)
+    info, llr = make_llr(O, 2, 52, 6, 2000, -2.0, rng, filler=104)
+    a = O.decode_bp(2, 52, llr, 8)                                    # orc_decode_bp_f32
+    b = O.decode_bp(2, 52, llr.astype(np.float64), 8, want_app=True)  # orc_decode_bp_ex
+    assert (a["hard"] == b["hard"]).all() and (a["iters"] == b["iters"]).all() and (a["parity_ok"] == b["parity_ok"]).all()
+    assert np.isinf(b["app"][:, 416:520]).all()                       # +inf filler stays +inf through every iteration
+    assert ((b["app"][:, :520] < 0) == b["hard"].astype(bool)).all()
+    c = O.decode_bp(2, 52, llr, 8, early_term=False)
+    assert (c["iters"] == 8).all()
+    done = a["parity_ok"] == 1
+    assert done.any() and (c["hard"][done] == a["hard"][done]).all()  # a converged word stays converged (fixed point of hard)
+    clean = np.where(O.encode(2, 52, info) == 0, 20.0, -20.0).astype(np.float32)
+    clean[:, :104] = 0
+    d = O.decode_bp(2, 52, clean, 8)
+    assert (d["hard"] == info).all() and (d["iters"] <= 2).all()
