@@ -26,7 +26,10 @@
 
 namespace nrldpc {
 
-constexpr int kBpThreads = 512;   // 128 registers per thread: the degree-19 rows keep 2 x 19 doubles live
+// CTA width is a template parameter: 512 threads leave 128 registers per thread (the degree-19 rows keep 2 x 19
+// doubles live), 1024 threads double the warps that hide the latency of the float64 math sequences and of the message
+// loads at 64 registers.  Measured on 4096 x BG1 Z=384, 8 iterations: 102 ms at 512 threads, 73 ms at 1024 (default).
+constexpr int kBpThreadsMax = 1024;
 
 struct BpArgs {
     const void *llr;         // [batch][ncw] float32 or float64 (template parameter)
@@ -49,39 +52,56 @@ struct BpArgs {
     const int *col_edge;     // [edges]
 };
 
+// The two float64 math sequences are kept out of line: inlined into the nine per-degree row bodies they made ~280 KB
+// of code, and the kernel stalled on instruction fetch (ncu: stall_no_instruction 1.3 per issue).
+#ifndef NRLDPC_BP_INLINE_MATH
+#define NRLDPC_BP_INLINE_MATH 0
+#endif
+#if NRLDPC_BP_INLINE_MATH
+#define NRLDPC_BP_MATH __device__ __forceinline__
+#else
+#define NRLDPC_BP_MATH __device__ __noinline__
+#endif
+NRLDPC_BP_MATH double bp_tanh_half(double q) { return tanh(__dmul_rn(0.5, q)); }
+NRLDPC_BP_MATH double bp_two_atanh_clipped(double x) {
+    const double lim = 1.0 - 1.1102230246251565e-16;   // 1 - 2^-53: +inf filler cannot produce inf - inf
+    x = x > lim ? lim : (x < -lim ? -lim : x);
+    return __dmul_rn(2.0, atanh(x));
+}
+
 // One check of degree DEG: reads Q (shared) and its own previous messages, writes its new messages in place.
 template <int DEG>
 __device__ __forceinline__ void bp_check(const double *__restrict__ Q, double *__restrict__ rm, const int *__restrict__ e_shift,
                                          const int *__restrict__ e_colz, const int e0, const int z, const int Z,
                                          const bool first) {
-    double th[DEG];
+    double th[DEG], q[DEG];
 #pragma unroll
     for (int k = 0; k < DEG; ++k) {
         int p = z + __ldg(e_shift + e0 + k);
         if (p >= Z) p -= Z;
         const double Qv = Q[__ldg(e_colz + e0 + k) + p];
-        // q_ij = Q_i - r_ji; in the first iteration q_ij = L(c_i) (Q holds the channel values, no message yet)
-        const double q = first ? Qv : __dsub_rn(Qv, rm[(size_t)(e0 + k) * Z + z]);
-        th[k] = tanh(__dmul_rn(0.5, q));
+        // q_ij = Q_i - r_ji; in the first iteration q_ij = L(c_i) (Q holds the channel values, no message yet: the
+        // slot is read anyway -- it is this CTA's own scratch -- so that the load never waits behind a branch)
+        const double r_old = rm[(size_t)(e0 + k) * Z + z];
+        q[k] = first ? Qv : __dsub_rn(Qv, r_old);
     }
+#pragma unroll
+    for (int k = 0; k < DEG; ++k) th[k] = bp_tanh_half(q[k]);
     // suffix products suf[k] = th[k] * th[k+1] * ... (formed from the right, as the restatement does)
     double suf[DEG + 1];
     suf[DEG] = 1.0;
 #pragma unroll
     for (int k = DEG - 1; k >= 0; --k) suf[k] = __dmul_rn(suf[k + 1], th[k]);
-    const double lim = 1.0 - 1.1102230246251565e-16;   // 1 - 2^-53
     double pre = 1.0;
 #pragma unroll
     for (int k = 0; k < DEG; ++k) {
-        double x = __dmul_rn(pre, suf[k + 1]);
-        x = x > lim ? lim : (x < -lim ? -lim : x);
-        rm[(size_t)(e0 + k) * Z + z] = __dmul_rn(2.0, atanh(x));
+        rm[(size_t)(e0 + k) * Z + z] = bp_two_atanh_clipped(__dmul_rn(pre, suf[k + 1]));
         pre = __dmul_rn(pre, th[k]);
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kBpThreads, 1) decode_bp_kernel(const BpArgs a) {
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) decode_bp_kernel(const BpArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw_bp[];
     double *Q = reinterpret_cast<double *>(smem_raw_bp);
     __shared__ int s_group;

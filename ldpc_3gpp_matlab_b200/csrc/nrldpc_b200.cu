@@ -96,6 +96,7 @@ struct nrldpc_handle {
     size_t dev_widen_cw = 0;
     // sum-product kernel tables (decode_kernel_bp.cuh)
     int *bp_shift = nullptr, *bp_colz = nullptr, *bp_col_start = nullptr, *bp_col_edge = nullptr;
+    int bp_threads = 1024;           // CTA width of the sum-product kernel (NRLDPC_BP_THREADS=512 selects the 128-register build)
 };
 
 namespace {
@@ -216,8 +217,9 @@ int launch_decode_bp(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const T
                      uint8_t *hard, T *soft, int32_t *iters, uint8_t *ok) {
     const int Z = h->d.Z;
     const size_t smem = (size_t)h->d.n_cw * sizeof(double);
-    const int threads = std::min(nrldpc::kBpThreads, (n_rows * Z + 31) / 32 * 32);
-    auto kern = nrldpc::decode_bp_kernel<T>;
+    int width = h->bp_threads;
+    const int threads = std::min(width, (n_rows * Z + 31) / 32 * 32);
+    auto kern = width > 512 ? nrldpc::decode_bp_kernel<T, 1024> : nrldpc::decode_bp_kernel<T, 512>;
     CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
@@ -484,6 +486,7 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
     h->num_sms = prop.multiProcessorCount;
     if (const char *v = getenv("NRLDPC_DECODE_VARIANT")) h->dec_variant = strcmp(v, "loop") == 0 ? 0 : 1;
     if (const char *v = getenv("NRLDPC_L2_PIN")) h->l2_pin = atoi(v) ? 1 : 0;
+    if (const char *v = getenv("NRLDPC_BP_THREADS")) h->bp_threads = atoi(v) > 512 ? 1024 : 512;
 
     const BgView v = bg_view(cfg->bg);
     const int Z = cfg->Z;

@@ -12,6 +12,13 @@ et = bool(int(sys.argv[5])) if len(sys.argv) > 5 else False
 rng = np.random.default_rng(1)
 d = O.dims(bg, Z)
 info, llr = make_llr(O, bg, Z, B, d["N"] // 2 * 2, 1.0, rng)
+if dt == 2:   # the sum-product (reference algorithm) kernel against oracle B
+    h = capi.Handle(bg, Z, 6, et, algorithm=capi.ALG_BP)
+    out = h.decode(llr.astype(np.float64), want_soft=True)
+    ref = O.decode_bp(bg, Z, llr.astype(np.float64), 6, early_term=et, want_app=True)
+    print("hard equal", (out["hard"] == ref["hard"]).all(), "app close", np.allclose(out["app"], ref["app"], rtol=1e-9, atol=1e-9),
+          "iters", (out["iters"] == ref["iters"]).all(), "ok", (out["parity_ok"] == ref["parity_ok"]).all())
+    sys.exit(0)
 h = capi.Handle(bg, Z, 6, et, llr_dtype=dt)
 out = h.decode(llr, want_soft=True)
 ref = O.decode_nms(bg, Z, llr, 6, early_term=et, f16=bool(dt))
