@@ -378,11 +378,25 @@ def main():
         torch.cuda.synchronize()
         dt = D.max_over_ranks((time.perf_counter() - t0) / n_e2e)
         assert bool((hard_h.cuda() == hard).all()), "host-path result differs from device-path result"
+        # the PCIe floor of that call: the same pinned buffer copied to the device and nothing else (CUDA events)
+        dst = torch.empty_like(llr)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dst.copy_(llr_h, non_blocking=True)
+        torch.cuda.synchronize()
+        c0.record()
+        for _ in range(3):
+            dst.copy_(llr_h, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        h2d_only_ms = c0.elapsed_time(c1) / 3
+        del dst
         e2e = {"value": world * B * K / dt / 1e9, "unit": "Gb/s", "h2d_bytes_per_step": B * h.n_cw * 4,
                "d2h_bytes_per_step": B * K, "ms_per_step": dt * 1e3, "steps": n_e2e,
                "timer": "host perf_counter around the synchronous host-memory C-ABI call, max over ranks",
                "pipeline": "3 streams, chunked H2D / kernel / D2H overlap inside nrldpc_decode",
-               "numa_bound": bool(numa_bound)}
+               "numa_bound": bool(numa_bound), "h2d_copy_alone_ms": h2d_only_ms,
+               "h2d_copy_alone_gbs": B * h.n_cw * 4 / (h2d_only_ms * 1e-3) / 1e9,
+               "note": "PCIe-bound: h2d_copy_alone_ms is the same pinned float32 buffer copied to the device with nothing else running"}
         # same call with the LLRs transported as binary16 (nrldpc_decode16): half the H2D bytes; reported beside the
         # float32-boundary figure above, which stays the e2e headline
         llr_h16 = torch.empty((B, h.n_cw), dtype=torch.float16, pin_memory=True)
@@ -407,18 +421,22 @@ def main():
     bytes_per_cw = 4 * h.n_cw + K
     k_ms = sum(per_launch_ms) / len(per_launch_ms)
     achieved = B * bytes_per_cw / (k_ms * 1e-3) / 1e9
-    traffic = None
+    traffic = pipes = None
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text()).get(args.workload + ("|f16x2" if f16 else ""))
+            tj = json.loads(tp.read_text())
+            traffic = tj.get(args.workload + ("|f16x2" if f16 else ""))
+            pipes = (tj.get("pipes") or {}).get(args.workload + ("|f16x2" if f16 else ""))
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "decode_nms_h2_kernel" if f16 else "decode_nms_kernel", "kernel_ms": k_ms, "bytes_per_codeword": bytes_per_cw,
                 "peak_source": peak_src,
-                "note": "state stays on chip for all iterations; the kernel is issue/shared-memory bound by construction "
-                        "(SURVEY.md 8d), so the HBM fraction is small; see profiles/ for issue-slot utilisation"}
+                "binding_pipe": {"name": "SM ALU pipe (integer / logic / min-max / select)", "ncu": pipes,
+                                 "source": "profiles/traffic.json <- ncu --set full capture of this kernel"},
+                "note": "state stays on chip for all iterations; the kernel is bound by the SM's ALU pipe by construction "
+                        "(SURVEY.md 8d), so the HBM fraction is small; binding_pipe carries the ncu utilisation of the pipe that binds"}
 
     # ---- CPU baseline (rank 0, N=1 only) ------------------------------------------------------------
     cpu = None

@@ -48,6 +48,26 @@ __device__ __forceinline__ float clamp_llr_h2(float x) { return __fadd_rn(fmaxf(
 //   w    : DEG > 11 only: arg-min edge indices in bits 0..4 / 16..20 and, for DEG > 16, the sign bits of
 //          edges 16..DEG-1 at the top of each half
 // Arg-min indices are compared as fp16 bit patterns (HSET2 without flush-to-zero).
+// syndrome with the base graph's shape known at compile time (see SyndromeRows in decode_kernel.cuh)
+template <int BG, int R, bool FULL>
+struct SyndromeRowsH2 {
+    static __device__ __forceinline__ uint32_t run(const DecArgs &a, const Lane &l, uint32_t fail) {
+        if (R >= 4 && R >= a.n_rows) return fail;
+        constexpr int DEG = BgShape<BG>::deg(R);
+        constexpr int E0 = BgShape<BG>::start(R);
+        uint32_t par = 0;
+#pragma unroll
+        for (int e = 0; e < DEG; ++e) par ^= lds_u32(edge_addr<FULL>(l, a.ed[E0 + e], (R >= 4) && e == DEG - 1));
+        fail |= par;
+        asm volatile("" : "+r"(fail));   // one row's loads are consumed before the next row's are issued (register pressure)
+        return SyndromeRowsH2<BG, R + 1, FULL>::run(a, l, fail);
+    }
+};
+template <int BG, bool FULL>
+struct SyndromeRowsH2<BG, BgShape<BG>::kRows, FULL> {
+    static __device__ __forceinline__ uint32_t run(const DecArgs &, const Lane &, uint32_t fail) { return fail; }
+};
+
 template <int DEG>
 struct RowStateH2 {
     uint32_t t[DEG];
@@ -320,7 +340,9 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
             if (!fin_b) it_b = it + 1;
             if (a.early_term || (want_ok && last)) {
                 if (!c.done) {
-                    const uint32_t f = syndrome_fail_h2(a, c);
+                    Lane ls = c.l;
+                    asm volatile("" : "+r"(ls.one));   // keeps the address computations inside the iteration loop
+                    const uint32_t f = SyndromeRowsH2<BG, 0, FULL>::run(a, ls, 0u) & kH2Sign;
                     if (f & 0x00008000u) s_flag[2 * slot] = 1;
                     if (f & 0x80000000u) s_flag[2 * slot + 1] = 1;
                 }

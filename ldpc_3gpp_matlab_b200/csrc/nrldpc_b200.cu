@@ -96,6 +96,9 @@ struct nrldpc_handle {
     size_t dev_widen_cw = 0;
     // sum-product kernel tables (decode_kernel_bp.cuh)
     int *bp_shift = nullptr, *bp_colz = nullptr, *bp_col_start = nullptr, *bp_col_edge = nullptr;
+    const void *dec_kern_cached = nullptr;   // launch_decode: kernel / smem size the cached occupancy belongs to
+    size_t dec_smem_cached = 0;
+    int dec_occ_cached = 1;
     int bp_threads = 1024;           // CTA width of the sum-product kernel (NRLDPC_BP_THREADS=512 selects the 128-register build)
 };
 
@@ -184,11 +187,18 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
     else
         kern = bg1 ? (full ? (Kern)nrldpc::decode_nms_kernel<1, true> : (Kern)nrldpc::decode_nms_kernel<1, false>)
                    : (full ? (Kern)nrldpc::decode_nms_kernel<2, true> : (Kern)nrldpc::decode_nms_kernel<2, false>);
-    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // persistent grid: every SM filled to its occupancy (2 CTAs of 384 threads at Z = 384, more for narrower CTAs)
-    int occ = 0;
-    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
-    occ = std::max(1, std::min(occ, 4));
+    // persistent grid: every SM filled to its occupancy (2 CTAs of 384 threads at Z = 384, more for narrower CTAs);
+    // attribute and occupancy are looked up once per (kernel, shared-memory size): single-codeword calls (the
+    // reference's calling pattern, NRLDPCDecoder.m:265) should not pay two runtime queries per step
+    if (h->dec_kern_cached != reinterpret_cast<const void *>(kern) || h->dec_smem_cached != smem) {
+        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int q = 0;
+        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, threads, smem));
+        h->dec_occ_cached = std::max(1, std::min(q, 4));
+        h->dec_kern_cached = reinterpret_cast<const void *>(kern);
+        h->dec_smem_cached = smem;
+    }
+    const int occ = h->dec_occ_cached;
     int grid = (int)std::min<int64_t>(n_groups, (int64_t)h->num_sms * occ);
     if (const char *v = getenv("NRLDPC_GRID_CAP")) grid = std::max(1, std::min(grid, atoi(v)));  // experiments only
     if (int rc = ensure_scratch(h, s, (size_t)grid * nrldpc::kRecWords * nrldpc::kRecStride)) return rc;
