@@ -368,6 +368,13 @@ struct SyndromeRows<BG, BgShape<BG>::kRows, FULL> {
     static __device__ __forceinline__ uint32_t run(const DecArgs &, const Lane &, uint32_t fail) { return fail; }
 };
 
+// Out of line on purpose: inlined into the decode kernel the 316 unrolled loads changed the register allocation of
+// the layer code (552 bytes of spills, 3.10 -> 3.97 ms on the fixed-iteration headline that never runs it).
+template <int BG, bool FULL>
+__device__ __noinline__ uint32_t syndrome_unrolled(const DecArgs &a, const Lane l) {
+    return SyndromeRows<BG, 0, FULL>::run(a, l, 0u);
+}
+
 // ---- one full iteration over the layers: looped (generic) --------------------------------------
 __device__ __forceinline__ void iteration_looped(const DecArgs &a, DecCtx &c, const int it) {
     const bool store_rec = it + 1 < a.max_iters;
@@ -528,10 +535,8 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
             const bool last = it + 1 == a.max_iters;
             if (a.early_term || (want_ok && last)) {
                 if (!c.done) {
-                    Lane ls = c.l;
-                    asm volatile("" : "+r"(ls.one));   // keeps the 316 address computations inside the iteration loop
                     const int f = BG == 0 ? syndrome_fail(a, c)
-                                          : (int)(SyndromeRows<(BG == 0 ? 1 : BG), 0, FULL>::run(a, ls, 0u) >> 31);
+                                          : (int)(syndrome_unrolled<(BG == 0 ? 1 : BG), FULL>(a, c.l) >> 31);
                     if (f) s_flag[slot] = 1;
                 }
                 __syncthreads();

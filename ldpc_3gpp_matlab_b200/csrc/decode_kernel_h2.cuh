@@ -68,6 +68,11 @@ struct SyndromeRowsH2<BG, BgShape<BG>::kRows, FULL> {
     static __device__ __forceinline__ uint32_t run(const DecArgs &, const Lane &, uint32_t fail) { return fail; }
 };
 
+template <int BG, bool FULL>
+__device__ __noinline__ uint32_t syndrome_unrolled_h2(const DecArgs &a, const Lane l) {   // out of line: see decode_kernel.cuh
+    return SyndromeRowsH2<BG, 0, FULL>::run(a, l, 0u);
+}
+
 template <int DEG>
 struct RowStateH2 {
     uint32_t t[DEG];
@@ -340,9 +345,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
             if (!fin_b) it_b = it + 1;
             if (a.early_term || (want_ok && last)) {
                 if (!c.done) {
-                    Lane ls = c.l;
-                    asm volatile("" : "+r"(ls.one));   // keeps the address computations inside the iteration loop
-                    const uint32_t f = SyndromeRowsH2<BG, 0, FULL>::run(a, ls, 0u) & kH2Sign;
+                    const uint32_t f = syndrome_unrolled_h2<BG, FULL>(a, c.l) & kH2Sign;
                     if (f & 0x00008000u) s_flag[2 * slot] = 1;
                     if (f & 0x80000000u) s_flag[2 * slot + 1] = 1;
                 }
