@@ -62,6 +62,7 @@ struct DecArgs {
     uint8_t *ok;             // [batch] or null
     long long batch;
     int Z, ncols, kcols, n_rows, n_edges, max_iters, early_term, cwpc;
+    int slot_stride;         // words between the APP arrays of two codewords (pairs) of a CTA: cols*Z + pad, see decode_slot_stride
     float alpha;
     int l2_pin;              // 1: c2v scratch accesses carry an L2 evict_last policy
     int one;                 // = 1 (see mad_u32)
@@ -286,6 +287,28 @@ struct DecCtx {
 // memory without passing through registers; the clamp (+-LLR_MAX, NaN filler, -0) is then applied in place.
 __device__ __forceinline__ void load_group(const DecArgs &a, float *app, long long cw0, int n_here, int ncw,
                                            uint64_t *bar, uint32_t &parity) {
+    if (a.slot_stride != ncw) {
+        // padded slots (several codewords per CTA, see decode_slot_stride): the group is still one contiguous range in
+        // HBM; it is read with coalesced loads and scattered to the padded slots with the clamp applied on the way
+        const float *src = a.llr + cw0 * ncw;
+        const int S = a.slot_stride;
+        if ((S & 3) == 0) {          // ncw is a multiple of 4 for every (BG, Z): a float4 never straddles two codewords
+            const int n4 = (n_here * ncw) >> 2, ncw4 = ncw >> 2;
+            for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+                float4 v = __ldcs(reinterpret_cast<const float4 *>(src) + i);
+                v.x = clamp_llr(v.x); v.y = clamp_llr(v.y); v.z = clamp_llr(v.z); v.w = clamp_llr(v.w);
+                const int sl = i / ncw4;
+                *reinterpret_cast<float4 *>(app + (size_t)sl * S + ((i - sl * ncw4) << 2)) = v;
+            }
+        } else {
+            const int n = n_here * ncw;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                const int sl = i / ncw;
+                app[(size_t)sl * S + (i - sl * ncw)] = clamp_llr(__ldcs(src + i));
+            }
+        }
+        return;
+    }
     const uint32_t bytes = (uint32_t)(n_here * ncw) * 4u;     // ncw*4 is a multiple of 16 for every (BG, Z)
     if (threadIdx.x == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses to app vs the async write
@@ -319,10 +342,10 @@ __device__ __forceinline__ int syndrome_fail(const DecArgs &a, const DecCtx &c) 
 
 __device__ __forceinline__ void store_outputs(const DecArgs &a, const float *app, long long cw0, int n_here, int ncw, int K) {
     // hard decisions, four per 32-bit store (K = kcols*Z is a multiple of 4 for every even Z; odd Z stores bytes)
-    if ((K & 3) == 0) {
+    if ((K & 3) == 0 && (a.slot_stride & 3) == 0) {
         const int K4 = K >> 2;
         for (int s = 0; s < n_here; ++s) {
-            const float4 *src = reinterpret_cast<const float4 *>(app + (size_t)s * ncw);
+            const float4 *src = reinterpret_cast<const float4 *>(app + (size_t)s * a.slot_stride);
             uint32_t *dst = reinterpret_cast<uint32_t *>(a.hard + (cw0 + s) * K);
             for (int k = threadIdx.x; k < K4; k += blockDim.x) {
                 const float4 v = src[k];
@@ -332,16 +355,23 @@ __device__ __forceinline__ void store_outputs(const DecArgs &a, const float *app
         }
     } else {
         for (int s = 0; s < n_here; ++s) {
-            const float *src = app + (size_t)s * ncw;
+            const float *src = app + (size_t)s * a.slot_stride;
             uint8_t *dst = a.hard + (cw0 + s) * K;
             for (int k = threadIdx.x; k < K; k += blockDim.x) dst[k] = src[k] < 0.0f ? 1 : 0;
         }
     }
-    if (a.soft) {
+    if (a.soft && a.slot_stride == ncw) {
         float4 *dst = reinterpret_cast<float4 *>(a.soft + cw0 * ncw);
         const float4 *src = reinterpret_cast<const float4 *>(app);
         const int n4 = (n_here * ncw) >> 2;
         for (int i = threadIdx.x; i < n4; i += blockDim.x) __stcs(dst + i, src[i]);
+    } else if (a.soft) {
+        float *dst = a.soft + cw0 * ncw;
+        const int n = n_here * ncw;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const int sl = i / ncw;
+            __stcs(dst + i, app[(size_t)sl * a.slot_stride + (i - sl * ncw)]);
+        }
     }
 }
 
@@ -481,7 +511,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
     const int ncw = a.ncols * Z;
     const int K = a.kcols * Z;
     float *app = reinterpret_cast<float *>(smem_raw);
-    int *s_flag = reinterpret_cast<int *>(app + (size_t)a.cwpc * ncw);  // [cwpc] + work-group slot
+    int *s_flag = reinterpret_cast<int *>(app + (size_t)a.cwpc * a.slot_stride);  // [cwpc] + work-group slot
     int &s_group = s_flag[a.cwpc];
     uint64_t *bar = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(s_flag + a.cwpc + 1) + 7) & ~(uintptr_t)7);
     uint32_t bar_parity = 0;
@@ -502,7 +532,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
     DecCtx c;
     c.l.zoff = (uint32_t)z * 4u;
     c.l.nZ4 = 0u - (uint32_t)Z * 4u;
-    c.l.slot_off = FULL ? 0u : (uint32_t)(slot * ncw) * 4u;
+    c.l.slot_off = FULL ? 0u : (uint32_t)(slot * a.slot_stride) * 4u;
     c.l.one = (uint32_t)a.one;
     c.my_rec = a.c2v + (size_t)blockIdx.x * (kRecWords * kRecStride) + tid;
     c.pol = make_l2_policy(a.l2_pin);

@@ -171,6 +171,11 @@ struct DecCtxH2 {
 // Load one codeword pair (B may be absent: zeros) into its interleaved APP array.
 __device__ __forceinline__ void load_pair(const float *__restrict__ rowA, const float *__restrict__ rowB, uint32_t *app,
                                           int ncw, int lane, int nlanes) {
+    if (reinterpret_cast<uintptr_t>(app) & 15) {   // padded slot stride that is not a multiple of four words (tiny odd Z)
+        for (int i = lane; i < ncw; i += nlanes)
+            app[i] = as_u32(__floats2half2_rn(clamp_llr_h2(__ldcs(rowA + i)), clamp_llr_h2(rowB ? __ldcs(rowB + i) : 0.f)));
+        return;
+    }
     const float4 *a4 = reinterpret_cast<const float4 *>(rowA);
     const float4 *b4 = reinterpret_cast<const float4 *>(rowB);
     uint4 *dst = reinterpret_cast<uint4 *>(app);
@@ -192,7 +197,7 @@ __device__ __forceinline__ void store_half(const DecArgs &a, const uint32_t *app
                                            int lane, int nlanes) {
     const int sh = half ? 31 : 15;
     uint8_t *hard = a.hard + cw * K;
-    if ((K & 3) == 0) {
+    if ((K & 3) == 0 && (reinterpret_cast<uintptr_t>(app) & 15) == 0) {
         const uint4 *src = reinterpret_cast<const uint4 *>(app);
         uint32_t *dst = reinterpret_cast<uint32_t *>(hard);
         for (int k = lane; k < (K >> 2); k += nlanes) {
@@ -295,7 +300,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
     const int ncw = a.ncols * Z;
     const int K = a.kcols * Z;
     uint32_t *app = reinterpret_cast<uint32_t *>(smem_raw);
-    int *s_flag = reinterpret_cast<int *>(app + (size_t)a.cwpc * ncw);  // [2*cwpc] + work-group slot
+    int *s_flag = reinterpret_cast<int *>(app + (size_t)a.cwpc * a.slot_stride);  // [2*cwpc] + work-group slot
     int &s_group = s_flag[2 * a.cwpc];
     if ((uint32_t)__cvta_generic_to_shared(smem_raw) != a.smem_base) __trap();
 
@@ -310,11 +315,11 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
     DecCtxH2 c;
     c.l.zoff = (uint32_t)z * 4u;
     c.l.nZ4 = 0u - (uint32_t)Z * 4u;
-    c.l.slot_off = FULL ? 0u : (uint32_t)(slot * ncw) * 4u;
+    c.l.slot_off = FULL ? 0u : (uint32_t)(slot * a.slot_stride) * 4u;
     c.l.one = (uint32_t)a.one;
     c.my_rec = a.c2v + (size_t)blockIdx.x * (kRecWords * kRecStride) + tid;
     c.pol = make_l2_policy(a.l2_pin);
-    uint32_t *my_app = app + (size_t)(lane_ok ? slot : 0) * ncw;
+    uint32_t *my_app = app + (size_t)(lane_ok ? slot : 0) * a.slot_stride;
 
     while (true) {
         __syncthreads();  // previous group's outputs are out of smem

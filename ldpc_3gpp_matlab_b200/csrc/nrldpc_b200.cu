@@ -144,13 +144,28 @@ BgView bg_view(int bg) {
     return v;
 }
 
-int decode_cwpc(int Z) { return std::max(1, nrldpc::kDecThreads / Z); }
-int decode_threads(int Z) { return std::max(32, (decode_cwpc(Z) * Z + 31) / 32 * 32); }
+// Words between the APP arrays of two codewords (float32) / codeword pairs (packed half) that share a CTA.
+// Lane (slot, z) of a warp addresses slot*stride + col*Z + (z + shift) mod Z; with stride = cols*Z the slots of a warp
+// collide in the shared-memory banks (BG1, Z = 8: stride 544 = 0 mod 32, four slots per warp -> 4-way conflicts; ncu:
+// shared-memory wavefronts at 74 % of peak, ALU pipe at 59 %).  With stride = Z (mod 32) the banks of a warp follow the
+// lane index through every circulant rotation, so whole slots never collide.
+int decode_slot_stride(int cols, int Z) {
+    const int ncw = cols * Z;
+    if (Z >= nrldpc::kDecThreads / 2 + 1) return ncw;   // one codeword per CTA
+    return ncw + (((Z - ncw) % 32) + 32) % 32;
+}
+// Codewords (pairs) per CTA: as many as fit in 384 threads, and in the shared memory two CTAs per SM can have.
+int decode_cwpc(int cols, int Z) {
+    const int by_threads = std::max(1, nrldpc::kDecThreads / Z);
+    const int by_smem = std::max(1, (108 * 1024 / 4) / decode_slot_stride(cols, Z));
+    return std::min(by_threads, by_smem);
+}
+int decode_threads(int cols, int Z) { return std::max(32, (decode_cwpc(cols, Z) * Z + 31) / 32 * 32); }
 
 size_t decode_smem_bytes(const nrldpc_handle *h, int n_rows) {
-    const int cwpc = decode_cwpc(h->d.Z);
+    const int cwpc = decode_cwpc(h->d.cols, h->d.Z);
     (void)n_rows;
-    return (size_t)cwpc * h->d.n_cw * 4 + (size_t)(2 * cwpc + 1) * 4 + 16;
+    return (size_t)cwpc * decode_slot_stride(h->d.cols, h->d.Z) * 4 + (size_t)(2 * cwpc + 1) * 4 + 16;
 }
 
 int ensure_scratch(nrldpc_handle *h, PipeSlot &s, size_t recs) {
@@ -169,7 +184,7 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
     const int Z = h->d.Z;
     const bool h2 = h->cfg.llr_dtype == NRLDPC_F16X2;
     // cwpc: codewords (float32) or codeword pairs (packed half) resident per CTA
-    const int cwpc = decode_cwpc(Z), threads = decode_threads(Z);
+    const int cwpc = decode_cwpc(h->d.cols, Z), threads = decode_threads(h->d.cols, Z);
     const int per_group = h2 ? 2 * cwpc : cwpc;
     const int64_t n_groups = (batch + per_group - 1) / per_group;
     const size_t smem = decode_smem_bytes(h, n_rows);
@@ -207,6 +222,7 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
     a.llr = llr; a.hard = hard; a.soft = soft; a.iters = iters; a.ok = ok;
     a.batch = batch; a.Z = Z; a.ncols = h->d.cols; a.kcols = h->d.kcols; a.n_rows = n_rows;
     a.n_edges = h->h_row_start[n_rows]; a.max_iters = h->cfg.max_iters; a.early_term = h->cfg.early_term;
+    a.slot_stride = cwpc == 1 ? h->d.n_cw : decode_slot_stride(h->d.cols, Z);
     a.cwpc = cwpc; a.alpha = h->cfg.alpha; a.l2_pin = h->l2_pin; a.one = 1;
     a.c2v = s.c2v; a.work_counter = s.counter;
     const uint32_t ah = __half_as_ushort(__float2half_rn(h->cfg.alpha));
@@ -686,7 +702,7 @@ int decode_impl(nrldpc_t *h, const void *llr, int in_kind, int64_t batch, int32_
     // persistent-grid wave of codewords (doubled while small) so the un-overlapped tail stays short.
     if (int rc = ensure_pipe(h)) return rc;
     if (h->dev_done) CUDA_TRY(h, cudaStreamWaitEvent(h->pipe[0].stream, h->dev_done, 0));
-    const int cwpc = decode_cwpc(h->d.Z);
+    const int cwpc = decode_cwpc(h->d.cols, h->d.Z);
     const int64_t wave = bp ? (int64_t)h->num_sms
                             : (int64_t)h->num_sms * nrldpc::kDecCtasPerSm * cwpc *
                                   (h->cfg.llr_dtype == NRLDPC_F16X2 ? 2 : 1);  // codewords per full grid
