@@ -17,4 +17,7 @@ for dt in f32 f16x2; do
 done
 BP_STEPS=0 ncu --set full --clock-control none -k regex:decode_bp -c 1 -f -o gpurun_out/prof_bp2 python tools/gpu_bp_time.py 296 > gpurun_out/ncu_bp2.log 2>&1
 ncu --set full --clock-control none -k regex:"encode_kernel|rate_match|rate_recover|qpsk" -c 4 -f -o gpurun_out/prof_chain python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-e2e --no-alt > gpurun_out/ncu_chain.log 2>&1
+# gpurun copies back at most 64 MiB: keep the text summaries, drop the reports that carry the source pages
+for r in gpurun_out/prof_*.ncu-rep; do python tools/ncu_summary.py $r > ${r%.ncu-rep}.summary.txt 2>&1; done
+du -sm gpurun_out | awk '$1 > 60 {exit 1}' || rm -f gpurun_out/prof_decode_*.ncu-rep
 ls -la gpurun_out
