@@ -42,6 +42,11 @@ def golden_decode():
     return np.load(GOLDEN / "decode_nms.npz")
 
 
+@pytest.fixture(scope="session")
+def golden_decode_bp():
+    return np.load(GOLDEN / "decode_bp.npz")
+
+
 def make_llr(O, bg, Z, B, E, esn0, rng, filler=0, k0=0):
     """Encode random info with the oracle, QPSK + AWGN, exact LLRs in the decoder's cw layout."""
     d = O.dims(bg, Z)

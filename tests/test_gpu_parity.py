@@ -568,3 +568,16 @@ def test_decode64_with_default_algorithm_rounds_to_float32(capi, O):
         capi.Handle(2, 52, 8, True, llr_dtype=capi.F16X2, algorithm=capi.ALG_BP)
     with pytest.raises(capi.UnsupportedParameters):
         capi.Handle(2, 52, 8, True, algorithm=7)
+
+
+def test_decode_bp_golden_vectors_on_gpu(capi, golden_decode, golden_decode_bp):
+    """The CUDA sum-product kernel against the committed oracle-B vectors (decisions, iteration counts, parity flags)."""
+    for n in sorted({k.split("__")[0] for k in golden_decode_bp.files}):
+        bg, Z, iters = golden_decode_bp[n + "__cfg"].tolist()
+        for tag, early in (("stop", True), ("full", False)):
+            h = capi.Handle(bg, Z, iters, early, algorithm=capi.ALG_BP)
+            out = h.decode(golden_decode[n + "__llr"])
+            h.close()
+            assert (np.packbits(out["hard"], axis=1) == golden_decode_bp[f"{n}__{tag}__hard"]).all(), (n, tag)
+            assert (out["iters"] == golden_decode_bp[f"{n}__{tag}__iters"]).all(), (n, tag)
+            assert (out["parity_ok"] == golden_decode_bp[f"{n}__{tag}__ok"]).all(), (n, tag)

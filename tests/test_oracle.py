@@ -221,3 +221,15 @@ def test_oracle_b_variants_agree(O):
     clean[:, :104] = 0
     d = O.decode_bp(2, 52, clean, 8)
     assert (d["hard"] == info).all() and (d["iters"] <= 2).all()
+
+
+def test_oracle_b_golden_vectors(O, golden_decode, golden_decode_bp):
+    """Oracle B on the committed LLRs reproduces the committed decisions / iteration counts / parity flags
+    (tools/make_golden_bp.py), with the reference's termination rule and with the iteration count fixed."""
+    for n in sorted({k.split("__")[0] for k in golden_decode_bp.files}):
+        bg, Z, iters = golden_decode_bp[n + "__cfg"].tolist()
+        for tag, early in (("stop", True), ("full", False)):
+            r = O.decode_bp(bg, Z, golden_decode[n + "__llr"], iters, early_term=early)
+            assert (np.packbits(r["hard"], axis=1) == golden_decode_bp[f"{n}__{tag}__hard"]).all(), (n, tag)
+            assert (r["iters"] == golden_decode_bp[f"{n}__{tag}__iters"]).all(), (n, tag)
+            assert (r["parity_ok"] == golden_decode_bp[f"{n}__{tag}__ok"]).all(), (n, tag)
