@@ -614,26 +614,61 @@ __global__ void __launch_bounds__(256) mod_awgn_demod_kernel(const uint8_t *__re
 
 // ------------------------------------------------------------------------------------------------
 // CRC attach / check for batches of blocks: comm.CRCGenerator / comm.CRCDetector with the polynomials of
-// get_3gpp_crc_polynomial.m:3-17 (zero initial state, no reflection, no final XOR), one thread per block
-// walking its bits MSB-first through an L-bit LFSR.  parity != NULL: the L parity bits of bits[0..n_bits)
+// get_3gpp_crc_polynomial.m:3-17 (zero initial state, no reflection, no final XOR; bits MSB-first through an L-bit
+// LFSR).  parity != NULL: the L parity bits of bits[0..n_bits)
 // are written to parity (NRLDPCEncoder.m:80,114).  ok != NULL: 1 iff the remainder of all n_bits is zero,
 // i.e. a block that already carries its parity passes (NRLDPCDecoder.m:300,336).
-// ------------------------------------------------------------------------------------------------
+//
+// One WARP per block: lane i runs the LFSR over its own contiguous chunk of ceil(n_bits/32) bits (chunks are aligned to
+// the END of the block, so leading lanes may hold short or empty chunks), which yields r_i = chunk_i(x) * x^L mod P;
+// the block's CRC is sum_i r_i * g^(31-i) mod P with g = x^chunk mod P, formed by a five-level Horner tree over the
+// lanes (shuffles + carry-less modular multiplications).  The serial one-thread-per-block version it replaces took
+// 675 us per call on 4096 blocks of 8448 bits (19 % of a BLER-loop batch); the CRC values are identical.
+__device__ __forceinline__ uint32_t crc_step_bit(uint32_t reg, uint32_t bit, uint32_t poly, uint32_t mask, int L) {
+    const uint32_t fb = ((reg >> (L - 1)) ^ bit) & 1u;
+    reg = (reg << 1) & mask;
+    return fb ? reg ^ poly : reg;
+}
+// a(x) * b(x) mod P over GF(2), operands and result below x^L
+__device__ __forceinline__ uint32_t crc_mulmod(uint32_t a, uint32_t b, uint32_t poly, uint32_t mask, int L) {
+    uint32_t res = 0;
+    for (int k = L - 1; k >= 0; --k) {
+        const uint32_t top = (res >> (L - 1)) & 1u;
+        res = (res << 1) & mask;
+        if (top) res ^= poly;
+        if ((b >> k) & 1u) res ^= a;
+    }
+    return res;
+}
+
 __global__ void __launch_bounds__(128) crc_kernel(const uint8_t *__restrict__ bits, long long batch, int n_bits, long long stride,
                                                   uint32_t poly, int L, uint8_t *__restrict__ parity, long long parity_stride,
                                                   uint8_t *__restrict__ ok) {
     const uint32_t mask = L == 32 ? 0xffffffffu : ((1u << L) - 1u);
-    for (long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x; b < batch; b += (long long)gridDim.x * blockDim.x) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const int chunk = (n_bits + 31) >> 5;                       // bits per lane
+    // g = x^chunk mod P (the same for every block of the call)
+    uint32_t g = 1u;
+    for (int i = 0; i < chunk; ++i) g = crc_step_bit(g, 0u, poly, mask, L);
+    for (long long b = warp; b < batch; b += n_warps) {
         const uint8_t *row = bits + b * stride;
-        uint32_t reg = 0;
-        for (int i = 0; i < n_bits; ++i) {
-            const uint32_t fb = ((reg >> (L - 1)) ^ row[i]) & 1u;
-            reg = (reg << 1) & mask;
-            if (fb) reg ^= poly;
+        const int end = n_bits - (31 - lane) * chunk;           // this lane's chunk is [end - chunk, end) clipped at 0
+        const int beg = end - chunk < 0 ? 0 : end - chunk;
+        uint32_t v = 0;
+        for (int i = beg; i < end; ++i) v = crc_step_bit(v, row[i], poly, mask, L);
+        // Horner tree: lane 31 ends up with sum_i r_i * g^(31 - i)
+        uint32_t gp = g;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xffffffffu, v, d);
+            if ((lane & (2 * d - 1)) == 2 * d - 1) v ^= crc_mulmod(up, gp, poly, mask, L);
+            gp = crc_mulmod(gp, gp, poly, mask, L);
         }
-        if (parity)
-            for (int i = 0; i < L; ++i) parity[b * parity_stride + i] = (uint8_t)((reg >> (L - 1 - i)) & 1u);
-        if (ok) ok[b] = reg == 0 ? 1 : 0;
+        const uint32_t reg = __shfl_sync(0xffffffffu, v, 31);
+        if (parity && lane < L) parity[b * parity_stride + lane] = (uint8_t)((reg >> (L - 1 - lane)) & 1u);
+        if (ok && lane == 0) ok[b] = reg == 0 ? 1 : 0;
     }
 }
 

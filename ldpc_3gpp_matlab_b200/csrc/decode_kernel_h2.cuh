@@ -68,6 +68,42 @@ struct SyndromeRowsH2<BG, BgShape<BG>::kRows, FULL> {
     static __device__ __forceinline__ uint32_t run(const DecArgs &, const Lane &, uint32_t fail) { return fail; }
 };
 
+// Bit-sliced syndrome of a codeword pair (see pack_hard_bits / syndrome_bitsliced in decode_kernel.cuh): the hard
+// decisions of codeword A (bit 15 of every word) and B (bit 31) are packed into hb[0][col][Z/32] and hb[1][col][Z/32].
+__device__ __forceinline__ void pack_hard_bits_h2(const uint32_t *app, uint32_t *hb, int Z, int n_cols, int n_cols_all, int z) {
+    const int W = Z >> 5, w = z >> 5;
+    for (int col = 0; col < n_cols; ++col) {
+        const uint32_t x = app[col * Z + z];
+        const uint32_t wa = __ballot_sync(0xffffffffu, (x >> 15) & 1u);
+        const uint32_t wb = __ballot_sync(0xffffffffu, x >> 31);
+        if ((z & 31) == 0) {
+            hb[col * W + w] = wa;
+            hb[(n_cols_all + col) * W + w] = wb;
+        }
+    }
+}
+// returns bit 15 set if codeword A fails, bit 31 if B fails (the convention of syndrome_unrolled_h2)
+__device__ __noinline__ uint32_t syndrome_bitsliced_h2(const DecArgs &a, const uint32_t *hb, int z) {
+    const int Z = a.Z, W = Z >> 5, z0 = z & ~31;
+    const uint32_t *hbB = hb + a.ncols * W;
+    uint32_t fa = 0, fb = 0;
+    for (int r = z & 31; r < a.n_rows; r += 32) {
+        uint32_t xa = 0, xb = 0;
+        for (int e = a.row_start[r]; e < a.row_start[r + 1]; ++e) {
+            const uint2 d = a.ed[e];
+            int p = z0 + (int)(d.x >> 2);
+            if (p >= Z) p -= Z;
+            const uint32_t cb = (d.y - a.smem_base) >> 7;
+            const int i0 = p >> 5, i1 = i0 + 1 == W ? 0 : i0 + 1;
+            xa ^= __funnelshift_r(hb[cb + i0], hb[cb + i1], p & 31);
+            xb ^= __funnelshift_r(hbB[cb + i0], hbB[cb + i1], p & 31);
+        }
+        fa |= xa;
+        fb |= xb;
+    }
+    return (fa ? 0x00008000u : 0u) | (fb ? 0x80000000u : 0u);
+}
+
 template <int BG, bool FULL>
 __device__ __noinline__ uint32_t syndrome_unrolled_h2(const DecArgs &a, const Lane l) {   // out of line: see decode_kernel.cuh
     return SyndromeRowsH2<BG, 0, FULL>::run(a, l, 0u);
@@ -302,6 +338,8 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
     uint32_t *app = reinterpret_cast<uint32_t *>(smem_raw);
     int *s_flag = reinterpret_cast<int *>(app + (size_t)a.cwpc * a.slot_stride);  // [2*cwpc] + work-group slot
     int &s_group = s_flag[2 * a.cwpc];
+    // FULL kernels: packed hard decisions of both codewords, behind the work slot and the (unused here) barrier slot
+    uint32_t *hb = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(s_flag + 2 * a.cwpc + 1) + 7) & ~(uintptr_t)7) + 2;
     if ((uint32_t)__cvta_generic_to_shared(smem_raw) != a.smem_base) __trap();
 
     const int tid = threadIdx.x;
@@ -349,7 +387,13 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
             if (!fin_a) it_a = it + 1;
             if (!fin_b) it_b = it + 1;
             if (a.early_term || (want_ok && last)) {
-                if (!c.done) {
+                if (FULL && a.n_rows >= kBitslicedSyndromeMinRows) {
+                    pack_hard_bits_h2(app, hb, Z, min(a.ncols, a.kcols + a.n_rows), a.ncols, tid);
+                    __syncthreads();
+                    const uint32_t f = syndrome_bitsliced_h2(a, hb, tid);
+                    if (f & 0x00008000u) s_flag[0] = 1;
+                    if (f & 0x80000000u) s_flag[1] = 1;
+                } else if (!c.done) {
                     const uint32_t f = syndrome_unrolled_h2<BG, FULL>(a, c.l) & kH2Sign;
                     if (f & 0x00008000u) s_flag[2 * slot] = 1;
                     if (f & 0x80000000u) s_flag[2 * slot + 1] = 1;

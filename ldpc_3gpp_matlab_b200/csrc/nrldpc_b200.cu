@@ -165,7 +165,10 @@ int decode_threads(int cols, int Z) { return std::max(32, (decode_cwpc(cols, Z) 
 size_t decode_smem_bytes(const nrldpc_handle *h, int n_rows) {
     const int cwpc = decode_cwpc(h->d.cols, h->d.Z);
     (void)n_rows;
-    return (size_t)cwpc * decode_slot_stride(h->d.cols, h->d.Z) * 4 + (size_t)(2 * cwpc + 1) * 4 + 16;
+    // APP arrays, flags + work slot, mbarrier, and (one codeword per CTA, Z a multiple of 32) the packed hard decisions
+    // of the bit-sliced syndrome: two words per (column, warp) cover the float32 and the packed-half kernel
+    const size_t hb = (cwpc == 1 && h->d.Z % 32 == 0) ? (size_t)h->d.cols * (h->d.Z / 32) * 8 : 0;
+    return (size_t)cwpc * decode_slot_stride(h->d.cols, h->d.Z) * 4 + (size_t)(2 * cwpc + 1) * 4 + 16 + hb;
 }
 
 int ensure_scratch(nrldpc_handle *h, PipeSlot &s, size_t recs) {
@@ -972,7 +975,7 @@ NRLDPC_EXPORT int nrldpc_crc(nrldpc_t *h, const uint8_t *bits, int64_t batch, in
     if (!bits || (!parity && !ok)) return fail(h, NRLDPC_ESHAPE, "bits and one of parity / ok must not be NULL");
     if (parity && parity_stride < L) return fail(h, NRLDPC_ESHAPE, "parity_stride must be at least the CRC length");
     CUDA_TRY(h, cudaSetDevice(h->device));
-    nrldpc::crc_kernel<<<grid_for(h, batch, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(bits, batch, n_bits, stride, poly, L,
+    nrldpc::crc_kernel<<<grid_for(h, batch * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(bits, batch, n_bits, stride, poly, L,
                                                                                              parity, parity_stride, ok);
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
