@@ -65,6 +65,8 @@ struct DecArgs {
     int slot_stride;         // words between the APP arrays of two codewords (pairs) of a CTA: cols*Z + pad, see decode_slot_stride
     float alpha;
     int l2_pin;              // 1: c2v scratch accesses carry an L2 evict_last policy
+    int bitsliced_min_rows;  // FULL kernels: bit-sliced syndrome from this many active rows on (else per-thread unrolled)
+    int staged_min_rows;     // per-thread syndrome: core rows first, extension rows only if they hold, from this many rows on
     int one;                 // = 1 (see mad_u32)
     uint32_t smem_base;      // shared-window address of the kernel's dynamic shared memory
     uint32_t alpha_h2;       // {fp16(alpha), fp16(alpha)} for the packed-half kernel
@@ -77,12 +79,14 @@ struct DecArgs {
 template <int BG> struct BgShape;
 template <> struct BgShape<1> {
     static constexpr int kRows = NRLDPC_BG1_ROWS;
+    static constexpr int kCols = 68, kKcols = 22;   // block columns, information columns (NRLDPC.m:414-454)
     static __host__ __device__ constexpr int deg(int r) { return nrldpc_bg1_deg[r]; }
     static __host__ __device__ constexpr int start(int r) { return nrldpc_bg1_start[r]; }
     static __host__ __device__ constexpr int col(int e) { return nrldpc_bg1_col[e]; }
 };
 template <> struct BgShape<2> {
     static constexpr int kRows = NRLDPC_BG2_ROWS;
+    static constexpr int kCols = 52, kKcols = 10;
     static __host__ __device__ constexpr int deg(int r) { return nrldpc_bg2_deg[r]; }
     static __host__ __device__ constexpr int start(int r) { return nrldpc_bg2_start[r]; }
     static __host__ __device__ constexpr int col(int e) { return nrldpc_bg2_col[e]; }
@@ -120,6 +124,14 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
 }
 __device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t x;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(addr));
+    return x;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
 // c2v scratch accesses: L1-bypassing, with an L2 cache policy (evict_last pins the scratch in L2 so
@@ -335,10 +347,10 @@ __device__ __forceinline__ void load_group(const DecArgs &a, float *app, long lo
     }
 }
 
-// exact syndrome of hard = (app < 0) over the active rows ('Parity check satisfied', NRLDPCDecoder.m:120)
-__device__ __forceinline__ int syndrome_fail(const DecArgs &a, const DecCtx &c) {
+// exact syndrome of hard = (app < 0) over the active rows r0 <= r < r1 ('Parity check satisfied', NRLDPCDecoder.m:120)
+__device__ __forceinline__ uint32_t syndrome_fail(const DecArgs &a, const DecCtx &c, int r0, int r1) {
     uint32_t fail = 0;
-    for (int r = 0; r < a.n_rows; ++r) {
+    for (int r = r0; r < r1; ++r) {
         uint32_t par = 0;
         for (int e = a.row_start[r]; e < a.row_start[r + 1]; ++e) {
             const uint2 d = a.ed[e];
@@ -346,7 +358,7 @@ __device__ __forceinline__ int syndrome_fail(const DecArgs &a, const DecCtx &c) 
         }
         fail |= par;
     }
-    return (int)(fail >> 31);
+    return fail;
 }
 
 __device__ __forceinline__ void store_outputs(const DecArgs &a, const float *app, long long cw0, int n_here, int ncw, int K) {
@@ -387,7 +399,7 @@ __device__ __forceinline__ void store_outputs(const DecArgs &a, const float *app
 // The same syndrome with the base graph's shape known at compile time: edge operands come from the parameter bank
 // as in the layer code (no descriptor loads, no loop control) -- about 5 instructions per edge instead of 12.  With
 // 'Parity check satisfied' (the reference's only setting, NRLDPCDecoder.m:120) this runs after EVERY iteration.
-template <int BG, int R, bool FULL>
+template <int BG, int R, int REND, bool FULL>
 struct SyndromeRows {
     static __device__ __forceinline__ uint32_t run(const DecArgs &a, const Lane &l, uint32_t fail) {
         if (R >= 4 && R >= a.n_rows) return fail;
@@ -399,53 +411,102 @@ struct SyndromeRows {
             par ^= __float_as_uint(lds_f32(edge_addr<FULL>(l, a.ed[E0 + e], (R >= 4) && e == DEG - 1)));
         fail |= par;
         asm volatile("" : "+r"(fail));   // one row's loads are consumed before the next row's are issued (register pressure)
-        return SyndromeRows<BG, R + 1, FULL>::run(a, l, fail);
+        return SyndromeRows<BG, R + 1, REND, FULL>::run(a, l, fail);
     }
 };
-template <int BG, bool FULL>
-struct SyndromeRows<BG, BgShape<BG>::kRows, FULL> {
+template <int BG, int REND, bool FULL>
+struct SyndromeRows<BG, REND, REND, FULL> {
     static __device__ __forceinline__ uint32_t run(const DecArgs &, const Lane &, uint32_t fail) { return fail; }
 };
 
 // Out of line on purpose: inlined into the decode kernel the 316 unrolled loads changed the register allocation of
 // the layer code (552 bytes of spills, 3.10 -> 3.97 ms on the fixed-iteration headline that never runs it).
+// Two stages: the four core rows (degree 19 / 8..10, they cover every information and core-parity column), then the
+// extension rows.  A codeword that has not converged almost surely fails a core check, so with enough active rows the
+// kernel runs the extension stage only for codewords whose core checks hold (DecArgs::staged_min_rows): the exact
+// result of the full syndrome at a quarter of the loads in every iteration but a codeword's last.
 template <int BG, bool FULL>
-__device__ __noinline__ uint32_t syndrome_unrolled(const DecArgs &a, const Lane l) {
-    return SyndromeRows<BG, 0, FULL>::run(a, l, 0u);
+__device__ __noinline__ uint32_t syndrome_unrolled_core(const DecArgs &a, const Lane l) {
+    return SyndromeRows<BG, 0, 4, FULL>::run(a, l, 0u);
+}
+template <int BG, bool FULL>
+__device__ __noinline__ uint32_t syndrome_unrolled_ext(const DecArgs &a, const Lane l) {
+    return SyndromeRows<BG, 4, BgShape<BG>::kRows, FULL>::run(a, l, 0u);
 }
 
 // Bit-sliced syndrome for the FULL kernels (Z a multiple of 32, one codeword per CTA).  After an iteration every warp
-// packs the hard decisions of its 32 variables of each block column into one word (ballot), giving hb[col][Z/32];
+// packs the hard decisions of its 32 variables of a block column into one word (ballot), giving hb[col][Z/32];
 // the 32 checks z0..z0+31 of base row r then see, for an edge (col, shift), the 32 consecutive bits starting at
-// (z0 + shift) mod Z of column col: two words and a funnel shift.  Warp w owns the checks 32w..32w+31 of EVERY row
-// and spreads the rows over its lanes (lane l: rows l, l+32), so the whole syndrome costs each warp about
-// 2 x 19 edge visits instead of 316 -- with 'Parity check satisfied' this runs after every iteration.
-// With few active rows (high code rates) the unrolled per-thread syndrome is cheaper than pack + barrier + the lane-serial
-// row walk: measured on BG1 Z=384 with 5 rows, 25.4 Gb/s (unrolled) against 21.6 Gb/s (bit-sliced).
-constexpr int kBitslicedSyndromeMinRows = 12;
-__device__ __forceinline__ void pack_hard_bits(const float *app, uint32_t *hb, int Z, int n_cols, int z) {
-    const int W = Z >> 5, w = z >> 5;
-    for (int col = 0; col < n_cols; ++col) {
-        const uint32_t word = __ballot_sync(0xffffffffu, __float_as_uint(app[col * Z + z]) >> 31);
-        if ((z & 31) == 0) hb[col * W + w] = word;
+// (z0 + shift) mod Z of column col: two words and a funnel shift.  Warp w owns the checks 32w..32w+31 of EVERY row.
+// Two stages (with 'Parity check satisfied', NRLDPCDecoder.m:120, this runs after every iteration, and all but a
+// codeword's last run fail):
+//   1. pack the kcols + 4 core columns; the four core rows, ONE EDGE PER LANE (degree <= 19) and a warp XOR reduction
+//      (REDUX) per row; CTA-wide OR.  A codeword that has not converged almost surely stops here: ~200 instructions
+//      per thread instead of the ~1300 of packing all columns and walking all rows;
+//   2. only if every core check holds: pack the extension columns, walk the extension rows (lane l: rows 4+l, 36+l).
+// The edge descriptors of this routine are lane-indexed, so they are read from a shared-memory copy (`sed`, filled
+// once per CTA: shift | col*W << 16) -- lane-divergent reads of the kernel-parameter constant bank serialise.
+// With few active rows the unrolled per-thread syndrome was cheaper than the unstaged bit-sliced one (BG1 Z=384, 5 rows:
+// 25.4 against 21.6 Gb/s): DecArgs::bitsliced_min_rows.
+// All pointers are shared-window byte addresses (explicit LDS / STS: a generic pointer costs an address-space
+// resolution per access in an out-of-line routine).
+__device__ __forceinline__ void pack_hard_bits(uint32_t app_s, uint32_t hb_s, int Z, int col0, int col1, int z) {
+    uint32_t src = app_s + (uint32_t)(col0 * Z + z) * 4u;
+    uint32_t dst = hb_s + (uint32_t)(col0 * (Z >> 5) + (z >> 5)) * 4u;
+    for (int col = col0; col < col1; ++col, src += (uint32_t)Z * 4u, dst += (uint32_t)(Z >> 5) * 4u) {
+        const uint32_t word = __ballot_sync(0xffffffffu, lds_u32(src) >> 31);
+        if ((z & 31) == 0) sts_u32(dst, word);
     }
 }
-__device__ __noinline__ uint32_t syndrome_bitsliced(const DecArgs &a, const uint32_t *hb, int z) {
-    const int Z = a.Z, W = Z >> 5, z0 = z & ~31;
+__device__ __forceinline__ void fill_syndrome_edges(const DecArgs &a, uint32_t sed_s) {
+    for (int e = threadIdx.x; e < a.n_edges; e += blockDim.x) {
+        const uint2 d = a.ed[e];
+        // shift | byte offset of the column's words (col * Z * 4 / 32 = col * W * 4) << 16
+        sts_u32(sed_s + (uint32_t)e * 4u, (d.x >> 2) | (((d.y - a.smem_base) >> 5) << 16));
+    }
+}
+// the 32 hard decisions checks z0..z0+31 see through edge `desc`
+__device__ __forceinline__ uint32_t hb_window(uint32_t hb_s, uint32_t desc, int z0, int Z, int W) {
+    int p = z0 + (int)(desc & 0xffffu);
+    if (p >= Z) p -= Z;
+    const uint32_t col_s = hb_s + (desc >> 16);
+    const int i0 = p >> 5, i1 = i0 + 1 == W ? 0 : i0 + 1;
+    return __funnelshift_r(lds_u32(col_s + (uint32_t)i0 * 4u), lds_u32(col_s + (uint32_t)i1 * 4u), p & 31);
+}
+// syndrome words of the warp's 32 checks of one core row: one edge per lane, XOR across the warp (REDUX)
+template <int DEG, int E0>
+__device__ __forceinline__ uint32_t core_row_syndrome(uint32_t hb_s, uint32_t sed_s, int lane, int z0, int Z, int W) {
+    uint32_t v = 0;
+    if (lane < DEG) v = hb_window(hb_s, lds_u32(sed_s + (uint32_t)(E0 + lane) * 4u), z0, Z, W);
+    return __reduce_xor_sync(0xffffffffu, v);
+}
+// CTA-uniform result (non-zero: some active check fails).  Contains barriers: every thread of the CTA calls it.
+// app_s: the codeword's APP array; hb_s: packed hard decisions [cols][W], the lane-indexed edge table lies 2*cols*W
+// words behind it.  Scalars by value and the core rows' shape from BgShape: a reference to the kernel parameters would
+// be a generic pointer in this out-of-line routine (LD.E per field); only the rare extension stage reads row_start.
+template <int BG>
+__device__ __noinline__ int syndrome_bitsliced(uint32_t app_s, uint32_t hb_s, int Z, int n_rows, int z, const unsigned short *row_start) {
+    using S = BgShape<BG>;
+    const int W = Z >> 5, z0 = z & ~31, lane = z & 31;
+    constexpr int kCore = S::kKcols + 4;
+    const uint32_t sed_s = hb_s + (uint32_t)(S::kCols * W) * 8u;
+    pack_hard_bits(app_s, hb_s, Z, 0, kCore, z);
+    __syncthreads();
     uint32_t fail = 0;
-    for (int r = z & 31; r < a.n_rows; r += 32) {
+    fail |= core_row_syndrome<S::deg(0), S::start(0)>(hb_s, sed_s, lane, z0, Z, W);
+    fail |= core_row_syndrome<S::deg(1), S::start(1)>(hb_s, sed_s, lane, z0, Z, W);
+    fail |= core_row_syndrome<S::deg(2), S::start(2)>(hb_s, sed_s, lane, z0, Z, W);
+    fail |= core_row_syndrome<S::deg(3), S::start(3)>(hb_s, sed_s, lane, z0, Z, W);
+    if (__syncthreads_or(fail != 0u)) return 1;
+    if (n_rows <= 4) return 0;
+    pack_hard_bits(app_s, hb_s, Z, kCore, min(S::kCols, S::kKcols + n_rows), z);
+    __syncthreads();
+    for (int r = 4 + lane; r < n_rows; r += 32) {
         uint32_t acc = 0;
-        for (int e = a.row_start[r]; e < a.row_start[r + 1]; ++e) {
-            const uint2 d = a.ed[e];
-            int p = z0 + (int)(d.x >> 2);
-            if (p >= Z) p -= Z;
-            const uint32_t cb = (d.y - a.smem_base) >> 7;          // col * Z * 4 / 128 = col * W
-            const int i0 = p >> 5, i1 = i0 + 1 == W ? 0 : i0 + 1;
-            acc ^= __funnelshift_r(hb[cb + i0], hb[cb + i1], p & 31);
-        }
+        for (int e = row_start[r]; e < row_start[r + 1]; ++e) acc ^= hb_window(hb_s, lds_u32(sed_s + (uint32_t)e * 4u), z0, Z, W);
         fail |= acc;
     }
-    return fail;
+    return __syncthreads_or(fail != 0u);
 }
 
 // ---- one full iteration over the layers: looped (generic) --------------------------------------
@@ -554,10 +615,12 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
     const int ncw = a.ncols * Z;
     const int K = a.kcols * Z;
     float *app = reinterpret_cast<float *>(smem_raw);
-    int *s_flag = reinterpret_cast<int *>(app + (size_t)a.cwpc * a.slot_stride);  // [cwpc] + work-group slot
-    int &s_group = s_flag[a.cwpc];
-    uint64_t *bar = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(s_flag + a.cwpc + 1) + 7) & ~(uintptr_t)7);
-    uint32_t *hb = reinterpret_cast<uint32_t *>(bar + 1);   // FULL kernels: packed hard decisions [ncols][Z/32]
+    // behind the APP arrays: syndrome flags of the two stages [2][cwpc] (the packed-half kernel has [2][2*cwpc]), the
+    // work-group slot, the TMA mbarrier, and for the FULL kernels the packed hard decisions [ncols][Z/32] (two planes
+    // in the packed-half kernel) and the lane-indexed edge table of the bit-sliced syndrome (decode_smem_bytes)
+    int *s_flag = reinterpret_cast<int *>(app + (size_t)a.cwpc * a.slot_stride);
+    int &s_group = s_flag[4 * a.cwpc];
+    uint64_t *bar = reinterpret_cast<uint64_t *>((reinterpret_cast<uintptr_t>(s_flag + 4 * a.cwpc + 1) + 7) & ~(uintptr_t)7);
     uint32_t bar_parity = 0;
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
@@ -565,6 +628,9 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
     }
     // the edge descriptors carry absolute shared addresses (DecArgs::ed): fail loudly if the window moved
     if ((uint32_t)__cvta_generic_to_shared(smem_raw) != a.smem_base) __trap();
+    const bool bitsliced = FULL && a.n_rows >= a.bitsliced_min_rows;
+    if (bitsliced && (a.early_term || a.ok != nullptr))   // ordered by the barriers below
+        fill_syndrome_edges(a, (uint32_t)__cvta_generic_to_shared(bar + 1) + (uint32_t)(a.ncols * (Z >> 5)) * 8u);
 
     const int tid = threadIdx.x;
     const int slot = tid / Z;
@@ -591,7 +657,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
         const int n_here = (int)min((long long)a.cwpc, a.batch - cw0);
 
         load_group(a, app, cw0, n_here, ncw, bar, bar_parity);
-        if (tid < a.cwpc) s_flag[tid] = 0;
+        if (tid < 2 * a.cwpc) s_flag[tid] = 0;
         __syncthreads();
 
         const bool active = lane_ok && slot < n_here;
@@ -608,23 +674,36 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
             if (!c.done) my_iters = it + 1;
             const bool last = it + 1 == a.max_iters;
             if (a.early_term || (want_ok && last)) {
-                if (FULL && a.n_rows >= kBitslicedSyndromeMinRows) {
-                    pack_hard_bits(app, hb, Z, min(a.ncols, a.kcols + a.n_rows), tid);
+                if (FULL && bitsliced) {
+                    // one codeword per CTA: the verdict is CTA-uniform, no flags
+                    my_ok = syndrome_bitsliced<(BG == 0 ? 1 : BG)>(a.smem_base, (uint32_t)__cvta_generic_to_shared(bar + 1), Z, a.n_rows, tid, a.row_start) ? 0 : 1;
+                    if (a.early_term && my_ok) break;
+                } else {
+                    constexpr int B = BG == 0 ? 1 : BG;
+                    int *s_flag2 = s_flag + a.cwpc;
+                    const bool staged = a.n_rows >= a.staged_min_rows;
+                    if (!c.done) {
+                        uint32_t f = BG == 0 ? syndrome_fail(a, c, 0, 4) : syndrome_unrolled_core<B, FULL>(a, c.l);
+                        if (!staged) f |= BG == 0 ? syndrome_fail(a, c, 4, a.n_rows) : syndrome_unrolled_ext<B, FULL>(a, c.l);
+                        if (f >> 31) s_flag[slot] = 1;
+                    }
+                    if (staged) {
+                        // extension rows only for codewords whose core checks all hold
+                        __syncthreads();
+                        if (!c.done && !s_flag[slot]) {
+                            const uint32_t f = BG == 0 ? syndrome_fail(a, c, 4, a.n_rows) : syndrome_unrolled_ext<B, FULL>(a, c.l);
+                            if (f >> 31) s_flag2[slot] = 1;
+                        }
+                    }
                     __syncthreads();
-                    if (syndrome_bitsliced(a, hb, tid)) s_flag[0] = 1;
-                } else if (!c.done) {
-                    const int f = BG == 0 ? syndrome_fail(a, c)
-                                          : (int)(syndrome_unrolled<(BG == 0 ? 1 : BG), FULL>(a, c.l) >> 31);
-                    if (f) s_flag[slot] = 1;
+                    if (!c.done) {
+                        my_ok = (s_flag[slot] | s_flag2[slot]) ? 0 : 1;
+                        if (my_ok && a.early_term) c.done = true;
+                    }
+                    const int all_done = __syncthreads_and(c.done ? 1 : 0);  // also orders the flag reset below
+                    if (tid < 2 * a.cwpc) s_flag[tid] = 0;
+                    if (a.early_term && all_done) break;
                 }
-                __syncthreads();
-                if (!c.done) {
-                    my_ok = s_flag[slot] ? 0 : 1;
-                    if (my_ok && a.early_term) c.done = true;
-                }
-                const int all_done = __syncthreads_and(c.done ? 1 : 0);  // also orders the flag reset below
-                if (tid < a.cwpc) s_flag[tid] = 0;
-                if (a.early_term && all_done) break;
             }
         }
         __syncthreads();

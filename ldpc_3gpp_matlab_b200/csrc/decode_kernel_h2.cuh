@@ -29,15 +29,6 @@ constexpr uint32_t kH2Sign = 0x80008000u;
 __device__ __forceinline__ __half2 as_h2(uint32_t u) { return *reinterpret_cast<__half2 *>(&u); }
 __device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
 
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t x;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(addr));
-    return x;
-}
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-
 __device__ __forceinline__ float clamp_llr_h2(float x) { return __fadd_rn(fmaxf(fminf(x, kH2LlrMax), -kH2LlrMax), 0.0f); }
 
 // One check row of degree DEG for check z of a codeword pair.  Record layout (uint4; three words
@@ -49,7 +40,7 @@ __device__ __forceinline__ float clamp_llr_h2(float x) { return __fadd_rn(fmaxf(
 //          edges 16..DEG-1 at the top of each half
 // Arg-min indices are compared as fp16 bit patterns (HSET2 without flush-to-zero).
 // syndrome with the base graph's shape known at compile time (see SyndromeRows in decode_kernel.cuh)
-template <int BG, int R, bool FULL>
+template <int BG, int R, int REND, bool FULL>
 struct SyndromeRowsH2 {
     static __device__ __forceinline__ uint32_t run(const DecArgs &a, const Lane &l, uint32_t fail) {
         if (R >= 4 && R >= a.n_rows) return fail;
@@ -60,53 +51,84 @@ struct SyndromeRowsH2 {
         for (int e = 0; e < DEG; ++e) par ^= lds_u32(edge_addr<FULL>(l, a.ed[E0 + e], (R >= 4) && e == DEG - 1));
         fail |= par;
         asm volatile("" : "+r"(fail));   // one row's loads are consumed before the next row's are issued (register pressure)
-        return SyndromeRowsH2<BG, R + 1, FULL>::run(a, l, fail);
+        return SyndromeRowsH2<BG, R + 1, REND, FULL>::run(a, l, fail);
     }
 };
-template <int BG, bool FULL>
-struct SyndromeRowsH2<BG, BgShape<BG>::kRows, FULL> {
+template <int BG, int REND, bool FULL>
+struct SyndromeRowsH2<BG, REND, REND, FULL> {
     static __device__ __forceinline__ uint32_t run(const DecArgs &, const Lane &, uint32_t fail) { return fail; }
 };
 
-// Bit-sliced syndrome of a codeword pair (see pack_hard_bits / syndrome_bitsliced in decode_kernel.cuh): the hard
+// Bit-sliced, two-stage syndrome of a codeword pair (see syndrome_bitsliced in decode_kernel.cuh): the hard
 // decisions of codeword A (bit 15 of every word) and B (bit 31) are packed into hb[0][col][Z/32] and hb[1][col][Z/32].
-__device__ __forceinline__ void pack_hard_bits_h2(const uint32_t *app, uint32_t *hb, int Z, int n_cols, int n_cols_all, int z) {
-    const int W = Z >> 5, w = z >> 5;
-    for (int col = 0; col < n_cols; ++col) {
-        const uint32_t x = app[col * Z + z];
+// All pointers are shared-window byte addresses (explicit LDS / STS: a generic pointer costs an address-space
+// resolution per access in an out-of-line routine).
+__device__ __forceinline__ void pack_hard_bits_h2(uint32_t app_s, uint32_t hb_s, int Z, int col0, int col1, int n_cols_all, int z) {
+    const uint32_t plane = (uint32_t)n_cols_all * (uint32_t)(Z >> 5) * 4u;
+    uint32_t src = app_s + (uint32_t)(col0 * Z + z) * 4u;
+    uint32_t dst = hb_s + (uint32_t)(col0 * (Z >> 5) + (z >> 5)) * 4u;
+    for (int col = col0; col < col1; ++col, src += (uint32_t)Z * 4u, dst += (uint32_t)(Z >> 5) * 4u) {
+        const uint32_t x = lds_u32(src);
         const uint32_t wa = __ballot_sync(0xffffffffu, (x >> 15) & 1u);
         const uint32_t wb = __ballot_sync(0xffffffffu, x >> 31);
         if ((z & 31) == 0) {
-            hb[col * W + w] = wa;
-            hb[(n_cols_all + col) * W + w] = wb;
+            sts_u32(dst, wa);
+            sts_u32(dst + plane, wb);
         }
     }
 }
-// returns bit 15 set if codeword A fails, bit 31 if B fails (the convention of syndrome_unrolled_h2)
-__device__ __noinline__ uint32_t syndrome_bitsliced_h2(const DecArgs &a, const uint32_t *hb, int z) {
-    const int Z = a.Z, W = Z >> 5, z0 = z & ~31;
-    const uint32_t *hbB = hb + a.ncols * W;
+// CTA-uniform result: bit 15 set if codeword A fails, bit 31 if B fails (the convention of the per-thread syndrome).
+// live_a / live_b (CTA-uniform): the codeword is still being decoded -- the extension stage runs only if a live
+// codeword passed the core stage.  Contains barriers: every thread of the CTA calls it.
+template <int BG>
+__device__ __noinline__ uint32_t syndrome_bitsliced_h2(uint32_t app_s, uint32_t hb_s, int Z, int n_rows, int z, const unsigned short *row_start,
+                                                       bool live_a, bool live_b) {
+    using S = BgShape<BG>;
+    const int W = Z >> 5, z0 = z & ~31, lane = z & 31;
+    constexpr int kCore = S::kKcols + 4;
+    const uint32_t hbB_s = hb_s + (uint32_t)(S::kCols * W) * 4u, sed_s = hb_s + (uint32_t)(S::kCols * W) * 8u;
+    pack_hard_bits_h2(app_s, hb_s, Z, 0, kCore, S::kCols, z);
+    __syncthreads();
     uint32_t fa = 0, fb = 0;
-    for (int r = z & 31; r < a.n_rows; r += 32) {
+    fa |= core_row_syndrome<S::deg(0), S::start(0)>(hb_s, sed_s, lane, z0, Z, W);
+    fb |= core_row_syndrome<S::deg(0), S::start(0)>(hbB_s, sed_s, lane, z0, Z, W);
+    fa |= core_row_syndrome<S::deg(1), S::start(1)>(hb_s, sed_s, lane, z0, Z, W);
+    fb |= core_row_syndrome<S::deg(1), S::start(1)>(hbB_s, sed_s, lane, z0, Z, W);
+    fa |= core_row_syndrome<S::deg(2), S::start(2)>(hb_s, sed_s, lane, z0, Z, W);
+    fb |= core_row_syndrome<S::deg(2), S::start(2)>(hbB_s, sed_s, lane, z0, Z, W);
+    fa |= core_row_syndrome<S::deg(3), S::start(3)>(hb_s, sed_s, lane, z0, Z, W);
+    fb |= core_row_syndrome<S::deg(3), S::start(3)>(hbB_s, sed_s, lane, z0, Z, W);
+    // __syncthreads_or reduces a predicate, not a bit mask: one barrier per codeword
+    uint32_t f = __syncthreads_or(fa != 0u) ? 0x00008000u : 0u;
+    if (__syncthreads_or(fb != 0u)) f |= 0x80000000u;
+    const bool need_ext = (live_a && !(f & 0x00008000u)) || (live_b && !(f & 0x80000000u));
+    if (!need_ext || n_rows <= 4) return f;
+    pack_hard_bits_h2(app_s, hb_s, Z, kCore, min(S::kCols, S::kKcols + n_rows), S::kCols, z);
+    __syncthreads();
+    fa = 0; fb = 0;
+    for (int r = 4 + lane; r < n_rows; r += 32) {
         uint32_t xa = 0, xb = 0;
-        for (int e = a.row_start[r]; e < a.row_start[r + 1]; ++e) {
-            const uint2 d = a.ed[e];
-            int p = z0 + (int)(d.x >> 2);
-            if (p >= Z) p -= Z;
-            const uint32_t cb = (d.y - a.smem_base) >> 7;
-            const int i0 = p >> 5, i1 = i0 + 1 == W ? 0 : i0 + 1;
-            xa ^= __funnelshift_r(hb[cb + i0], hb[cb + i1], p & 31);
-            xb ^= __funnelshift_r(hbB[cb + i0], hbB[cb + i1], p & 31);
+        for (int e = row_start[r]; e < row_start[r + 1]; ++e) {
+            const uint32_t d = lds_u32(sed_s + (uint32_t)e * 4u);
+            xa ^= hb_window(hb_s, d, z0, Z, W);
+            xb ^= hb_window(hbB_s, d, z0, Z, W);
         }
         fa |= xa;
         fb |= xb;
     }
-    return (fa ? 0x00008000u : 0u) | (fb ? 0x80000000u : 0u);
+    if (__syncthreads_or(fa != 0u)) f |= 0x00008000u;
+    if (__syncthreads_or(fb != 0u)) f |= 0x80000000u;
+    return f;
 }
 
+// out of line, two stages: see syndrome_unrolled_core / _ext in decode_kernel.cuh
 template <int BG, bool FULL>
-__device__ __noinline__ uint32_t syndrome_unrolled_h2(const DecArgs &a, const Lane l) {   // out of line: see decode_kernel.cuh
-    return SyndromeRowsH2<BG, 0, FULL>::run(a, l, 0u);
+__device__ __noinline__ uint32_t syndrome_unrolled_core_h2(const DecArgs &a, const Lane l) {
+    return SyndromeRowsH2<BG, 0, 4, FULL>::run(a, l, 0u);
+}
+template <int BG, bool FULL>
+__device__ __noinline__ uint32_t syndrome_unrolled_ext_h2(const DecArgs &a, const Lane l) {
+    return SyndromeRowsH2<BG, 4, BgShape<BG>::kRows, FULL>::run(a, l, 0u);
 }
 
 template <int DEG>
@@ -328,6 +350,12 @@ struct UnrolledRowsH2<BG, BgShape<BG>::kRows, FULL> {
     static __device__ __forceinline__ void run(const DecArgs &, DecCtxH2 &, int, int, bool) {}
 };
 
+// shared-window address of the packed hard decisions of both codewords (FULL kernels): behind the flags, the work slot
+// and the (unused here) barrier slot
+__device__ __forceinline__ uint32_t h2_hard_bits(int *s_flag, int cwpc) {
+    return (((uint32_t)__cvta_generic_to_shared(s_flag + 4 * cwpc + 1) + 7u) & ~7u) + 8u;
+}
+
 // Here cwpc counts codeword PAIRS per CTA; FULL = one pair per CTA and every thread owns a check.
 template <int BG, bool FULL>
 __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kernel(const __grid_constant__ DecArgs a) {
@@ -336,11 +364,14 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
     const int ncw = a.ncols * Z;
     const int K = a.kcols * Z;
     uint32_t *app = reinterpret_cast<uint32_t *>(smem_raw);
-    int *s_flag = reinterpret_cast<int *>(app + (size_t)a.cwpc * a.slot_stride);  // [2*cwpc] + work-group slot
-    int &s_group = s_flag[2 * a.cwpc];
-    // FULL kernels: packed hard decisions of both codewords, behind the work slot and the (unused here) barrier slot
-    uint32_t *hb = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(s_flag + 2 * a.cwpc + 1) + 7) & ~(uintptr_t)7) + 2;
+    // layout behind the APP arrays as in decode_nms_kernel: flags [2 stages][2*cwpc], work-group slot, (unused here)
+    // barrier slot, packed hard decisions of both codewords, lane-indexed edge table
+    int *s_flag = reinterpret_cast<int *>(app + (size_t)a.cwpc * a.slot_stride);
+    int &s_group = s_flag[4 * a.cwpc];
     if ((uint32_t)__cvta_generic_to_shared(smem_raw) != a.smem_base) __trap();
+    const bool bitsliced = FULL && a.n_rows >= a.bitsliced_min_rows;
+    if (bitsliced && (a.early_term || a.ok != nullptr))   // ordered by the barriers below
+        fill_syndrome_edges(a, h2_hard_bits(s_flag, a.cwpc) + (uint32_t)(a.ncols * (Z >> 5)) * 8u);
 
     const int tid = threadIdx.x;
     const int slot = tid / Z;
@@ -372,7 +403,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
         const bool active = lane_ok && 2 * slot < n_here;
         const bool has_b = lane_ok && 2 * slot + 1 < n_here;
         if (active) load_pair(a.llr + cwA * ncw, has_b ? a.llr + cwB * ncw : nullptr, my_app, ncw, z, Z);
-        if (tid < per_group) s_flag[tid] = 0;
+        for (int i = tid; i < 2 * per_group; i += blockDim.x) s_flag[i] = 0;
         __syncthreads();
 
         bool fin_a = !active, fin_b = !has_b;   // finished (converged and already written out, or absent)
@@ -387,27 +418,39 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
             if (!fin_a) it_a = it + 1;
             if (!fin_b) it_b = it + 1;
             if (a.early_term || (want_ok && last)) {
-                if (FULL && a.n_rows >= kBitslicedSyndromeMinRows) {
-                    pack_hard_bits_h2(app, hb, Z, min(a.ncols, a.kcols + a.n_rows), a.ncols, tid);
+                uint32_t fu = 0;   // bit 15: codeword A fails, bit 31: B fails
+                if (FULL && bitsliced) {
+                    fu = syndrome_bitsliced_h2<BG>(a.smem_base, h2_hard_bits(s_flag, a.cwpc), Z, a.n_rows, tid, a.row_start, !fin_a, !fin_b);
+                } else {
+                    const bool staged = a.n_rows >= a.staged_min_rows;
+                    int *s_flag2 = s_flag + 2 * a.cwpc;
+                    if (!c.done) {
+                        uint32_t f = syndrome_unrolled_core_h2<BG, FULL>(a, c.l);
+                        if (!staged) f |= syndrome_unrolled_ext_h2<BG, FULL>(a, c.l);
+                        if (f & 0x00008000u) s_flag[2 * slot] = 1;
+                        if (f & 0x80000000u) s_flag[2 * slot + 1] = 1;
+                    }
+                    if (staged) {
+                        // extension rows only for pairs with a live codeword whose core checks all hold
+                        __syncthreads();
+                        if (!c.done && ((!fin_a && !s_flag[2 * slot]) || (!fin_b && !s_flag[2 * slot + 1]))) {
+                            const uint32_t f = syndrome_unrolled_ext_h2<BG, FULL>(a, c.l);
+                            if (f & 0x00008000u) s_flag2[2 * slot] = 1;
+                            if (f & 0x80000000u) s_flag2[2 * slot + 1] = 1;
+                        }
+                    }
                     __syncthreads();
-                    const uint32_t f = syndrome_bitsliced_h2(a, hb, tid);
-                    if (f & 0x00008000u) s_flag[0] = 1;
-                    if (f & 0x80000000u) s_flag[1] = 1;
-                } else if (!c.done) {
-                    const uint32_t f = syndrome_unrolled_h2<BG, FULL>(a, c.l) & kH2Sign;
-                    if (f & 0x00008000u) s_flag[2 * slot] = 1;
-                    if (f & 0x80000000u) s_flag[2 * slot + 1] = 1;
+                    if (!c.done) fu = ((s_flag[2 * slot] | s_flag2[2 * slot]) ? 0x00008000u : 0u) | ((s_flag[2 * slot + 1] | s_flag2[2 * slot + 1]) ? 0x80000000u : 0u);
                 }
-                __syncthreads();
                 if (!fin_a) {
-                    ok_a = s_flag[2 * slot] ? 0 : 1;
+                    ok_a = (fu & 0x00008000u) ? 0 : 1;
                     if (ok_a && a.early_term) {   // converged: freeze this codeword's outputs now
                         store_half(a, my_app, cwA, 0, ncw, K, z, Z);
                         fin_a = true;
                     }
                 }
                 if (!fin_b) {
-                    ok_b = s_flag[2 * slot + 1] ? 0 : 1;
+                    ok_b = (fu & 0x80000000u) ? 0 : 1;
                     if (ok_b && a.early_term) {
                         store_half(a, my_app, cwB, 1, ncw, K, z, Z);
                         fin_b = true;
@@ -415,7 +458,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
                 }
                 c.done = fin_a && fin_b;
                 const int all_done = __syncthreads_and(c.done ? 1 : 0);  // also orders the flag reset below
-                if (tid < per_group) s_flag[tid] = 0;
+                for (int i = tid; i < 2 * per_group; i += blockDim.x) s_flag[i] = 0;
                 if (a.early_term && all_done) break;
             }
         }

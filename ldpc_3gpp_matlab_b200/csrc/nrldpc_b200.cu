@@ -88,6 +88,8 @@ struct nrldpc_handle {
     int dec_smem_optin = 0;
     int enc_smem_optin = 0;
     int dec_variant = 1;             // NRLDPC_DECODE_VARIANT=loop selects the generic looped kernel
+    int bitsliced_min_rows = 4;      // syndrome variants, see DecArgs (NRLDPC_BITSLICED_MIN_ROWS / NRLDPC_STAGED_MIN_ROWS: experiments)
+    int staged_min_rows = 8;
     int l2_pin = 1;                  // NRLDPC_L2_PIN=0 drops the evict_last policy on the c2v scratch
     uint32_t smem_base = 0;          // shared-window address of dynamic shared memory (probed at create)
     nrldpc::DecArgs dec_args;
@@ -165,10 +167,11 @@ int decode_threads(int cols, int Z) { return std::max(32, (decode_cwpc(cols, Z) 
 size_t decode_smem_bytes(const nrldpc_handle *h, int n_rows) {
     const int cwpc = decode_cwpc(h->d.cols, h->d.Z);
     (void)n_rows;
-    // APP arrays, flags + work slot, mbarrier, and (one codeword per CTA, Z a multiple of 32) the packed hard decisions
-    // of the bit-sliced syndrome: two words per (column, warp) cover the float32 and the packed-half kernel
-    const size_t hb = (cwpc == 1 && h->d.Z % 32 == 0) ? (size_t)h->d.cols * (h->d.Z / 32) * 8 : 0;
-    return (size_t)cwpc * decode_slot_stride(h->d.cols, h->d.Z) * 4 + (size_t)(2 * cwpc + 1) * 4 + 16 + hb;
+    // APP arrays, syndrome flags of both stages (float32: [2][cwpc], packed half: [2][2*cwpc]) + work slot, mbarrier, and
+    // (one codeword per CTA, Z a multiple of 32) the packed hard decisions of the bit-sliced syndrome -- two words per
+    // (column, warp) cover the float32 and the packed-half kernel -- followed by its lane-indexed edge table
+    const size_t hb = (cwpc == 1 && h->d.Z % 32 == 0) ? (size_t)h->d.cols * (h->d.Z / 32) * 8 + (size_t)h->d.edges * 4 : 0;
+    return (size_t)cwpc * decode_slot_stride(h->d.cols, h->d.Z) * 4 + (size_t)(4 * cwpc + 1) * 4 + 16 + hb;
 }
 
 int ensure_scratch(nrldpc_handle *h, PipeSlot &s, size_t recs) {
@@ -227,6 +230,7 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
     a.n_edges = h->h_row_start[n_rows]; a.max_iters = h->cfg.max_iters; a.early_term = h->cfg.early_term;
     a.slot_stride = cwpc == 1 ? h->d.n_cw : decode_slot_stride(h->d.cols, Z);
     a.cwpc = cwpc; a.alpha = h->cfg.alpha; a.l2_pin = h->l2_pin; a.one = 1;
+    a.bitsliced_min_rows = h->bitsliced_min_rows; a.staged_min_rows = h->staged_min_rows;
     a.c2v = s.c2v; a.work_counter = s.counter;
     const uint32_t ah = __half_as_ushort(__float2half_rn(h->cfg.alpha));
     a.alpha_h2 = ah | (ah << 16);
@@ -515,6 +519,8 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
     h->num_sms = prop.multiProcessorCount;
     if (const char *v = getenv("NRLDPC_DECODE_VARIANT")) h->dec_variant = strcmp(v, "loop") == 0 ? 0 : 1;
     if (const char *v = getenv("NRLDPC_L2_PIN")) h->l2_pin = atoi(v) ? 1 : 0;
+    if (const char *v = getenv("NRLDPC_BITSLICED_MIN_ROWS")) h->bitsliced_min_rows = std::max(4, atoi(v));
+    if (const char *v = getenv("NRLDPC_STAGED_MIN_ROWS")) h->staged_min_rows = std::max(5, atoi(v));
     if (const char *v = getenv("NRLDPC_BP_THREADS")) h->bp_threads = atoi(v) > 512 ? 1024 : 512;
 
     const BgView v = bg_view(cfg->bg);
