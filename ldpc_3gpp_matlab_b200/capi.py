@@ -7,12 +7,15 @@ the sm_100a kernels.  There is no CPU fallback: if the shared library is missing
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libnrldpc_b200.so"
+if os.environ.get("NRLDPC_B200_LIB"):   # kernel experiments only: another build of the same library (tools/gpu_variants.sh)
+    LIB_PATH = Path(os.environ["NRLDPC_B200_LIB"])
 
 NRLDPC_OK = 0
 NRLDPC_EUNSUPPORTED = -1

@@ -453,6 +453,7 @@ __device__ __noinline__ uint32_t syndrome_unrolled_ext(const DecArgs &a, const L
 __device__ __forceinline__ void pack_hard_bits(uint32_t app_s, uint32_t hb_s, int Z, int col0, int col1, int z) {
     uint32_t src = app_s + (uint32_t)(col0 * Z + z) * 4u;
     uint32_t dst = hb_s + (uint32_t)(col0 * (Z >> 5) + (z >> 5)) * 4u;
+#pragma unroll 1   // code size: see syndrome_bitsliced
     for (int col = col0; col < col1; ++col, src += (uint32_t)Z * 4u, dst += (uint32_t)(Z >> 5) * 4u) {
         const uint32_t word = __ballot_sync(0xffffffffu, lds_u32(src) >> 31);
         if ((z & 31) == 0) sts_u32(dst, word);
@@ -473,12 +474,12 @@ __device__ __forceinline__ uint32_t hb_window(uint32_t hb_s, uint32_t desc, int 
     const int i0 = p >> 5, i1 = i0 + 1 == W ? 0 : i0 + 1;
     return __funnelshift_r(lds_u32(col_s + (uint32_t)i0 * 4u), lds_u32(col_s + (uint32_t)i1 * 4u), p & 31);
 }
-// syndrome words of the warp's 32 checks of one core row: one edge per lane, XOR across the warp (REDUX)
-template <int DEG, int E0>
-__device__ __forceinline__ uint32_t core_row_syndrome(uint32_t hb_s, uint32_t sed_s, int lane, int z0, int Z, int W) {
-    uint32_t v = 0;
-    if (lane < DEG) v = hb_window(hb_s, lds_u32(sed_s + (uint32_t)(E0 + lane) * 4u), z0, Z, W);
-    return __reduce_xor_sync(0xffffffffu, v);
+// first edges of the four core rows and their end, one byte each (BG1: 0 19 38 57 76; BG2: 0 8 18 26 36)
+template <int BG>
+__host__ __device__ constexpr unsigned long long core_row_starts() {
+    unsigned long long v = 0;
+    for (int r = 0; r <= 4; ++r) v |= (unsigned long long)BgShape<BG>::start(r) << (8 * r);
+    return v;
 }
 // CTA-uniform result (non-zero: some active check fails).  Contains barriers: every thread of the CTA calls it.
 // app_s: the codeword's APP array; hb_s: packed hard decisions [cols][W], the lane-indexed edge table lies 2*cols*W
@@ -493,10 +494,14 @@ __device__ __noinline__ int syndrome_bitsliced(uint32_t app_s, uint32_t hb_s, in
     pack_hard_bits(app_s, hb_s, Z, 0, kCore, z);
     __syncthreads();
     uint32_t fail = 0;
-    fail |= core_row_syndrome<S::deg(0), S::start(0)>(hb_s, sed_s, lane, z0, Z, W);
-    fail |= core_row_syndrome<S::deg(1), S::start(1)>(hb_s, sed_s, lane, z0, Z, W);
-    fail |= core_row_syndrome<S::deg(2), S::start(2)>(hb_s, sed_s, lane, z0, Z, W);
-    fail |= core_row_syndrome<S::deg(3), S::start(3)>(hb_s, sed_s, lane, z0, Z, W);
+    constexpr unsigned long long kStarts = core_row_starts<BG>();
+#pragma unroll 1
+    for (int r = 0; r < 4; ++r) {
+        const int e = (int)((kStarts >> (8 * r)) & 0xffu) + lane;
+        uint32_t v = 0;
+        if (e < (int)((kStarts >> (8 * r + 8)) & 0xffu)) v = hb_window(hb_s, lds_u32(sed_s + (uint32_t)e * 4u), z0, Z, W);
+        fail |= __reduce_xor_sync(0xffffffffu, v);
+    }
     if (__syncthreads_or(fail != 0u)) return 1;
     if (n_rows <= 4) return 0;
     pack_hard_bits(app_s, hb_s, Z, kCore, min(S::kCols, S::kKcols + n_rows), z);

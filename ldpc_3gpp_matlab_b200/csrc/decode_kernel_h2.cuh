@@ -67,6 +67,7 @@ __device__ __forceinline__ void pack_hard_bits_h2(uint32_t app_s, uint32_t hb_s,
     const uint32_t plane = (uint32_t)n_cols_all * (uint32_t)(Z >> 5) * 4u;
     uint32_t src = app_s + (uint32_t)(col0 * Z + z) * 4u;
     uint32_t dst = hb_s + (uint32_t)(col0 * (Z >> 5) + (z >> 5)) * 4u;
+#pragma unroll 1
     for (int col = col0; col < col1; ++col, src += (uint32_t)Z * 4u, dst += (uint32_t)(Z >> 5) * 4u) {
         const uint32_t x = lds_u32(src);
         const uint32_t wa = __ballot_sync(0xffffffffu, (x >> 15) & 1u);
@@ -90,14 +91,19 @@ __device__ __noinline__ uint32_t syndrome_bitsliced_h2(uint32_t app_s, uint32_t 
     pack_hard_bits_h2(app_s, hb_s, Z, 0, kCore, S::kCols, z);
     __syncthreads();
     uint32_t fa = 0, fb = 0;
-    fa |= core_row_syndrome<S::deg(0), S::start(0)>(hb_s, sed_s, lane, z0, Z, W);
-    fb |= core_row_syndrome<S::deg(0), S::start(0)>(hbB_s, sed_s, lane, z0, Z, W);
-    fa |= core_row_syndrome<S::deg(1), S::start(1)>(hb_s, sed_s, lane, z0, Z, W);
-    fb |= core_row_syndrome<S::deg(1), S::start(1)>(hbB_s, sed_s, lane, z0, Z, W);
-    fa |= core_row_syndrome<S::deg(2), S::start(2)>(hb_s, sed_s, lane, z0, Z, W);
-    fb |= core_row_syndrome<S::deg(2), S::start(2)>(hbB_s, sed_s, lane, z0, Z, W);
-    fa |= core_row_syndrome<S::deg(3), S::start(3)>(hb_s, sed_s, lane, z0, Z, W);
-    fb |= core_row_syndrome<S::deg(3), S::start(3)>(hbB_s, sed_s, lane, z0, Z, W);
+    constexpr unsigned long long kStarts = core_row_starts<BG>();
+#pragma unroll 1
+    for (int r = 0; r < 4; ++r) {
+        const int e = (int)((kStarts >> (8 * r)) & 0xffu) + lane;
+        uint32_t va = 0, vb = 0;
+        if (e < (int)((kStarts >> (8 * r + 8)) & 0xffu)) {
+            const uint32_t d = lds_u32(sed_s + (uint32_t)e * 4u);
+            va = hb_window(hb_s, d, z0, Z, W);
+            vb = hb_window(hbB_s, d, z0, Z, W);
+        }
+        fa |= __reduce_xor_sync(0xffffffffu, va);
+        fb |= __reduce_xor_sync(0xffffffffu, vb);
+    }
     // __syncthreads_or reduces a predicate, not a bit mask: one barrier per codeword
     uint32_t f = __syncthreads_or(fa != 0u) ? 0x00008000u : 0u;
     if (__syncthreads_or(fb != 0u)) f |= 0x80000000u;
