@@ -62,3 +62,29 @@ def make_llr(O, bg, Z, B, E, esn0, rng, filler=0, k0=0):
     if filler:
         llr[:, d["K"] - filler:d["K"]] = np.inf
     return info, llr
+
+
+def make_core_pass_llr(O, bg, Z, B, n_rows, rng, mag=8.0, wrong=1048576.0):
+    """Noise-free codewords (LLR magnitude `mag`, cw layout incl. the punctured 2Z zeros) in three flavours by index mod 3:
+    0 clean; 1 one EXTENSION parity variable (a degree-1 column of an active extension row) wrong with the largest
+    magnitude -- every core check holds on the hard decisions and one extension check never does; 2 one information bit
+    weakly wrong (the decoder corrects it).  Exercises the two-stage parity-check stop: a codeword that passes the
+    core-row stage must still be rejected by the extension-row stage."""
+    d = O.dims(bg, Z)
+    kcols = d["K"] // Z
+    info = rng.integers(0, 2, (B, d["K"]), dtype=np.uint8)
+    cw = O.encode(bg, Z, info)
+    llr = ((1.0 - 2.0 * cw) * mag).astype(np.float32)
+    llr[:, :2 * Z] = 0
+    kind = np.arange(B) % 3
+    for i in range(B):
+        if kind[i] == 1 and n_rows > 4:
+            col = kcols + 4 + int(rng.integers(0, n_rows - 4))
+            v = col * Z + int(rng.integers(0, Z))
+            llr[i, v] = -np.sign(llr[i, v]) * wrong
+        elif kind[i] == 2:
+            v = 2 * Z + int(rng.integers(0, d["K"] - 2 * Z))
+            llr[i, v] = -llr[i, v] / 4
+    # columns beyond the active rows were "not transmitted"
+    llr[:, (kcols + n_rows) * Z:] = 0
+    return info, llr, kind

@@ -6,7 +6,7 @@ import math
 import numpy as np
 import pytest
 
-from conftest import ALL_Z, make_llr
+from conftest import ALL_Z, make_core_pass_llr, make_llr
 
 pytestmark = pytest.mark.gpu
 
@@ -147,6 +147,29 @@ def test_decode_special_values_and_row_trimming(capi, O, bg, Z, rows):
         assert np.isfinite(out["app"]).all()
         assert (out["hard"] == ref["hard"]).all() and _same_bits(out["app"], ref["app"])
         assert (out["iters"] == ref["iters"]).all() and (out["parity_ok"] == ref["parity_ok"]).all()
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f16x2"])
+@pytest.mark.parametrize("bg,Z,n_rows", [(1, 384, 46), (1, 384, 13), (1, 384, 5), (1, 224, 24), (2, 256, 42), (2, 352, 8),
+                                         (1, 52, 46), (2, 52, 33), (1, 7, 46), (2, 12, 20), (1, 96, 4)])
+def test_early_stop_core_checks_hold_extension_check_fails(capi, O, bg, Z, n_rows, dtype):
+    """Two-stage 'Parity check satisfied' stop (NRLDPCDecoder.m:120): codewords whose core checks all hold while one
+    extension check fails must run to the iteration limit with parity_ok = 0; clean ones stop after one iteration; both
+    kinds share CTAs (small Z) and packed-half pairs.  Bit-exact against the oracle in every output."""
+    rng = np.random.default_rng(7 * Z + n_rows + bg)
+    f16 = dtype == "f16x2"
+    B = 2 * max(1, 384 // Z) + 5
+    info, llr, kind = make_core_pass_llr(O, bg, Z, B, n_rows, rng, wrong=2048.0 if f16 else 1048576.0)
+    ref = O.decode_nms(bg, Z, llr, 3, early_term=True, n_rows=n_rows, f16=f16)
+    h = capi.Handle(bg, Z, 3, True, llr_dtype=capi.F16X2 if f16 else capi.F32)
+    out = h.decode(llr, n_rows=n_rows, want_soft=True)
+    h.close()
+    assert (out["hard"] == ref["hard"]).all() and _same_bits(out["app"], ref["app"])
+    assert (out["iters"] == ref["iters"]).all() and (out["parity_ok"] == ref["parity_ok"]).all()
+    assert (out["parity_ok"][kind == 0] == 1).all() and (out["iters"][kind == 0] == 1).all()
+    if n_rows > 4:
+        assert (out["parity_ok"][kind == 1] == 0).all() and (out["iters"][kind == 1] == 3).all()
+    assert (out["hard"][kind != 1] == info[kind != 1]).all()
 
 
 def test_decode_alpha_and_iteration_sweep(capi, O):

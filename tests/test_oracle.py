@@ -233,3 +233,31 @@ def test_oracle_b_golden_vectors(O, golden_decode, golden_decode_bp):
             assert (np.packbits(r["hard"], axis=1) == golden_decode_bp[f"{n}__{tag}__hard"]).all(), (n, tag)
             assert (r["iters"] == golden_decode_bp[f"{n}__{tag}__iters"]).all(), (n, tag)
             assert (r["parity_ok"] == golden_decode_bp[f"{n}__{tag}__ok"]).all(), (n, tag)
+
+
+@pytest.mark.parametrize("bg,Z,n_rows", [(1, 384, 46), (2, 52, 33), (1, 7, 13)])
+def test_core_checks_hold_extension_check_fails(O, bg, Z, n_rows):
+    """The scenario the GPU's two-stage parity-check stop must get right, pinned on the oracle: a strongly wrong
+    degree-1 extension parity bit leaves every core check satisfied and one extension check failing for ever."""
+    from conftest import make_core_pass_llr
+    rng = np.random.default_rng(Z + n_rows)
+    info, llr, kind = make_core_pass_llr(O, bg, Z, 9, n_rows, rng)
+    for f16 in (False, True):
+        if f16:
+            llr = np.clip(llr, -2048, 2048)
+        ref = O.decode_nms(bg, Z, llr, 3, early_term=True, n_rows=n_rows, f16=f16)
+        assert (ref["parity_ok"][kind == 0] == 1).all() and (ref["iters"][kind == 0] == 1).all()
+        assert (ref["parity_ok"][kind == 1] == 0).all() and (ref["iters"][kind == 1] == 3).all()
+        assert (ref["parity_ok"][kind == 2] == 1).all()
+        assert (ref["hard"][kind != 1] == info[kind != 1]).all()
+        # structural claim: on the final hard decisions of the kind-1 codewords no core check (rows 0..4Z-1 of H,
+        # get_pcm.m:8) fails, and at least one active extension check does
+        rows, cols = O.pcm(bg, Z)
+        hard_all = (ref["app"] < 0).astype(np.uint8)
+        syn = np.zeros((hard_all.shape[0], int(rows.max()) + 1), dtype=np.uint8)
+        for b in range(hard_all.shape[0]):
+            np.bitwise_xor.at(syn[b], rows, hard_all[b, cols])
+        core_fail = syn[:, :4 * Z].any(axis=1)
+        ext_fail = syn[:, 4 * Z:n_rows * Z].any(axis=1)
+        assert not core_fail[kind == 1].any() and ext_fail[kind == 1].all()
+        assert not core_fail[kind == 0].any() and not ext_fail[kind == 0].any()
