@@ -1,5 +1,6 @@
 """Device-resident BLER-vs-SNR Monte-Carlo loop: the protocol of plot_BLER_vs_SNR.m:104-171 with the
-frame loop (:116) turned into batches that never leave the GPU.
+frame loop (:116) turned into batches that never leave the GPU; snr_vs_a() drives the same loop with the
+protocol of plot_SNR_vs_A.m (required Es/N0 as a function of the block length).
 
 Per batch: random information blocks -> LDPC encode -> rate match (bit selection + interleave) ->
 QPSK + AWGN + exact LLR -> rate recover (+HARQ combine over the rv_id sequence, :124-137) -> decode
@@ -219,6 +220,62 @@ def sweep(A, R, BG, iterations=8, target_block_errors=100, target_BLER=1e-3, EsN
     return rows
 
 
+def interp_required_snr(prev_BLER, BLER, prev_EsN0, EsN0, target_BLER):
+    """plot_SNR_vs_A.m:175: linear interpolation of Es/N0 over log10(BLER) between the last two simulated points, i.e.
+    interp1(log10([prev_BLER, BLER]), [prev_EsN0, EsN0], log10(target_BLER)).  NaN where interp1 returns NaN: no previous
+    point (the first SNR already met the target), a point without errors, or a target outside the bracket."""
+    if prev_BLER is None or not (prev_BLER > 0) or not (BLER > 0) or prev_BLER == BLER:
+        return float("nan")
+    x0, x1, xt = math.log10(prev_BLER), math.log10(BLER), math.log10(target_BLER)
+    if not (min(x0, x1) <= xt <= max(x0, x1)):
+        return float("nan")
+    return prev_EsN0 + (EsN0 - prev_EsN0) * (xt - x0) / (x1 - x0)
+
+
+def snr_vs_a(A_list, R_list, BG, iterations=50, target_block_errors=100, target_BLER=1e-2, EsN0_start=-2.0, EsN0_delta=0.1,
+             seed=0, rv_id_sequence=(0,), batch=4096, max_blocks=None, out_dir="results", log=print, Q_m=2,
+             llr_dtype=capi.F32, algorithm=capi.ALG_NMS):
+    """plot_SNR_vs_A.m:69-193 on device: for every coding rate and information block length, step Es/N0 up from
+    EsN0_start until the BLER falls to target_BLER (:102-162, the frame loop being BlerSimulator batches), then
+    interpolate the Es/N0 at which it equals the target (:175).  Unsupported (A, R) combinations are skipped as in
+    :164-172.  One results file per rate in the reference's format ("%d\t%f\n", :186).  Returns {R: [(A, EsN0)]}."""
+    rank, local_rank, world = D.init()
+    import torch
+    torch.cuda.set_device(local_rank)
+    out = {}
+    for R in R_list:
+        fid = None
+        if rank == 0 and out_dir:
+            Path(out_dir).mkdir(parents=True, exist_ok=True)
+            name = f"SNR_vs_A_{target_BLER:g}_{R:g}_{BG}_{_MOD_NAME[Q_m]}_{iterations}_{target_block_errors}_{seed}.txt"   # :79
+            fid = open(Path(out_dir) / name, "w")
+        rows = []
+        for A in A_list:
+            try:
+                sim = BlerSimulator(A, R, BG, Q_m, rv_id_sequence, iterations, True, 0.75, batch, seed, local_rank, rank, world,
+                                    llr_dtype=llr_dtype, algorithm=algorithm)
+            except capi.UnsupportedParameters as e:                                    # :164-168
+                log(f"A={A} R={R:g}: the requested combination of parameters is not supported ({e}); skipped")
+                continue
+            BLER, prev_BLER, found = 1.0, None, False
+            EsN0, prev_EsN0 = float(EsN0_start) - float(EsN0_delta), None
+            while BLER > target_BLER:                                                  # :102
+                prev_EsN0, EsN0 = EsN0, EsN0 + float(EsN0_delta)
+                tot, found = sim.run_point(EsN0, target_block_errors, max_blocks, found)
+                prev_BLER, BLER = BLER, (tot[1] / tot[0] if found else 1.0)
+            sim.close()
+            req = interp_required_snr(prev_BLER, BLER, prev_EsN0, EsN0, target_BLER)
+            rows.append((int(A), req))
+            log(f"R={R:g} A={A}: required Es/N0 {req:.3f} dB (BLER {prev_BLER:.3e} @ {prev_EsN0:.2f} dB, {BLER:.3e} @ {EsN0:.2f} dB)")
+            if fid:
+                fid.write("%d\t%f\n" % (A, req))                                       # :186
+                fid.flush()
+        if fid:
+            fid.close()
+        out[R] = rows
+    return out
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(description="BLER vs SNR on device (protocol of plot_BLER_vs_SNR.m)")
     ap.add_argument("--A", type=int, default=3842); ap.add_argument("--R", type=float, default=1 / 3)
@@ -232,8 +289,16 @@ def main(argv=None):
     ap.add_argument("--llr-dtype", default="f32", choices=["f32", "f16x2"])
     ap.add_argument("--algorithm", default="nms", choices=["nms", "bp"],
                     help="nms: layered normalized min-sum (default); bp: the reference's flooding sum-product in float64")
+    ap.add_argument("--snr-vs-A", type=int, nargs="+", default=None, metavar="A",
+                    help="run the plot_SNR_vs_A.m protocol over these block lengths instead (uses --R, --target-BLER ...)")
     a = ap.parse_args(argv)
     Q_m = {v: k for k, v in _MOD_NAME.items()}[a.modulation]
+    if a.snr_vs_A:
+        snr_vs_a(a.snr_vs_A, [a.R], a.BG, a.iterations, a.target_block_errors, a.target_BLER, a.EsN0_start, a.EsN0_delta,
+                 a.seed, a.rv, a.batch, a.max_blocks, a.out_dir, Q_m=Q_m,
+                 llr_dtype=capi.F16X2 if a.llr_dtype == "f16x2" else capi.F32,
+                 algorithm=capi.ALG_BP if a.algorithm == "bp" else capi.ALG_NMS)
+        return
     sweep(a.A, a.R, a.BG, a.iterations, a.target_block_errors, a.target_BLER, a.EsN0_start, a.EsN0_delta, a.seed, a.rv,
           a.batch, a.max_blocks, True, a.out_dir, Q_m=Q_m, llr_dtype=capi.F16X2 if a.llr_dtype == "f16x2" else capi.F32,
           algorithm=capi.ALG_BP if a.algorithm == "bp" else capi.ALG_NMS)

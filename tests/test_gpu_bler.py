@@ -161,3 +161,22 @@ def test_host_mirror_sum_product_option(O):
     with pytest.raises(capi.UnsupportedParameters):
         NRLDPCDecoder(BG=2, A=400, G=2000, algorithm="bogus").step(g_tilde)
     enc.release(); dec.release(); nms.release()
+
+
+def test_snr_vs_a_driver(tmp_path):
+    """plot_SNR_vs_A.m protocol on device: required Es/N0 per block length, the reference's "%d\\t%f" file, an unsupported
+    length skipped (the callers catch 'ldpc_3gpp_matlab:UnsupportedParameters', plot_SNR_vs_A.m:164-168)."""
+    from ldpc_3gpp_matlab_b200 import bler
+    out = bler.snr_vs_a([20, 200, 10 ** 7], [0.2], 2, iterations=8, target_block_errors=200, target_BLER=5e-2, EsN0_start=-4.0,
+                        EsN0_delta=0.5, seed=1, batch=4096, out_dir=str(tmp_path), log=lambda *_: None)
+    rows = out[0.2]
+    assert [a for a, _ in rows] == [20, 200]                  # A = 10^7 at R = 1/5 is not supported and is skipped
+    req = dict(rows)
+    assert all(np.isfinite(v) for v in req.values())
+    assert -4.0 <= req[200] < req[20] <= 4.0                   # longer blocks need less Es/N0
+    f = tmp_path / "SNR_vs_A_0.05_0.2_2_QPSK_8_200_1.txt"
+    lines = f.read_text().splitlines()
+    assert len(lines) == 2
+    for line, (a, v) in zip(lines, rows):
+        x, y = line.split("\t")
+        assert int(x) == a and abs(float(y) - v) < 1e-6

@@ -77,3 +77,14 @@ def test_cbgti_and_lbrm():
     o = nrldpc.NRLDPC(A=8424, BG=1, G=25272, Q_m=2, I_LBRM=1, TBS_LBRM=8424)
     assert o.N_ref == 12636 and o.N_cb == 12636
     assert nrldpc.NRLDPC(A=8424, BG=1, G=25272, Q_m=2, I_LBRM=1, TBS_LBRM=8424, rv_id=2).k_0 == (33 * 12636) // (66 * 384) * 384
+
+
+def test_required_snr_interpolation_follows_interp1():
+    """plot_SNR_vs_A.m:175: interp1(log10([prev_BLER, BLER]), [prev_EsN0, EsN0], log10(target_BLER))."""
+    from ldpc_3gpp_matlab_b200.bler import interp_required_snr as f
+    assert f(0.1, 0.001, 1.0, 1.5, 0.01) == pytest.approx(1.25)
+    assert f(1.0, 0.005, -2.1, -2.0, 1e-2) == pytest.approx(-2.1 + 0.1 * math.log10(1e-2) / math.log10(0.005))
+    assert f(0.03, 0.01, 0.0, 0.5, 0.01) == pytest.approx(0.5)            # the target is the last point itself
+    assert math.isnan(f(1.0, 0.0, 0.5, 1.0, 0.01))                        # a point without errors: log10(0)
+    assert math.isnan(f(None, 0.001, None, 1.0, 0.01))                    # no previous point
+    assert math.isnan(f(0.5, 0.2, 0.0, 0.5, 0.01))                        # target outside the bracket
