@@ -358,6 +358,49 @@ def test_headline_size_round_trip_properties(capi):
     h.close()
 
 
+@pytest.mark.parametrize("dtype", ["f32", "f16x2"])
+@pytest.mark.parametrize("E,n_rows,iters,esn0", [(9478, 5, 20, 6.3), (25272, 46, 8, -0.35), (16896, 24, 8, 1.7)])
+def test_full_size_parity_flag_is_exactly_the_syndrome(capi, E, n_rows, iters, esn0, dtype):
+    """BASELINE config 4 (BG1 Z=384 rate 8/9, 20 iterations with the parity-check stop, batch 4096), the headline code and a
+    rate-1/2 case with the stop, near their waterfalls so that converged and failed blocks both occur.  Size-independent
+    property of 'Parity check satisfied' (NRLDPCDecoder.m:120): parity_ok = 1 exactly when the signs of the returned
+    a-posteriori values form a codeword on the active part of H -- i.e. when re-encoding the decoded information bits
+    reproduces them (the parity bits of the active columns are uniquely determined by the active checks); blocks that
+    stop early report fewer iterations than the limit, the others exactly the limit."""
+    import torch
+    B, Z = 4096, 384
+    h = capi.Handle(1, Z, iters, True, llr_dtype=capi.F16X2 if dtype == "f16x2" else capi.F32)
+    st = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cuda").manual_seed(11)
+    info = torch.randint(0, 2, (B, h.K), dtype=torch.uint8, device="cuda", generator=g)
+    cw = torch.empty((B, h.n_cw), dtype=torch.uint8, device="cuda")
+    f = torch.empty((B, E), dtype=torch.uint8, device="cuda")
+    fl = torch.empty((B, E), dtype=torch.float32, device="cuda")
+    llr = torch.empty((B, h.n_cw), dtype=torch.float32, device="cuda")
+    hard = torch.empty((B, h.K), dtype=torch.uint8, device="cuda")
+    app = torch.empty((B, h.n_cw), dtype=torch.float32, device="cuda")
+    ok = torch.empty(B, dtype=torch.uint8, device="cuda")
+    its = torch.empty(B, dtype=torch.int32, device="cuda")
+    rm = capi.Rm(E, 0, h.N, h.K, 2)
+    h.encode_raw(info, B, cw, mem=capi.MEM_DEVICE, stream=st)
+    h.rate_match_raw(cw, B, rm, f, mem=capi.MEM_DEVICE, stream=st)
+    h.qpsk_awgn_llr_raw(f, B, E, 10 ** (-esn0 / 10), 3, 0, fl, stream=st)
+    h.rate_recover_raw(fl, B, rm, None, llr, mem=capi.MEM_DEVICE, stream=st)
+    h.decode_raw(llr, B, hard, soft=app, iters=its, ok=ok, n_rows=n_rows, mem=capi.MEM_DEVICE, stream=st)
+    recw = torch.empty_like(cw)
+    h.encode_raw(hard, B, recw, mem=capi.MEM_DEVICE, stream=st)
+    torch.cuda.synchronize()
+    n_act = (22 + n_rows) * Z
+    is_cw = ((app[:, :n_act] < 0).to(torch.uint8) == recw[:, :n_act]).all(dim=1)
+    assert torch.equal(is_cw, ok.bool())
+    assert int(ok.sum()) > 0
+    if n_rows != 24:                                               # the two BASELINE operating points: BLER about 1e-2
+        assert int(ok.sum()) < B                                   # converged and failed blocks both occur
+    assert bool((its[~ok.bool()] == iters).all()) and bool((its[ok.bool()] <= iters).all()) and bool((its >= 1).all())
+    assert bool((hard[ok.bool()] == info[ok.bool()]).all(dim=1).float().mean() > 0.99)   # undetected errors are rare
+    h.close()
+
+
 def test_small_z_high_batch_config3(capi, O):
     """BASELINE config 3 (BG2 Z=52, 104 filler, E=2000, 33 active rows, batch 65536): GPU batch equals the
     oracle on a strided sample and is idempotent (decoding twice gives the same bytes)."""
