@@ -255,9 +255,11 @@ __device__ __forceinline__ void row_gather(const Lane &l, const uint2 *__restric
     s.m1 = m1; s.m2 = m2; s.sx = sx; s.ts = ts;
 }
 
-// second half: new messages, APP write-back, the row's new record
-template <int DEG>
-__device__ __forceinline__ uint4 row_scatter(const RowState<DEG> &s, const float alpha) {
+// second half: new messages, APP write-back, the row's new record.  PAR: also XOR the new APP values into `par` -- its sign
+// bit is this check's parity on the hard decisions just written (used for the last layer of an iteration, whose decisions
+// are final: see UnrolledRows)
+template <int DEG, bool PAR>
+__device__ __forceinline__ uint4 row_scatter_par(const RowState<DEG> &s, const float alpha, uint32_t &par) {
     // both candidate magnitudes with the row's sign product folded in: multiply by alpha carrying the sign
     // (m >= 0, so the product's sign bit is sg also when m = 0: bit-identical to (alpha*m) | sg)
     const float alpha_s = __uint_as_float(bitselect(__float_as_uint(alpha), s.sx, 0x80000000u));
@@ -272,9 +274,16 @@ __device__ __forceinline__ uint4 row_scatter(const RowState<DEG> &s, const float
         const uint32_t sel = is_min ? m2ss : m1ss;
         arg = is_min ? (uint32_t)e : arg;
         const float c = __uint_as_float(sel ^ (__float_as_uint(s.t[e]) & 0x80000000u));
-        sts_f32(s.addr[e], __fadd_rn(s.t[e], c));
+        const float app = __fadd_rn(s.t[e], c);
+        if (PAR) par ^= __float_as_uint(app);
+        sts_f32(s.addr[e], app);
     }
     return make_uint4(m1ss, m2ss, arg | (s.ts << 5), 0u);
+}
+template <int DEG>
+__device__ __forceinline__ uint4 row_scatter(const RowState<DEG> &s, const float alpha) {
+    uint32_t unused = 0;
+    return row_scatter_par<DEG, false>(s, alpha, unused);
 }
 
 template <int DEG, bool IDENT_LAST, bool ONE_CW>
@@ -292,6 +301,7 @@ struct DecCtx {
     uint64_t pol;
     uint4 cur, cur2; // prefetched records of the next layer (and of its partner when the next layer is a pair)
     bool done;       // this thread does no row work (inactive lane, or its codeword has converged)
+    int last_fail;   // FULL kernels, every base row active: some check of the iteration's last layer is unsatisfied (CTA-uniform)
 };
 
 // TMA staging of a codeword group: the group's rows are contiguous in HBM, so ONE bulk asynchronous copy
@@ -562,6 +572,8 @@ struct UnrolledRows {
             // rows R and R+1 touch disjoint block columns: one layer, one barrier
             constexpr int DEG2 = BgShape<BG>::deg(PAIR ? R + 1 : R);
             constexpr int E1 = BgShape<BG>::start(PAIR ? R + 1 : R);
+            constexpr bool kLastPair = FULL && PAIR && R + 2 == BgShape<BG>::kRows;
+            uint32_t par = 0;
             if (FULL || !c.done) {
                 uint4 nxt = make_uint4(0u, 0u, 0u, 0u), nxt2 = nxt;
                 if ((R + 1 >= ld_from && R + 1 < ld_to)) {
@@ -572,8 +584,8 @@ struct UnrolledRows {
                 RowState<DEG2> s1;
                 row_gather<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur.x, c.cur.y, c.cur.z, s0);
                 row_gather<DEG2, (R >= 4), FULL>(c.l, a.ed + E1, c.cur2.x, c.cur2.y, c.cur2.z, s1);
-                const uint4 rec0 = row_scatter<DEG>(s0, a.alpha);
-                const uint4 rec1 = row_scatter<DEG2>(s1, a.alpha);
+                const uint4 rec0 = row_scatter_par<DEG, kLastPair>(s0, a.alpha, par);
+                const uint4 rec1 = row_scatter_par<DEG2, kLastPair>(s1, a.alpha, par);
                 if (store_rec) {
                     st_rec(c.my_rec, R == 0 ? a.n_rows : R, rec0, c.pol);
                     st_rec(c.my_rec, R + 1, rec1, c.pol);
@@ -581,7 +593,11 @@ struct UnrolledRows {
                 c.cur = nxt;
                 c.cur2 = nxt2;
             }
-            __syncthreads();
+            // The hard decisions written by the LAST layer of an iteration are final, so an unsatisfied check there
+            // proves that the codeword has not converged: with every base row active the layer's barrier doubles as the
+            // CTA-wide OR of those parities and the kernel skips the syndrome after most iterations (exact either way).
+            if (kLastPair) c.last_fail = __syncthreads_or((int)(par >> 31));
+            else __syncthreads();
             UnrolledRows<BG, (PAIR ? R + 2 : BgShape<BG>::kRows), FULL>::run(a, c, ld_from, ld_to, store_rec);
         } else {
             if (FULL || !c.done) {
@@ -609,6 +625,7 @@ struct UnrolledRows<BG, BgShape<BG>::kRows, FULL> {
 template <int BG, bool FULL>
 __device__ __forceinline__ void iteration_unrolled(const DecArgs &a, DecCtx &c, const int it) {
     const bool first = it == 0, last = it + 1 == a.max_iters;
+    c.last_fail = 0;   // set by the last layer when every base row is active
     UnrolledRows<BG, 0, FULL>::run(a, c, first ? a.n_rows - 1 : 0, last ? a.n_rows - 1 : a.n_rows, !last);
 }
 
@@ -681,7 +698,8 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
             if (a.early_term || (want_ok && last)) {
                 if (FULL && bitsliced) {
                     // one codeword per CTA: the verdict is CTA-uniform, no flags
-                    my_ok = syndrome_bitsliced<(BG == 0 ? 1 : BG)>(a.smem_base, (uint32_t)__cvta_generic_to_shared(bar + 1), Z, a.n_rows, tid, a.row_start) ? 0 : 1;
+                    my_ok = c.last_fail ? 0   // an unsatisfied check in the last layer: not converged, no syndrome needed
+                          : (syndrome_bitsliced<(BG == 0 ? 1 : BG)>(a.smem_base, (uint32_t)__cvta_generic_to_shared(bar + 1), Z, a.n_rows, tid, a.row_start) ? 0 : 1);
                     if (a.early_term && my_ok) break;
                 } else {
                     constexpr int B = BG == 0 ? 1 : BG;

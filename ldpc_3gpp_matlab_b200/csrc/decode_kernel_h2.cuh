@@ -185,8 +185,8 @@ __device__ __forceinline__ void row_gather_h2(const Lane &l, const uint2 *__rest
 }
 
 // second half: new messages, APP write-back, the row's new record
-template <int DEG>
-__device__ __forceinline__ uint4 row_scatter_h2(const RowStateH2<DEG> &s, const uint32_t alpha2) {
+template <int DEG, bool PAR>
+__device__ __forceinline__ uint4 row_scatter_h2_par(const RowStateH2<DEG> &s, const uint32_t alpha2, uint32_t &par) {
     constexpr int N0 = DEG < 16 ? DEG : 16;
     constexpr int N1 = DEG - N0;
     constexpr bool W3 = DEG <= 11;
@@ -206,13 +206,20 @@ __device__ __forceinline__ uint4 row_scatter_h2(const RowStateH2<DEG> &s, const 
         const uint32_t sel = bitselect(m1ss, m2ss, is_min);
         args = bitselect(args, (uint32_t)e * 0x00010001u, is_min);
         const uint32_t c = sel ^ (s.t[e] & kH2Sign);
-        sts_u32(s.addr[e], as_u32(__hadd2(as_h2(s.t[e]), as_h2(c))));
+        const uint32_t app = as_u32(__hadd2(as_h2(s.t[e]), as_h2(c)));
+        if (PAR) par ^= app;   // sign bits (15 / 31) = parities of this check on the hard decisions just written
+        sts_u32(s.addr[e], app);
     }
     constexpr uint32_t F0 = (((1u << N0) - 1u) << (16 - N0)) * 0x00010001u;
     constexpr uint32_t F1 = N1 > 0 ? (((1u << N1) - 1u) << (16 - N1)) * 0x00010001u : 0u;
     const uint32_t z = (s.s0 & F0) | (W3 ? args : 0u);
     const uint32_t w = W3 ? 0u : ((s.s1 & F1) | args);
     return make_uint4(m1ss, m2ss, z, w);
+}
+template <int DEG>
+__device__ __forceinline__ uint4 row_scatter_h2(const RowStateH2<DEG> &s, const uint32_t alpha2) {
+    uint32_t unused = 0;
+    return row_scatter_h2_par<DEG, false>(s, alpha2, unused);
 }
 
 template <int DEG, bool IDENT_LAST, bool ONE_CW>
@@ -230,6 +237,7 @@ struct DecCtxH2 {
     uint64_t pol;
     uint4 cur, cur2;   // prefetched records of the next layer (and of its partner when the next layer is a row pair)
     bool done;   // this thread does no row work (inactive lane, or both codewords of its pair are finished)
+    uint32_t last_fail;   // FULL, every base row active: bit 15 / 31 = codeword A / B has an unsatisfied check in the last layer
 };
 
 // Load one codeword pair (B may be absent: zeros) into its interleaved APP array.
@@ -306,6 +314,8 @@ struct UnrolledRowsH2 {
         if (PAIR && R + 1 < a.n_rows) {
             constexpr int DEG2 = BgShape<BG>::deg(PAIR ? R + 1 : R);
             constexpr int E1 = BgShape<BG>::start(PAIR ? R + 1 : R);
+            constexpr bool kLastPair = FULL && PAIR && R + 2 == BgShape<BG>::kRows;
+            uint32_t par = 0;
             if (FULL || !c.done) {
                 uint4 nxt = make_uint4(0u, 0u, 0u, 0u), nxt2 = nxt;
                 if ((R + 1 >= ld_from && R + 1 < ld_to)) {
@@ -316,8 +326,8 @@ struct UnrolledRowsH2 {
                 RowStateH2<DEG2> s1;
                 row_gather_h2<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur, s0);
                 row_gather_h2<DEG2, (R >= 4), FULL>(c.l, a.ed + E1, c.cur2, s1);
-                const uint4 rec0 = row_scatter_h2<DEG>(s0, a.alpha_h2);
-                const uint4 rec1 = row_scatter_h2<DEG2>(s1, a.alpha_h2);
+                const uint4 rec0 = row_scatter_h2_par<DEG, kLastPair>(s0, a.alpha_h2, par);
+                const uint4 rec1 = row_scatter_h2_par<DEG2, kLastPair>(s1, a.alpha_h2, par);
                 if (store_rec) {
                     st_rec(c.my_rec, R, rec0, c.pol);
                     st_rec(c.my_rec, R + 1, rec1, c.pol);
@@ -325,7 +335,15 @@ struct UnrolledRowsH2 {
                 c.cur = nxt;
                 c.cur2 = nxt2;
             }
-            __syncthreads();
+            // last layer of an iteration with every base row active: its hard decisions are final, the barrier doubles as
+            // the CTA-wide OR of its parities (see decode_kernel.cuh); one reduction per codeword of the pair
+            if (kLastPair) {
+                const int fa = __syncthreads_or((int)((par >> 15) & 1u));
+                const int fb = __syncthreads_or((int)(par >> 31));
+                c.last_fail = (fa ? 0x00008000u : 0u) | (fb ? 0x80000000u : 0u);
+            } else {
+                __syncthreads();
+            }
             UnrolledRowsH2<BG, (PAIR ? R + 2 : BgShape<BG>::kRows), FULL>::run(a, c, ld_from, ld_to, store_rec);
         } else {
             if (FULL || !c.done) {
@@ -420,13 +438,20 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
 
         for (int it = 0; it < a.max_iters; ++it) {
             const bool first = it == 0, last = it + 1 == a.max_iters;
+            c.last_fail = 0u;   // set by the last layer when every base row is active
             UnrolledRowsH2<BG, 0, FULL>::run(a, c, first ? a.n_rows - 1 : 0, last ? a.n_rows - 1 : a.n_rows, !last);
             if (!fin_a) it_a = it + 1;
             if (!fin_b) it_b = it + 1;
             if (a.early_term || (want_ok && last)) {
                 uint32_t fu = 0;   // bit 15: codeword A fails, bit 31: B fails
                 if (FULL && bitsliced) {
-                    fu = syndrome_bitsliced_h2<BG>(a.smem_base, h2_hard_bits(s_flag, a.cwpc), Z, a.n_rows, tid, a.row_start, !fin_a, !fin_b);
+                    // codewords with an unsatisfied check in the last layer have not converged; the syndrome runs only if
+                    // a live codeword of the pair is still undecided (it is exact for both)
+                    const uint32_t lf = c.last_fail;
+                    if ((!fin_a && !(lf & 0x00008000u)) || (!fin_b && !(lf & 0x80000000u)))
+                        fu = syndrome_bitsliced_h2<BG>(a.smem_base, h2_hard_bits(s_flag, a.cwpc), Z, a.n_rows, tid, a.row_start, !fin_a, !fin_b);
+                    else
+                        fu = 0x80008000u;
                 } else {
                     const bool staged = a.n_rows >= a.staged_min_rows;
                     int *s_flag2 = s_flag + 2 * a.cwpc;
