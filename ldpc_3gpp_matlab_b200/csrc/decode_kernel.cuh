@@ -371,6 +371,14 @@ __device__ __forceinline__ uint32_t syndrome_fail(const DecArgs &a, const DecCtx
     return fail;
 }
 
+// XOR of the a-posteriori words of check z of the LAST active base row (sign bit(s) = its parity); out of line so that the
+// layer code's register allocation does not see it
+__device__ __noinline__ uint32_t last_row_parity(const DecArgs &a, const Lane l) {
+    uint32_t par = 0;
+    for (int e = a.row_start[a.n_rows - 1]; e < a.row_start[a.n_rows]; ++e) par ^= lds_u32(edge_addr<false>(l, a.ed[e]));
+    return par;
+}
+
 __device__ __forceinline__ void store_outputs(const DecArgs &a, const float *app, long long cw0, int n_here, int ncw, int K) {
     // hard decisions, four per 32-bit store (K = kcols*Z is a multiple of 4 for every even Z; odd Z stores bytes)
     if ((K & 3) == 0 && (a.slot_stride & 3) == 0) {
@@ -698,6 +706,10 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
             if (a.early_term || (want_ok && last)) {
                 if (FULL && bitsliced) {
                     // one codeword per CTA: the verdict is CTA-uniform, no flags
+                    // trimmed row count: the last active row is only known at run time, so its Z checks (final as well) are
+                    // re-read from shared memory -- a few loads per thread and one reducing barrier
+                    if (a.n_rows < BgShape<(BG == 0 ? 1 : BG)>::kRows)
+                        c.last_fail = __syncthreads_or((int)(last_row_parity(a, c.l) >> 31));
                     my_ok = c.last_fail ? 0   // an unsatisfied check in the last layer: not converged, no syndrome needed
                           : (syndrome_bitsliced<(BG == 0 ? 1 : BG)>(a.smem_base, (uint32_t)__cvta_generic_to_shared(bar + 1), Z, a.n_rows, tid, a.row_start) ? 0 : 1);
                     if (a.early_term && my_ok) break;

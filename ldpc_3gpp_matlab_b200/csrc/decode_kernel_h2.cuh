@@ -447,6 +447,12 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
                 if (FULL && bitsliced) {
                     // codewords with an unsatisfied check in the last layer have not converged; the syndrome runs only if
                     // a live codeword of the pair is still undecided (it is exact for both)
+                    if (a.n_rows < BgShape<BG>::kRows) {   // trimmed row count: re-read the last active row (see decode_kernel.cuh)
+                        const uint32_t par = last_row_parity(a, c.l);
+                        const int fa = __syncthreads_or((int)((par >> 15) & 1u));
+                        const int fb = __syncthreads_or((int)(par >> 31));
+                        c.last_fail = (fa ? 0x00008000u : 0u) | (fb ? 0x80000000u : 0u);
+                    }
                     const uint32_t lf = c.last_fail;
                     if ((!fin_a && !(lf & 0x00008000u)) || (!fin_b && !(lf & 0x80000000u)))
                         fu = syndrome_bitsliced_h2<BG>(a.smem_base, h2_hard_bits(s_flag, a.cwpc), Z, a.n_rows, tid, a.row_start, !fin_a, !fin_b);
