@@ -13,9 +13,13 @@
 //     memory for all iterations; two CTAs fit per SM so one CTA's barriers/loads hide under the
 //     other's arithmetic;
 //   * check-to-variable messages are kept compressed (alpha*min1, alpha*min2, argmin, sign bits)
-//     as one 16-byte record per check in a per-CTA global scratch that is pinned in L2
+//     as one three-word record per check in a per-CTA global scratch that is pinned in L2
 //     (evict_last cache policy), software-prefetched one layer ahead; the first iteration reads
 //     nothing and the last writes nothing;
+//   * consecutive base rows that touch disjoint block columns run as one layer (one barrier);
+//   * 'Parity check satisfied' (the reference's stopping rule, NRLDPCDecoder.m:120): the last layer's
+//     barrier doubles as a CTA-wide OR of its (final) checks, and only when they all hold does the
+//     exact syndrome run, core rows first (bit-sliced for one codeword per CTA);
 //   * the base graph's shape (row degrees, edge order, identity extension columns) is a
 //     compile-time constant per base graph: the layer loop is fully unrolled, and the per-edge
 //     offsets / wrap thresholds are read straight from the kernel-parameter constant bank as
