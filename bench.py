@@ -41,6 +41,9 @@ WORKLOADS = {
     "bg1_z384_r13_it8et_b4096": dict(bg=1, Z=384, E=25272, n_rows=46, iters=8, early_term=1, batch=4096, esn0=-0.3, filler=0),
     # the stop armed but never taken (no block converges at -3 dB): every CTA runs 8 iterations plus 8 failing syndromes, in phase
     "bg1_z384_r13_it8et_lowsnr_b4096": dict(bg=1, Z=384, E=25272, n_rows=46, iters=8, early_term=1, batch=4096, esn0=-3.0, filler=0),
+    # four times the headline batch: how much of the stop path's cost is end-of-launch imbalance
+    "bg1_z384_r13_it8_b16384": dict(bg=1, Z=384, E=25272, n_rows=46, iters=8, early_term=0, batch=16384, esn0=-0.3, filler=0),
+    "bg1_z384_r13_it8et_b16384": dict(bg=1, Z=384, E=25272, n_rows=46, iters=8, early_term=1, batch=16384, esn0=-0.3, filler=0),
     "bg2_z52_r15_it8et_b65536": dict(bg=2, Z=52, E=2000, n_rows=33, iters=8, early_term=1, batch=65536, esn0=-2.0, filler=104),
     "bg1_z384_r89_it20et_b4096": dict(bg=1, Z=384, E=9478, n_rows=5, iters=20, early_term=1, batch=4096, esn0=6.3, filler=0),
 }
