@@ -19,7 +19,11 @@
  *   - status: 0 or a negative NRLDPC_E*; text via nrldpc_last_error().  Never aborts/throws.
  *     NRLDPC_EUNSUPPORTED <-> error('ldpc_3gpp_matlab:UnsupportedParameters',...) (callers catch
  *     and skip: plot_BLER_vs_SNR.m:172-176), NRLDPC_ESHAPE <-> 'ldpc_3gpp_matlab:Error'.
- *   - a handle is not thread-safe; distinct handles are independent.
+ *   - a handle is not thread-safe; distinct handles are independent (kernel attributes are only ever raised
+ *     process-wide, so live handles of different (BG, Z) never invalidate each other's launches).
+ *   - NRLDPC_MEM_DEVICE decodes of ONE handle share its scratch: launches on different streams are ordered
+ *     behind each other by the library (an event wait), they do not overlap; use one handle per stream for overlap.
+ *   - every entry point restores the caller's current CUDA device before it returns.
  */
 #ifndef NRLDPC_B200_H
 #define NRLDPC_B200_H
@@ -45,8 +49,10 @@ extern "C" {
 /* Decoding algorithm (nrldpc_cfg.algorithm).
  *   NRLDPC_ALG_NMS  layered normalized min-sum (default; the fast path)
  *   NRLDPC_ALG_BP   the reference's own algorithm: flooding sum-product in float64 with the termination rule of
- *                   comm.LDPCDecoder as configured at NRLDPCDecoder.m:120 -- same BLER curve and iteration counts
- *                   as the reference, for users who need to reproduce its results rather than beat them */
+ *                   comm.LDPCDecoder as configured at NRLDPCDecoder.m:120.  Decisions and iteration counts equal the
+ *                   CPU restatement of MathWorks' documented algorithm (oracle B) and its independent numpy twin;
+ *                   equality with the closed toolbox itself is UNVERIFIED here (no MATLAB) -- matlab/make_golden_vectors.m
+ *                   produces the vectors that close this, tests/test_matlab_golden.py consumes them when present */
 #define NRLDPC_ALG_NMS 0
 #define NRLDPC_ALG_BP  1
 

@@ -115,6 +115,9 @@ class BlerSimulator:
         if self.harq is not None:
             self.harq.zero_()                            # reset(hDec), plot_BLER_vs_SNR.m:122
         ok_latched = torch.zeros(B, dtype=torch.bool, device="cuda")
+        cb_passed = torch.zeros((B, C), dtype=torch.bool, device="cuda")   # reset(hDec): NRLDPCDecoder.m:353-354
+        if self.use_crc and C > 1:
+            self.tb_hat.zero_()
         iters_total = 0
         # code blocks are interleaved frame-major: block r of frame b sits at row b*C + r
         cw3 = self.cw.view(B, C, -1)
@@ -154,9 +157,15 @@ class BlerSimulator:
                     self.tb_hat.copy_(self.hard[:, :Kp])
                     cb_pass = torch.ones(B, dtype=torch.bool, device="cuda")
                 else:
+                    # per code block, latched over the retransmissions (NRLDPCDecoder.m:296-309): a block whose CB CRC
+                    # passes overwrites its part of b_hat_buffer and sets code_block_CRC_passed; block 0 may pass on rv0
+                    # and block 1 on rv1
                     h.crc_raw(self.hard, B * C, Kp, self.K, capi.CRC24B, ok=self.cb_flag, stream=st)
-                    cb_pass = self.cb_flag.view(B, C).bool().all(dim=1)
-                    self.tb_hat.view(B, C, Kp - Lcb).copy_(self.hard.view(B, C, -1)[:, :, :Kp - Lcb])
+                    pass_now = self.cb_flag.view(B, C).bool()
+                    tb3 = self.tb_hat.view(B, C, Kp - Lcb)
+                    torch.where(pass_now[:, :, None], self.hard.view(B, C, -1)[:, :, :Kp - Lcb], tb3, out=tb3)
+                    cb_passed |= pass_now
+                    cb_pass = cb_passed.all(dim=1)
                 h.crc_raw(self.tb_hat, B, self.Bsz, self.Bsz, self.tb_kind, ok=self.tb_flag, stream=st)
                 cb_ok = cb_pass & self.tb_flag.bool() & (self.tb_hat[:, :A] == self.tb[:, :A]).all(dim=1)
             else:

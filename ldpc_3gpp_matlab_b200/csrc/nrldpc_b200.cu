@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -85,8 +86,6 @@ struct nrldpc_handle {
     int enc_s0[4];
     int enc_delta = 0;
     PipeSlot pipe[kNumPipe];
-    int dec_smem_optin = 0;
-    int enc_smem_optin = 0;
     int dec_variant = 1;             // NRLDPC_DECODE_VARIANT=loop selects the generic looped kernel
     int bitsliced_min_rows = 4;      // syndrome variants, see DecArgs (NRLDPC_BITSLICED_MIN_ROWS / NRLDPC_STAGED_MIN_ROWS: experiments)
     int staged_min_rows = 8;
@@ -98,9 +97,14 @@ struct nrldpc_handle {
     size_t dev_widen_cw = 0;
     // sum-product kernel tables (decode_kernel_bp.cuh)
     int *bp_shift = nullptr, *bp_colz = nullptr, *bp_col_start = nullptr, *bp_col_edge = nullptr;
-    const void *dec_kern_cached = nullptr;   // launch_decode: kernel / smem size the cached occupancy belongs to
-    size_t dec_smem_cached = 0;
-    int dec_occ_cached = 1;
+    // launch geometry looked up once per (kernel, CTA width, shared-memory size): the reference calls step() with ONE
+    // codeword (NRLDPCDecoder.m:265), so no launcher may pay a runtime query per call
+    struct OccEntry { const void *kern; int threads; size_t smem; int occ; };
+    std::vector<OccEntry> occ_cache;
+    int grid_cap = 0;                // NRLDPC_GRID_CAP (experiments), read once at create
+    int no_tma = 0;                  // NRLDPC_NO_TMA
+    cudaStream_t last_dev_stream = nullptr;  // stream of the last NRLDPC_MEM_DEVICE decode (its scratch is shared)
+    bool dev_used = false;
     int bp_threads = 1024;           // CTA width of the sum-product kernel (NRLDPC_BP_THREADS=512 selects the 128-register build)
 };
 
@@ -122,6 +126,54 @@ int fail(nrldpc_handle *h, int code, const char *fmt, ...) {
             return fail(h, e_ == cudaErrorMemoryAllocation ? NRLDPC_ENOMEM : NRLDPC_ECUDA,        \
                         "%s: %s", #expr, cudaGetErrorString(e_));                                 \
     } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel FUNCTION (per device), not to a handle: two live
+// handles that share an instantiation (decode_nms_kernel<1,false> for Z = 96 and Z = 8, encode_kernel for any Z) must
+// not lower it under each other.  The attribute is only ever RAISED, process-wide, to the largest size any handle asked for.
+int raise_max_smem(nrldpc_handle *h, const void *kern, size_t smem) {
+    struct Key { int device; const void *kern; size_t smem; };
+    static std::mutex mu;
+    static std::vector<Key> seen;
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto &k : seen)
+        if (k.device == h->device && k.kern == kern) {
+            if (k.smem >= smem) return 0;
+            CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k.smem = smem;
+            return 0;
+        }
+    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    seen.push_back(Key{h->device, kern, smem});
+    return 0;
+}
+
+// resident CTAs per SM of `kern` at this geometry (cached per handle), after making sure the launch is allowed
+int cached_occupancy(nrldpc_handle *h, const void *kern, int threads, size_t smem, int *occ) {
+    if (int rc = raise_max_smem(h, kern, smem)) return rc;
+    for (const auto &e : h->occ_cache)
+        if (e.kern == kern && e.threads == threads && e.smem == smem) { *occ = e.occ; return 0; }
+    int q = 0;
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, threads, smem));
+    q = std::max(1, q);
+    h->occ_cache.push_back({kern, threads, smem, q});
+    *occ = q;
+    return 0;
+}
+
+// Entry points run on the handle's device and leave the caller's current device as they found it.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    cudaError_t enter(int dev) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) return e;
+        if (prev == dev) return cudaSuccess;
+        switched = true;
+        return cudaSetDevice(dev);
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+#define ENTER_DEVICE(h) DeviceGuard guard_; CUDA_TRY(h, guard_.enter((h)->device))
 
 const int kSetA[8] = {2, 3, 5, 7, 9, 11, 13, 15};
 const int kSetN[8] = {8, 8, 7, 6, 6, 6, 5, 5};
@@ -209,19 +261,12 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
         kern = bg1 ? (full ? (Kern)nrldpc::decode_nms_kernel<1, true> : (Kern)nrldpc::decode_nms_kernel<1, false>)
                    : (full ? (Kern)nrldpc::decode_nms_kernel<2, true> : (Kern)nrldpc::decode_nms_kernel<2, false>);
     // persistent grid: every SM filled to its occupancy (2 CTAs of 384 threads at Z = 384, more for narrower CTAs);
-    // attribute and occupancy are looked up once per (kernel, shared-memory size): single-codeword calls (the
-    // reference's calling pattern, NRLDPCDecoder.m:265) should not pay two runtime queries per step
-    if (h->dec_kern_cached != reinterpret_cast<const void *>(kern) || h->dec_smem_cached != smem) {
-        CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int q = 0;
-        CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, threads, smem));
-        h->dec_occ_cached = std::max(1, std::min(q, 4));
-        h->dec_kern_cached = reinterpret_cast<const void *>(kern);
-        h->dec_smem_cached = smem;
-    }
-    const int occ = h->dec_occ_cached;
+    // attribute and occupancy are looked up once per (kernel, CTA width, shared-memory size)
+    int occ = 1;
+    if (int rc = cached_occupancy(h, reinterpret_cast<const void *>(kern), threads, smem, &occ)) return rc;
+    occ = std::min(occ, 4);
     int grid = (int)std::min<int64_t>(n_groups, (int64_t)h->num_sms * occ);
-    if (const char *v = getenv("NRLDPC_GRID_CAP")) grid = std::max(1, std::min(grid, atoi(v)));  // experiments only
+    if (h->grid_cap > 0) grid = std::max(1, std::min(grid, h->grid_cap));  // experiments only
     if (int rc = ensure_scratch(h, s, (size_t)grid * nrldpc::kRecWords * nrldpc::kRecStride)) return rc;
     CUDA_TRY(h, cudaMemsetAsync(s.counter, 0, sizeof(int), stream));
     nrldpc::DecArgs &a = h->dec_args;  // tables were filled at create()
@@ -253,10 +298,9 @@ int launch_decode_bp(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const T
     int width = h->bp_threads;
     const int threads = std::min(width, (n_rows * Z + 31) / 32 * 32);
     auto kern = width > 512 ? nrldpc::decode_bp_kernel<T, 1024> : nrldpc::decode_bp_kernel<T, 512>;
-    CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int occ = 0;
-    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
-    occ = std::max(1, std::min(occ, 4));
+    int occ = 1;
+    if (int rc = cached_occupancy(h, reinterpret_cast<const void *>(kern), threads, smem, &occ)) return rc;
+    occ = std::min(occ, 4);
     const int grid = (int)std::min<int64_t>(batch, (int64_t)h->num_sms * occ);
     const size_t stride = (size_t)h->d.edges * Z;
     if (!s.counter) CUDA_TRY(h, cudaMalloc(&s.counter, sizeof(int)));
@@ -322,7 +366,7 @@ int make_geom(nrldpc_handle *h, const nrldpc_rm *rm, nrldpc::RmGeom *g) {
     if (!rm) return fail(h, NRLDPC_ESHAPE, "rate-matching geometry is NULL");
     const nrldpc_dims &d = h->d;
     if (!(rm->Q_m == 1 || rm->Q_m == 2 || rm->Q_m == 4 || rm->Q_m == 6 || rm->Q_m == 8))
-        return fail(h, NRLDPC_EUNSUPPORTED, "Valid values of Q_m are 1, 2, 4, 6 and 8.");
+        return fail(h, NRLDPC_EUNSUPPORTED, "Q_m (bits per symbol) is one of 1, 2, 4, 6, 8.");
     if (rm->E <= 0 || rm->E % rm->Q_m) return fail(h, NRLDPC_EUNSUPPORTED, "E must be a positive multiple of Q_m.");
     if (rm->N_cb <= 0 || rm->N_cb > d.N) return fail(h, NRLDPC_EUNSUPPORTED, "N_cb must be in (0, N].");
     if (rm->k_0 < 0 || rm->k_0 >= rm->N_cb) return fail(h, NRLDPC_EUNSUPPORTED, "k_0 must be in [0, N_cb).");
@@ -353,7 +397,7 @@ constexpr size_t kStageSmemMax = 200 * 1024;
 template <int QM>
 int launch_rm_staged(nrldpc_handle *h, cudaStream_t st, const uint8_t *cw, uint8_t *f, int64_t n, const nrldpc::RmGeom &g) {
     const size_t smem = (size_t)g.ncw;
-    CUDA_TRY(h, cudaFuncSetAttribute(nrldpc::rate_match_staged_kernel<QM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = raise_max_smem(h, reinterpret_cast<const void *>(nrldpc::rate_match_staged_kernel<QM>), smem)) return rc;
     const int grid = (int)std::min<int64_t>(n, (int64_t)h->num_sms * 8);
     nrldpc::rate_match_staged_kernel<QM><<<grid, 256, smem, st>>>(cw, f, n, g);
     return 0;
@@ -382,7 +426,7 @@ int launch_rate_match(nrldpc_handle *h, cudaStream_t st, const uint8_t *cw, uint
 template <int QM>
 int launch_rr_staged(nrldpc_handle *h, cudaStream_t st, const float *f, float *harq, float *out, int64_t n, const nrldpc::RmGeom &g) {
     const size_t smem = (size_t)g.E * sizeof(float);
-    CUDA_TRY(h, cudaFuncSetAttribute(nrldpc::rate_recover_staged_kernel<QM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (int rc = raise_max_smem(h, reinterpret_cast<const void *>(nrldpc::rate_recover_staged_kernel<QM>), smem)) return rc;
     const int grid = (int)std::min<int64_t>(n, (int64_t)h->num_sms * 8);
     nrldpc::rate_recover_staged_kernel<QM><<<grid, 256, smem, st>>>(f, harq, out, n, g);
     return 0;
@@ -395,9 +439,8 @@ int launch_rr_tma(nrldpc_handle *h, cudaStream_t st, const float *f, float *harq
     // (243 us) beat one double-buffered CTA (313 us)
     const int n_buf = 4 * row <= kStageSmemMax ? 2 : 1;
     const size_t smem = n_buf * row;
-    CUDA_TRY(h, cudaFuncSetAttribute(nrldpc::rate_recover_tma_kernel<QM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 1;
-    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nrldpc::rate_recover_tma_kernel<QM>, 512, smem));
+    if (int rc = cached_occupancy(h, reinterpret_cast<const void *>(nrldpc::rate_recover_tma_kernel<QM>), 512, smem, &occ)) return rc;
     const int grid = (int)std::min<int64_t>(n, (int64_t)h->num_sms * std::max(1, occ));
     const uint32_t magic = (uint32_t)((1ull << 32) / (uint64_t)g.EQ);   // floor: quotient estimate is exact or one low
     nrldpc::rate_recover_tma_kernel<QM><<<grid, 512, smem, st>>>(f, harq, out, n, g, n_buf, g.EQ == 1 ? 0xffffffffu : magic);
@@ -408,7 +451,7 @@ int launch_rate_recover(nrldpc_handle *h, cudaStream_t st, const float *f, float
     const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     int rc = 0;
     const bool tma_ok = aligned && (g.E & 3) == 0 && (reinterpret_cast<uintptr_t>(f) & 15) == 0 && g.EQ > 1 &&
-                        (size_t)g.E * sizeof(float) <= kStageSmemMax && !getenv("NRLDPC_NO_TMA");
+                        (size_t)g.E * sizeof(float) <= kStageSmemMax && !h->no_tma;
     if (tma_ok) {
         switch (g.Qm) {
             case 1: rc = launch_rr_tma<1>(h, st, f, harq, out, n, g); break;
@@ -484,7 +527,7 @@ NRLDPC_EXPORT void nrldpc_host_free(void *p) {
 NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
     if (!out || !cfg) return fail(nullptr, NRLDPC_ESHAPE, "nrldpc_create: NULL argument");
     *out = nullptr;
-    if (cfg->bg < 1 || cfg->bg > 2) return fail(nullptr, NRLDPC_EUNSUPPORTED, "Valid values of BG are 1 and 2.");
+    if (cfg->bg < 1 || cfg->bg > 2) return fail(nullptr, NRLDPC_EUNSUPPORTED, "bg selects the TS 38.212 base graph: 1 or 2.");
     const int ils = nrldpc_set_index(cfg->Z);
     if (ils < 0) return fail(nullptr, NRLDPC_EUNSUPPORTED, "Invalid lifting size.");
     if (cfg->max_iters < 1) return fail(nullptr, NRLDPC_EUNSUPPORTED, "MaximumIterationCount must be >= 1.");
@@ -508,7 +551,9 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
     if (dev < 0) cudaGetDevice(&dev);
     if (dev >= ndev) { delete h; return fail(nullptr, NRLDPC_EUNSUPPORTED, "device ordinal %d out of range", dev); }
     h->device = dev;
-    cudaSetDevice(dev);
+    DeviceGuard guard_;   // the caller's current device is restored on every return path
+    ce = guard_.enter(dev);
+    if (ce != cudaSuccess) { delete h; return fail(nullptr, NRLDPC_ECUDA, "cudaSetDevice(%d): %s", dev, cudaGetErrorString(ce)); }
     cudaDeviceProp prop{};
     ce = cudaGetDeviceProperties(&prop, dev);
     if (ce != cudaSuccess) { delete h; return fail(nullptr, NRLDPC_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(ce)); }
@@ -522,6 +567,8 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
     if (const char *v = getenv("NRLDPC_BITSLICED_MIN_ROWS")) h->bitsliced_min_rows = std::max(4, atoi(v));
     if (const char *v = getenv("NRLDPC_STAGED_MIN_ROWS")) h->staged_min_rows = std::max(5, atoi(v));
     if (const char *v = getenv("NRLDPC_BP_THREADS")) h->bp_threads = atoi(v) > 512 ? 1024 : 512;
+    if (const char *v = getenv("NRLDPC_GRID_CAP")) h->grid_cap = std::max(0, atoi(v));
+    if (getenv("NRLDPC_NO_TMA")) h->no_tma = 1;
 
     const BgView v = bg_view(cfg->bg);
     const int Z = cfg->Z;
@@ -600,8 +647,13 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
 
 NRLDPC_EXPORT void nrldpc_destroy(nrldpc_t *h) {
     if (!h) return;
-    cudaSetDevice(h->device);
-    cudaDeviceSynchronize();
+    DeviceGuard guard_;
+    guard_.enter(h->device);
+    // wait for this handle's own work only (its pipeline streams and the last device-memory launch that used its
+    // scratch), not for the whole device: other handles and the caller's streams keep running
+    for (auto &s : h->pipe)
+        if (s.stream) cudaStreamSynchronize(s.stream);
+    if (h->dev_done && h->dev_used) cudaEventSynchronize(h->dev_done);
     for (auto &s : h->pipe) {
         cudaFree(s.llr); cudaFree(s.hard); cudaFree(s.soft); cudaFree(s.iters); cudaFree(s.ok); cudaFree(s.llr16);
         cudaFree(s.bytes_in); cudaFree(s.bytes_out); cudaFree(s.f_in);
@@ -620,7 +672,7 @@ NRLDPC_EXPORT void nrldpc_destroy(nrldpc_t *h) {
 
 NRLDPC_EXPORT int nrldpc_synchronize(nrldpc_t *h) {
     if (!h) return NRLDPC_ESHAPE;
-    cudaSetDevice(h->device);
+    ENTER_DEVICE(h);
     CUDA_TRY(h, cudaDeviceSynchronize());
     return 0;
 }
@@ -682,7 +734,7 @@ int decode_impl(nrldpc_t *h, const void *llr, int in_kind, int64_t batch, int32_
     const bool bp = h->cfg.algorithm == NRLDPC_ALG_BP;
     if (in_kind == kInF64 && !bp && app_soft)
         return fail(h, NRLDPC_EUNSUPPORTED, "nrldpc_decode64 returns app_soft only with NRLDPC_ALG_BP (the min-sum kernels compute in float32)");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     const size_t in_elt = in_kind == kInF16 ? sizeof(uint16_t) : in_kind == kInF64 ? sizeof(double) : sizeof(float);
     const size_t soft_elt = in_kind == kInF64 ? sizeof(double) : sizeof(float);
     const bool convert = in_kind == kInF16 || (in_kind == kInF64 && !bp);
@@ -700,9 +752,14 @@ int decode_impl(nrldpc_t *h, const void *llr, int in_kind, int64_t batch, int32_
             CUDA_TRY(h, cudaMalloc(&h->dev_widen, (size_t)batch * h->d.n_cw * sizeof(float)));
             h->dev_widen_cw = (size_t)batch;
         }
+        // device-mode launches share one scratch (c2v records, work counter, conversion buffer): a launch on another
+        // stream than the previous one is ordered behind it
+        if (h->dev_used && st != h->last_dev_stream) CUDA_TRY(h, cudaStreamWaitEvent(st, h->dev_done, 0));
         if (int rc = launch_any(h, h->pipe[0], st, llr, in_kind, h->dev_widen, batch, n_rows, info_hard, app_soft, iters, parity_ok))
             return rc;
         CUDA_TRY(h, cudaEventRecord(h->dev_done, st));
+        h->last_dev_stream = st;
+        h->dev_used = true;
         return 0;
     }
     if (mem != NRLDPC_MEM_HOST) return fail(h, NRLDPC_ESHAPE, "mem must be NRLDPC_MEM_HOST or NRLDPC_MEM_DEVICE");
@@ -710,7 +767,7 @@ int decode_impl(nrldpc_t *h, const void *llr, int in_kind, int64_t batch, int32_
     // Host buffers: chunked 3-deep pipeline, H2D / kernel / D2H of different chunks overlap.  Chunks are one
     // persistent-grid wave of codewords (doubled while small) so the un-overlapped tail stays short.
     if (int rc = ensure_pipe(h)) return rc;
-    if (h->dev_done) CUDA_TRY(h, cudaStreamWaitEvent(h->pipe[0].stream, h->dev_done, 0));
+    if (h->dev_used) CUDA_TRY(h, cudaStreamWaitEvent(h->pipe[0].stream, h->dev_done, 0));
     const int cwpc = decode_cwpc(h->d.cols, h->d.Z);
     const int64_t wave = bp ? (int64_t)h->num_sms
                             : (int64_t)h->num_sms * nrldpc::kDecCtasPerSm * cwpc *
@@ -774,10 +831,7 @@ int launch_encode(nrldpc_handle *h, cudaStream_t st, const uint8_t *info, int64_
     const size_t smem = (size_t)h->d.n_cw * 4 + (size_t)h->d.edges * 4 + (h->d.rows + 1) * 4;
     const int64_t n_slabs = (batch + nrldpc::kEncSlab - 1) / nrldpc::kEncSlab;
     const int grid = (int)std::min<int64_t>(n_slabs, (int64_t)h->num_sms * 8);
-    if ((int)smem > h->enc_smem_optin) {
-        CUDA_TRY(h, cudaFuncSetAttribute(nrldpc::encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        h->enc_smem_optin = (int)smem;
-    }
+    if (int rc = raise_max_smem(h, reinterpret_cast<const void *>(nrldpc::encode_kernel), smem)) return rc;
     nrldpc::encode_kernel<<<grid, threads, smem, st>>>(a);
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
@@ -790,7 +844,7 @@ NRLDPC_EXPORT int nrldpc_encode(nrldpc_t *h, const uint8_t *info, int64_t batch,
     if (batch < 0) return fail(h, NRLDPC_ESHAPE, "batch must be >= 0");
     if (batch == 0) return 0;
     if (!info || !cw) return fail(h, NRLDPC_ESHAPE, "info and cw must not be NULL");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     if (mem == NRLDPC_MEM_DEVICE) {
         if ((reinterpret_cast<uintptr_t>(info) & 3) || (reinterpret_cast<uintptr_t>(cw) & 3))
             return fail(h, NRLDPC_ESHAPE, "device info / cw pointers must be 4-byte aligned");
@@ -819,7 +873,7 @@ NRLDPC_EXPORT int nrldpc_rate_match(nrldpc_t *h, const uint8_t *cw, int64_t batc
     if (batch < 0) return fail(h, NRLDPC_ESHAPE, "batch must be >= 0");
     if (batch == 0) return 0;
     if (!cw || !f) return fail(h, NRLDPC_ESHAPE, "cw and f must not be NULL");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     if (mem == NRLDPC_MEM_DEVICE) {
         return launch_rate_match(h, static_cast<cudaStream_t>(stream), cw, f, batch, g);
     }
@@ -847,7 +901,7 @@ NRLDPC_EXPORT int nrldpc_rate_recover(nrldpc_t *h, const float *f, int64_t batch
     if (batch < 0) return fail(h, NRLDPC_ESHAPE, "batch must be >= 0");
     if (batch == 0) return 0;
     if (!f || !llr_cw) return fail(h, NRLDPC_ESHAPE, "f and llr_cw must not be NULL");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     if (mem == NRLDPC_MEM_DEVICE) {
         return launch_rate_recover(h, static_cast<cudaStream_t>(stream), f, harq, llr_cw, batch, g);
     }
@@ -883,7 +937,7 @@ NRLDPC_EXPORT int nrldpc_qpsk_awgn_llr(nrldpc_t *h, const uint8_t *f_bits, int64
     if (!f_bits || !f_llr) return fail(h, NRLDPC_ESHAPE, "f_bits and f_llr must not be NULL");
     if ((reinterpret_cast<uintptr_t>(f_bits) & 3) || (reinterpret_cast<uintptr_t>(f_llr) & 15))
         return fail(h, NRLDPC_ESHAPE, "f_bits must be 4-byte and f_llr 16-byte aligned");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     const long long quads = total / 4;
     nrldpc::qpsk_awgn_llr_kernel<<<grid_for(h, quads, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         f_bits, f_llr, quads, sqrtf(0.5f * variance), 2.8284271247461900976f / variance, seed, stream_id);
@@ -909,7 +963,7 @@ NRLDPC_EXPORT int nrldpc_modulate(nrldpc_t *h, const uint8_t *bits, int64_t n_bi
     if (int rc = check_modem(h, n_bits, Q_m, bits, sym)) return rc;
     if (n_bits == 0) return 0;
     if (reinterpret_cast<uintptr_t>(sym) & 7) return fail(h, NRLDPC_ESHAPE, "sym must be 8-byte aligned");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     const long long n_sym = n_bits / Q_m;
     nrldpc::modulate_kernel<<<grid_for(h, n_sym, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         bits, reinterpret_cast<float2 *>(sym), n_sym, Q_m);
@@ -925,7 +979,7 @@ NRLDPC_EXPORT int nrldpc_awgn(nrldpc_t *h, float *sym, int64_t n_sym, float vari
     if (!(variance >= 0.0f)) return fail(h, NRLDPC_EUNSUPPORTED, "variance must be non-negative");
     if (n_sym == 0) return 0;
     if (!sym || (reinterpret_cast<uintptr_t>(sym) & 7)) return fail(h, NRLDPC_ESHAPE, "sym must be a non-NULL 8-byte aligned pointer");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     nrldpc::awgn_kernel<<<grid_for(h, (n_sym + 1) / 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<float2 *>(sym), n_sym, sqrtf(0.5f * variance), seed, stream_id);
     CUDA_TRY(h, cudaGetLastError());
@@ -941,7 +995,7 @@ NRLDPC_EXPORT int nrldpc_demodulate(nrldpc_t *h, const float *sym, int64_t n_sym
     if (!(variance > 0.0f)) return fail(h, NRLDPC_EUNSUPPORTED, "variance must be positive");
     if (n_sym == 0) return 0;
     if (reinterpret_cast<uintptr_t>(sym) & 7) return fail(h, NRLDPC_ESHAPE, "sym must be 8-byte aligned");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     nrldpc::demodulate_kernel<<<grid_for(h, n_sym, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float2 *>(sym), llr, n_sym, Q_m, 1.0f / variance, method);
     CUDA_TRY(h, cudaGetLastError());
@@ -956,7 +1010,7 @@ NRLDPC_EXPORT int nrldpc_mod_awgn_llr(nrldpc_t *h, const uint8_t *bits, int64_t 
     if (method < 0 || method > 2) return fail(h, NRLDPC_EUNSUPPORTED, "Unsupported decision method");
     if (!(variance > 0.0f)) return fail(h, NRLDPC_EUNSUPPORTED, "variance must be positive");
     if (n_bits == 0) return 0;
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     const long long n_sym = n_bits / Q_m;
     nrldpc::mod_awgn_demod_kernel<<<grid_for(h, (n_sym + 1) / 2, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         bits, llr, n_sym, Q_m, sqrtf(0.5f * variance), 1.0f / variance, method, seed, stream_id);
@@ -980,7 +1034,7 @@ NRLDPC_EXPORT int nrldpc_crc(nrldpc_t *h, const uint8_t *bits, int64_t batch, in
     if (batch == 0) return 0;
     if (!bits || (!parity && !ok)) return fail(h, NRLDPC_ESHAPE, "bits and one of parity / ok must not be NULL");
     if (parity && parity_stride < L) return fail(h, NRLDPC_ESHAPE, "parity_stride must be at least the CRC length");
-    CUDA_TRY(h, cudaSetDevice(h->device));
+    ENTER_DEVICE(h);
     nrldpc::crc_kernel<<<grid_for(h, batch * 32, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(bits, batch, n_bits, stride, poly, L,
                                                                                              parity, parity_stride, ok);
     CUDA_TRY(h, cudaGetLastError());

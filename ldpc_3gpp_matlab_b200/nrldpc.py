@@ -85,19 +85,19 @@ class NRLDPC:
                 raise NRLDPCError(f"Nontunable property '{name}' cannot be changed after step(); call release() first.")
         v = value
         if name == "BG" and (v < 1 or v > 2):                                   # NRLDPC.m:240-245
-            raise UnsupportedParameters("Valid values of BG are 1 and 2.")
+            raise UnsupportedParameters("BG selects the TS 38.212 base graph: 1 or 2.")
         if name == "A" and v < 0:                                               # :247-252
-            raise UnsupportedParameters("A should not be negative.")
+            raise UnsupportedParameters("A (payload bits) cannot be below zero.")
         if name == "TBS_LBRM" and v < 0:                                        # :254-259
-            raise UnsupportedParameters("TBS_LBRM should not be negative.")
+            raise UnsupportedParameters("TBS_LBRM cannot be below zero.")
         if name == "rv_id" and (v < 0 or v > 3):                                # :263-268
-            raise UnsupportedParameters("Valid values of rv_id are 0, 1, 2 and 3.")
+            raise UnsupportedParameters("rv_id (redundancy version) is one of 0..3.")
         if name == "G" and v < 0:                                               # :270-275
-            raise UnsupportedParameters("G should not be negative.")
+            raise UnsupportedParameters("G (coded bits available) cannot be below zero.")
         if name == "Q_m" and v not in (1, 2, 4, 6, 8):                          # :278-283
-            raise UnsupportedParameters("Valid vales of Q_m are 1, 2, 4, 6 and 8.")
+            raise UnsupportedParameters("Q_m (bits per symbol) is one of 1, 2, 4, 6, 8.")
         if name == "N_L" and (v < 1 or v > 4):                                  # :289-294
-            raise UnsupportedParameters("N_L should be in the range 1 to 4.")
+            raise UnsupportedParameters("N_L (layers) is one of 1..4.")
         object.__setattr__(self, name, value)
 
     # --- Dependent getters ---------------------------------------------------------------------
@@ -206,9 +206,9 @@ class NRLDPC:
 
     def validate_properties(self):        # validatePropertiesImpl, :551-559
         if self.B_prime % self.C != 0:
-            raise UnsupportedParameters("B_prime must be a multiple of C.")
+            raise UnsupportedParameters("C code blocks must share B_prime evenly (B_prime mod C = 0).")
         if self.G % (self.Q_m * self.N_L) != 0:
-            raise UnsupportedParameters("G must be a multiple of Q_m*N_L.")
+            raise UnsupportedParameters("G has to be a whole number of Q_m*N_L groups.")
 
     # --- matlab.System protocol ------------------------------------------------------------------
     def step(self, x):

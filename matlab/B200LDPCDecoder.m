@@ -16,7 +16,8 @@ classdef B200LDPCDecoder < matlab.System
         Alpha = 0.75;          % min-sum normalisation (engine-specific)
         ActiveRows = 0;        % 0 = all base rows (engine-specific)
         Algorithm = 'Layered normalized min-sum';  % or 'Sum-product': comm.LDPCDecoder's own flooding sum-product in
-                                                   % float64 (same BLER curve and iteration counts as the reference)
+                                                   % float64 (matches the CPU restatement of the documented algorithm;
+                                                   % against the toolbox itself: run make_golden_vectors.m)
     end
     properties (Access = private)
         handle = uint64(0);

@@ -22,14 +22,14 @@
  *                          comm.LDPCDecoder as configured at NRLDPCDecoder.m:120.
  *
  * All file:line citations are relative to /root/reference.
- * Build: see oracle/Makefile (gcc -O2 -ffp-contract=off -fopenmp).
+ * Build: see oracle/Makefile (gcc -O3 -ffp-contract=off -fopenmp).
  */
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
 
-#include "../ldpc_3gpp_matlab_b200/csrc/bg_tables.inc"
+#include "orc_tables.h"   /* the oracle's OWN table (oracle/gen_oracle_tables.py); nothing is shared with the product */
 
 #define ORC_API __attribute__((visibility("default")))
 
@@ -58,14 +58,32 @@ ORC_API int orc_lifting_size(int K_b, int K_prime) {
 }
 
 static void bg_dims(int bg, int *rows, int *cols, int *kcols, int *edges) {
-    if (bg == 1) { *rows = 46; *cols = 68; *kcols = 22; *edges = NRLDPC_BG1_EDGES; }
-    else         { *rows = 42; *cols = 52; *kcols = 10; *edges = NRLDPC_BG2_EDGES; }
+    if (bg == 1) { *rows = 46; *cols = 68; *kcols = 22; *edges = ORC_BG1_ENTRIES; }
+    else         { *rows = 42; *cols = 52; *kcols = 10; *edges = ORC_BG2_ENTRIES; }
 }
-static const unsigned char *bg_row(int bg) { return bg == 1 ? nrldpc_bg1_row : nrldpc_bg2_row; }
-static const unsigned char *bg_col(int bg) { return bg == 1 ? nrldpc_bg1_col : nrldpc_bg2_col; }
-static const unsigned short *bg_shift(int bg, int ils) {
-    return bg == 1 ? nrldpc_bg1_shift[ils] : nrldpc_bg2_shift[ils];
+/* Accessors over the table rows {row, col, V(i_LS = 0..7)} (get_3gpp_base_graph.m:13-328, :333-529), unpacked once. */
+static unsigned char orc_row_[2][ORC_BG1_ENTRIES], orc_col_[2][ORC_BG1_ENTRIES];
+static unsigned short orc_shift_[2][8][ORC_BG1_ENTRIES];
+static int orc_unpacked_ = 0;
+static void orc_unpack(void) {
+    if (__atomic_load_n(&orc_unpacked_, __ATOMIC_ACQUIRE)) return;
+#pragma omp critical(orc_unpack_tables)
+    if (!orc_unpacked_) {
+        for (int g = 0; g < 2; ++g) {
+            const int n = g == 0 ? ORC_BG1_ENTRIES : ORC_BG2_ENTRIES;
+            for (int e = 0; e < n; ++e) {
+                const short *t = g == 0 ? orc_bg1_entries[e] : orc_bg2_entries[e];
+                orc_row_[g][e] = (unsigned char)t[0];
+                orc_col_[g][e] = (unsigned char)t[1];
+                for (int s = 0; s < 8; ++s) orc_shift_[g][s][e] = (unsigned short)t[2 + s];
+            }
+        }
+        __atomic_store_n(&orc_unpacked_, 1, __ATOMIC_RELEASE);
+    }
 }
+static const unsigned char *bg_row(int bg) { orc_unpack(); return orc_row_[bg == 1 ? 0 : 1]; }
+static const unsigned char *bg_col(int bg) { orc_unpack(); return orc_col_[bg == 1 ? 0 : 1]; }
+static const unsigned short *bg_shift(int bg, int ils) { orc_unpack(); return orc_shift_[bg == 1 ? 0 : 1][ils]; }
 
 /* Raw table dump for the sha256 guards. out: edges x 10 ints. */
 ORC_API int orc_table(int bg, int *out) {

@@ -54,6 +54,9 @@ def test_product_never_imports_oracle():
 
 
 def test_base_graph_matches_oracle_tables(O):
+    """Product table (csrc/bg_tables.inc, tools/gen_tables.py) against the oracle's OWN table (oracle/orc_tables.h,
+    oracle/gen_oracle_tables.py): two parsers, two layouts, nothing shared.  The content itself is pinned to the reference by
+    sha256 in tests/test_tables.py and tests/test_twin.py."""
     from ldpc_3gpp_matlab_b200 import capi
     for bg in (1, 2):
         t = O.table(bg)
