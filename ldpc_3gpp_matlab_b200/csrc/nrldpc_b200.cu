@@ -20,6 +20,7 @@
 #include "decode_kernel.cuh"
 #include "decode_kernel_h2.cuh"
 #include "decode_kernel_bp.cuh"
+#include "host_staging.h"
 
 #define NRLDPC_EXPORT extern "C" __attribute__((visibility("default")))
 
@@ -68,6 +69,14 @@ struct PipeSlot {
     uint32_t *c2v = nullptr;    // decode scratch (one set per slot: kernels of different slots may overlap)
     int *counter = nullptr;
     size_t scratch_recs = 0;
+    // pinned host ring of the staged host path (pageable and / or float64 caller buffers, see host_staging.h)
+    unsigned char *h_in = nullptr;
+    size_t h_in_cap = 0;
+    uint8_t *h_hard = nullptr, *h_ok = nullptr;
+    int32_t *h_iters = nullptr;
+    size_t h_out_cw = 0;
+    cudaEvent_t h2d_done = nullptr;
+    int64_t pend_off = 0, pend_n = 0;   // chunk whose outputs still sit in the pinned buffers
 };
 
 }  // namespace
@@ -105,6 +114,9 @@ struct nrldpc_handle {
     int no_tma = 0;                  // NRLDPC_NO_TMA
     cudaStream_t last_dev_stream = nullptr;  // stream of the last NRLDPC_MEM_DEVICE decode (its scratch is shared)
     bool dev_used = false;
+    nrldpc::HostPool *pool = nullptr;        // worker threads of the staged host path (created on first use)
+    int host_threads = 0;
+    int no_staging = 0;                      // NRLDPC_NO_STAGING=1: hand pageable buffers to cudaMemcpyAsync as they are (A/B)
     int bp_threads = 1024;           // CTA width of the sum-product kernel (NRLDPC_BP_THREADS=512 selects the 128-register build)
 };
 
@@ -328,7 +340,38 @@ int ensure_pipe(nrldpc_handle *h) {
     for (auto &s : h->pipe) {
         if (!s.stream) CUDA_TRY(h, cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         if (!s.done) CUDA_TRY(h, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        if (!s.h2d_done) CUDA_TRY(h, cudaEventCreateWithFlags(&s.h2d_done, cudaEventDisableTiming));
     }
+    return 0;
+}
+
+// true for ordinary (pageable, unregistered) host memory: the copy engine cannot read / write it directly, the driver
+// would bounce it through its own small staging buffer on the calling thread
+bool is_pageable(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
+int ensure_host_ring(nrldpc_handle *h, PipeSlot &s, size_t in_bytes, size_t out_cw, bool want_iters, bool want_ok) {
+    if (in_bytes > s.h_in_cap) {
+        if (s.h_in) cudaFreeHost(s.h_in);
+        s.h_in = nullptr; s.h_in_cap = 0;
+        CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void **>(&s.h_in), in_bytes, cudaHostAllocDefault));
+        s.h_in_cap = in_bytes;
+    }
+    if (out_cw > s.h_out_cw) {
+        if (s.h_hard) cudaFreeHost(s.h_hard);
+        if (s.h_ok) cudaFreeHost(s.h_ok);
+        if (s.h_iters) cudaFreeHost(s.h_iters);
+        s.h_hard = s.h_ok = nullptr; s.h_iters = nullptr; s.h_out_cw = 0;
+        CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void **>(&s.h_hard), out_cw * h->d.K, cudaHostAllocDefault));
+        CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void **>(&s.h_ok), out_cw, cudaHostAllocDefault));
+        CUDA_TRY(h, cudaHostAlloc(reinterpret_cast<void **>(&s.h_iters), out_cw * sizeof(int32_t), cudaHostAllocDefault));
+        s.h_out_cw = out_cw;
+    }
+    (void)want_iters; (void)want_ok;
     return 0;
 }
 
@@ -569,6 +612,8 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
     if (const char *v = getenv("NRLDPC_BP_THREADS")) h->bp_threads = atoi(v) > 512 ? 1024 : 512;
     if (const char *v = getenv("NRLDPC_GRID_CAP")) h->grid_cap = std::max(0, atoi(v));
     if (getenv("NRLDPC_NO_TMA")) h->no_tma = 1;
+    if (getenv("NRLDPC_NO_STAGING")) h->no_staging = 1;
+    h->host_threads = nrldpc::default_host_threads();
 
     const BgView v = bg_view(cfg->bg);
     const int Z = cfg->Z;
@@ -659,9 +704,15 @@ NRLDPC_EXPORT void nrldpc_destroy(nrldpc_t *h) {
         cudaFree(s.bytes_in); cudaFree(s.bytes_out); cudaFree(s.f_in);
         cudaFree(s.c2v); cudaFree(s.counter);
         cudaFree(s.llr64); cudaFree(s.soft64); cudaFree(s.rmsg);
+        if (s.h_in) cudaFreeHost(s.h_in);
+        if (s.h_hard) cudaFreeHost(s.h_hard);
+        if (s.h_ok) cudaFreeHost(s.h_ok);
+        if (s.h_iters) cudaFreeHost(s.h_iters);
+        if (s.h2d_done) cudaEventDestroy(s.h2d_done);
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
+    delete h->pool;
     if (h->dev_done) cudaEventDestroy(h->dev_done);
     cudaFree(h->dev_widen);
     cudaFree(h->edesc);
@@ -776,28 +827,84 @@ int decode_impl(nrldpc_t *h, const void *llr, int in_kind, int64_t batch, int32_
     while (chunk * 2 * h->d.n_cw * 4 <= (int64_t)40 << 20 && chunk * 2 * kNumPipe <= batch) chunk *= 2;
     chunk = std::min<int64_t>(chunk, batch);
     for (auto &s : h->pipe)
-        if (int rc = ensure_decode_staging(h, s, (size_t)chunk, app_soft != nullptr, in_kind)) return rc;
+        if (int rc = ensure_decode_staging(h, s, (size_t)chunk, app_soft != nullptr,
+                                           (in_kind == kInF64 && !bp && !h->no_staging) ? (int)kInF32 : in_kind))
+            return rc;
     int k = 0;
     const unsigned char *llr_b = static_cast<const unsigned char *>(llr);
     unsigned char *soft_b = static_cast<unsigned char *>(app_soft);
+    // Staged path (host_staging.h): float64 LLRs for the float32 kernels are NARROWED on host threads into a pinned ring
+    // (PCIe then carries 4 bytes per LLR), pageable input of any type is copied there, and outputs bound for pageable
+    // memory leave through pinned buffers -- so every cudaMemcpyAsync below is truly asynchronous and the caller's
+    // thread prepares chunk i+1 while the copy engine and the kernel work on chunk i.
+    const bool narrow_in = in_kind == kInF64 && !bp && !h->no_staging;
+    const bool stage_in = narrow_in || (!h->no_staging && is_pageable(llr));
+    const bool stage_out = !h->no_staging && (is_pageable(info_hard) || is_pageable(iters) || is_pageable(parity_ok));
+    const size_t stage_elt = narrow_in ? sizeof(float) : in_elt;
+    const int kind_dev = narrow_in ? (int)kInF32 : in_kind;        // element type that reaches the device
+    if (stage_in || stage_out) {
+        if (!h->pool) h->pool = new (std::nothrow) nrldpc::HostPool(h->host_threads);
+        if (!h->pool) return fail(h, NRLDPC_ENOMEM, "out of host memory");
+        for (auto &s : h->pipe) {
+            if (int rc = ensure_host_ring(h, s, stage_in ? (size_t)chunk * h->d.n_cw * stage_elt : 0, stage_out ? (size_t)chunk : 0,
+                                          iters != nullptr, parity_ok != nullptr))
+                return rc;
+            s.pend_n = 0;
+        }
+    }
+    // outputs of a slot's previous chunk: pinned -> caller
+    auto drain = [&](PipeSlot &s) -> int {
+        if (!s.pend_n) return 0;
+        CUDA_TRY(h, cudaEventSynchronize(s.done));
+        const size_t nb = (size_t)s.pend_n * h->d.K;
+        uint8_t *dst = info_hard + s.pend_off * h->d.K;
+        const uint8_t *src = s.h_hard;
+        h->pool->parallel_for(nb, (size_t)1 << 20, [&](size_t b, size_t e) { memcpy(dst + b, src + b, e - b); });
+        if (iters) memcpy(iters + s.pend_off, s.h_iters, (size_t)s.pend_n * sizeof(int32_t));
+        if (parity_ok) memcpy(parity_ok + s.pend_off, s.h_ok, (size_t)s.pend_n);
+        s.pend_n = 0;
+        return 0;
+    };
     for (int64_t off = 0; off < batch; off += chunk, k = (k + 1) % kNumPipe) {
         PipeSlot &s = h->pipe[k];
         const int64_t n = std::min<int64_t>(chunk, batch - off);
-        void *d_in = in_kind == kInF16 ? static_cast<void *>(s.llr16) : in_kind == kInF64 ? static_cast<void *>(s.llr64)
-                                                                                         : static_cast<void *>(s.llr);
+        void *d_in = kind_dev == kInF16 ? static_cast<void *>(s.llr16) : kind_dev == kInF64 ? static_cast<void *>(s.llr64)
+                                                                                           : static_cast<void *>(s.llr);
         void *d_soft = !app_soft ? nullptr : in_kind == kInF64 ? static_cast<void *>(s.soft64) : static_cast<void *>(s.soft);
-        CUDA_TRY(h, cudaMemcpyAsync(d_in, llr_b + (size_t)off * h->d.n_cw * in_elt, (size_t)n * h->d.n_cw * in_elt,
-                                    cudaMemcpyHostToDevice, s.stream));
-        if (int rc = launch_any(h, s, s.stream, d_in, in_kind, s.llr, n, n_rows, s.hard, d_soft, iters ? s.iters : nullptr,
+        const unsigned char *src = llr_b + (size_t)off * h->d.n_cw * in_elt;
+        if (stage_out) { if (int rc = drain(s)) return rc; }
+        if (stage_in) {
+            CUDA_TRY(h, cudaEventSynchronize(s.h2d_done));   // the slot's previous chunk has left the pinned input buffer
+            const size_t total = (size_t)n * h->d.n_cw;
+            if (narrow_in) {
+                const double *in = reinterpret_cast<const double *>(src);
+                float *out = reinterpret_cast<float *>(s.h_in);
+                h->pool->parallel_for(total, (size_t)1 << 16, [&](size_t b, size_t e) { nrldpc::narrow_f64_to_f32(in + b, out + b, e - b); });
+            } else {
+                unsigned char *out = s.h_in;
+                h->pool->parallel_for(total * in_elt, (size_t)1 << 18, [&](size_t b, size_t e) { nrldpc::copy_stream(src + b, out + b, e - b); });
+            }
+            src = s.h_in;
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(d_in, src, (size_t)n * h->d.n_cw * stage_elt, cudaMemcpyHostToDevice, s.stream));
+        if (stage_in) CUDA_TRY(h, cudaEventRecord(s.h2d_done, s.stream));
+        if (int rc = launch_any(h, s, s.stream, d_in, kind_dev, s.llr, n, n_rows, s.hard, d_soft, iters ? s.iters : nullptr,
                                 parity_ok ? s.ok : nullptr))
             return rc;
-        CUDA_TRY(h, cudaMemcpyAsync(info_hard + off * h->d.K, s.hard, (size_t)n * h->d.K, cudaMemcpyDeviceToHost, s.stream));
+        CUDA_TRY(h, cudaMemcpyAsync(stage_out ? s.h_hard : info_hard + off * h->d.K, s.hard, (size_t)n * h->d.K, cudaMemcpyDeviceToHost, s.stream));
         if (app_soft)
             CUDA_TRY(h, cudaMemcpyAsync(soft_b + (size_t)off * h->d.n_cw * soft_elt, d_soft, (size_t)n * h->d.n_cw * soft_elt,
                                         cudaMemcpyDeviceToHost, s.stream));
-        if (iters) CUDA_TRY(h, cudaMemcpyAsync(iters + off, s.iters, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
-        if (parity_ok) CUDA_TRY(h, cudaMemcpyAsync(parity_ok + off, s.ok, (size_t)n, cudaMemcpyDeviceToHost, s.stream));
+        if (iters) CUDA_TRY(h, cudaMemcpyAsync(stage_out ? s.h_iters : iters + off, s.iters, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+        if (parity_ok) CUDA_TRY(h, cudaMemcpyAsync(stage_out ? s.h_ok : parity_ok + off, s.ok, (size_t)n, cudaMemcpyDeviceToHost, s.stream));
+        if (stage_out) {
+            CUDA_TRY(h, cudaEventRecord(s.done, s.stream));
+            s.pend_off = off; s.pend_n = n;
+        }
     }
+    if (stage_out)
+        for (int i = 0; i < kNumPipe; ++i, k = (k + 1) % kNumPipe)   // oldest pending chunk first
+            if (int rc = drain(h->pipe[k])) return rc;
     for (auto &s : h->pipe) CUDA_TRY(h, cudaStreamSynchronize(s.stream));
     return 0;
 }

@@ -1,14 +1,18 @@
 // nrldpc_mex.cpp -- thin MEX gateway over the C ABI (include/nrldpc_b200.h).
 //
-// UNVERIFIED: this image has no MATLAB and no mex.h, so this file is shipped as source only and has
-// never been compiled.  It is deliberately trivial: every behaviour lives behind the C ABI, which is
-// what the test-suite exercises.  Build (on a machine with MATLAB + CUDA):
+// Status: compiled and EXECUTED in this repository against a stub of the MEX API (tests/stubs/mex.h + mex_shim.cpp,
+// built by __graft_entry__.build()); tests/test_mex_gateway.py drives create / decode / encode / destroy through
+// mexFunction on the GPU box and checks the column-major layout, the logical packing and both error identifiers.  It has
+// not been run under a real MATLAB (none in the build image).  It is deliberately thin: every behaviour lives behind
+// the C ABI.  Build (on a machine with MATLAB + CUDA):
 //     mex -I../include nrldpc_mex.cpp -L../ldpc_3gpp_matlab_b200 -lnrldpc_b200
 //
 // Usage from MATLAB (see B200LDPCDecoder.m / B200LDPCEncoder.m):
 //     h     = nrldpc_mex('create', BG, Z, max_iters, early_term, alpha, llr_dtype, algorithm);
 //             algorithm: 0 = layered normalized min-sum (default), 1 = the reference's flooding sum-product in float64
 //     c_hat = nrldpc_mex('decode', h, cw_tilde, n_rows);   % cw_tilde: (68Z or 52Z) x batch double, +inf = filler
+//     [c_hat, num_iters, parity_ok] = nrldpc_mex('decode', ...)   % as comm.LDPCDecoder's NumIterationsOutputPort /
+//                                                                 % FinalParityChecksOutputPort (1 x batch each)
 //     cw    = nrldpc_mex('encode', h, c);                  % c: K x batch, values 0/1
 //     nrldpc_mex('destroy', h);
 // Error codes are mapped onto the reference's identifiers: NRLDPC_EUNSUPPORTED ->
@@ -34,12 +38,17 @@ static nrldpc_t *handle_of(const mxArray *a) {
     return reinterpret_cast<nrldpc_t *>(*static_cast<uint64_t *>(mxGetData(a)));
 }
 
+static void need(int nrhs, int n, const char *usage) {
+    if (nrhs < n) mexErrMsgIdAndTxt("ldpc_3gpp_matlab:Error", "usage: nrldpc_mex(%s)", usage);
+}
+
 void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     if (nrhs < 1 || !mxIsChar(prhs[0])) mexErrMsgIdAndTxt("ldpc_3gpp_matlab:Error", "first argument must be a command string");
     char cmd[32];
     mxGetString(prhs[0], cmd, sizeof(cmd));
 
     if (!strcmp(cmd, "create")) {
+        need(nrhs, 5, "'create', BG, Z, max_iters, early_term [, alpha, llr_dtype, algorithm]");
         nrldpc_cfg cfg{};
         cfg.bg = (int32_t)mxGetScalar(prhs[1]);
         cfg.Z = (int32_t)mxGetScalar(prhs[2]);
@@ -56,9 +65,12 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         return;
     }
     if (!strcmp(cmd, "destroy")) {
+        need(nrhs, 2, "'destroy', h");
         nrldpc_destroy(handle_of(prhs[1]));
         return;
     }
+    if (strcmp(cmd, "decode") && strcmp(cmd, "encode")) mexErrMsgIdAndTxt("ldpc_3gpp_matlab:Error", "unknown command '%s'", cmd);
+    need(nrhs, 3, "'decode' | 'encode', h, data [, n_rows]");
     nrldpc_t *h = handle_of(prhs[1]);
     nrldpc_dims d;
     nrldpc_get_dims(h, &d);
@@ -71,14 +83,26 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
             mexErrMsgIdAndTxt("ldpc_3gpp_matlab:Error", "cw_tilde should have %d rows.", d.n_cw);
         const int64_t batch = (int64_t)mxGetN(in);
         const int n_rows = nrhs > 3 ? (int)mxGetScalar(prhs[3]) : 0;
-        // the doubles go to the library as they are (nrldpc_decode64): the sum-product mode computes on them in
-        // float64 like comm.LDPCDecoder, the min-sum mode rounds them to float32 on the device (+inf stays +inf,
-        // NaN = filler too) -- no conversion loop on the MATLAB thread
-        std::vector<uint8_t> hard((size_t)batch * d.K);
-        check(nrldpc_decode64(h, mxGetPr(in), batch, n_rows, hard.data(), nullptr, nullptr, nullptr, NRLDPC_MEM_HOST, nullptr), h);
+        // the doubles go to the library as they are (nrldpc_decode64, ordinary pageable MATLAB memory): the sum-product
+        // mode computes on them in float64 like comm.LDPCDecoder; for the min-sum mode the library narrows them to
+        // float32 on host threads into a pinned staging ring (+inf stays +inf, NaN = filler too), so PCIe carries 4 bytes
+        // per LLR -- no conversion loop on the MATLAB thread.  The decisions are written straight into the logical matrix
+        // (mxLogical is one byte holding 0 / 1, which is what the library stores).
         plhs[0] = mxCreateLogicalMatrix(d.K, batch);  // comm.LDPCDecoder returns logical K x 1 (NRLDPCDecoder.m:265)
-        mxLogical *o = mxGetLogicals(plhs[0]);
-        for (size_t i = 0; i < hard.size(); ++i) o[i] = hard[i] != 0;
+        static_assert(sizeof(mxLogical) == 1, "mxLogical is one byte");
+        uint8_t *hard = reinterpret_cast<uint8_t *>(mxGetLogicals(plhs[0]));
+        std::vector<int32_t> iters(nlhs > 1 ? (size_t)batch : 0);
+        std::vector<uint8_t> ok(nlhs > 2 ? (size_t)batch : 0);
+        check(nrldpc_decode64(h, mxGetPr(in), batch, n_rows, hard, nullptr, nlhs > 1 ? iters.data() : nullptr,
+                              nlhs > 2 ? ok.data() : nullptr, NRLDPC_MEM_HOST, nullptr), h);
+        if (nlhs > 1) {
+            plhs[1] = mxCreateDoubleMatrix(1, batch, mxREAL);
+            for (int64_t i = 0; i < batch; ++i) mxGetPr(plhs[1])[i] = iters[i];
+        }
+        if (nlhs > 2) {
+            plhs[2] = mxCreateLogicalMatrix(1, batch);
+            for (int64_t i = 0; i < batch; ++i) mxGetLogicals(plhs[2])[i] = ok[i] != 0;
+        }
         return;
     }
     if (!strcmp(cmd, "encode")) {
@@ -95,5 +119,4 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         for (size_t i = 0; i < cw.size(); ++i) o[i] = cw[i];
         return;
     }
-    mexErrMsgIdAndTxt("ldpc_3gpp_matlab:Error", "unknown command '%s'", cmd);
 }

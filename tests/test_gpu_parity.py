@@ -647,3 +647,72 @@ def test_decode_bp_golden_vectors_on_gpu(capi, golden_decode, golden_decode_bp):
             assert (np.packbits(out["hard"], axis=1) == golden_decode_bp[f"{n}__{tag}__hard"]).all(), (n, tag)
             assert (out["iters"] == golden_decode_bp[f"{n}__{tag}__iters"]).all(), (n, tag)
             assert (out["parity_ok"] == golden_decode_bp[f"{n}__{tag}__ok"]).all(), (n, tag)
+
+
+def test_config4_sample_against_oracle(capi, O):
+    """BASELINE.json configs[3]: BG1 Z=384 rate 8/9 (E = 9478, 5 active rows), <= 20 iterations with the reference's
+    parity-check stop (NRLDPCDecoder.m:120), 256 blocks straddling the waterfall (6.25 dB: BLER ~ 1e-2; 6.0 dB: about half
+    the blocks fail and run all 20 iterations): decisions, iteration counts, parity flags and APP bit patterns equal
+    oracle A; packed-half equals oracle A16."""
+    rng = np.random.default_rng(4)
+    a = make_llr(O, 1, 384, 192, 9478, 6.25, rng)
+    b = make_llr(O, 1, 384, 64, 9478, 6.0, rng)
+    info, llr = np.concatenate([a[0], b[0]]), np.concatenate([a[1], b[1]])
+    ref = O.decode_nms(1, 384, llr, 20, early_term=True, n_rows=5)
+    assert 1 < ref["iters"].min() < ref["iters"].max() == 20          # the sample exercises early and late stops
+    h = capi.Handle(1, 384, 20, True)
+    out = h.decode(llr, n_rows=5, want_soft=True)
+    h.close()
+    assert (out["hard"] == ref["hard"]).all() and _same_bits(out["app"], ref["app"])
+    assert (out["iters"] == ref["iters"]).all() and (out["parity_ok"] == ref["parity_ok"]).all()
+    ref16 = O.decode_nms(1, 384, llr, 20, early_term=True, n_rows=5, f16=True)
+    h = capi.Handle(1, 384, 20, True, llr_dtype=capi.F16X2)
+    out = h.decode(llr, n_rows=5, want_soft=True)
+    h.close()
+    assert (out["hard"] == ref16["hard"]).all() and _same_bits(out["app"], ref16["app"])
+    assert (out["iters"] == ref16["iters"]).all() and (out["parity_ok"] == ref16["parity_ok"]).all()
+
+
+def test_live_handles_of_different_sizes_do_not_invalidate_each_other(capi, O):
+    """Two decoders / encoders alive at once whose kernels share an instantiation but need different amounts of dynamic
+    shared memory (a receiver alternating between two transport-block sizes): the kernel attribute is process-wide, so a
+    per-handle cache of it used to make the larger handle's next launch fail with cudaErrorInvalidValue."""
+    rng = np.random.default_rng(12)
+    big = [capi.Handle(1, 96, 6, False), capi.Handle(2, 176, 6, True)]
+    small = [capi.Handle(1, 8, 6, False), capi.Handle(2, 20, 6, True)]
+    data = {}
+    for h in big + small:
+        d = O.dims(h.bg, h.Z)
+        info, llr = make_llr(O, h.bg, h.Z, 5, d["N"] // 2 * 2, 1.5, rng)
+        data[id(h)] = (info, llr, O.decode_nms(h.bg, h.Z, llr, 6, early_term=(h.bg == 2)))
+    for _ in range(3):                      # alternate: large, small, large, ...
+        for hb, hs in zip(big, small):
+            for h in (hb, hs):
+                info, llr, ref = data[id(h)]
+                out = h.decode(llr)
+                assert (out["hard"] == ref["hard"]).all() and (out["iters"] == ref["iters"]).all()
+                assert (h.encode(info) == O.encode(h.bg, h.Z, info)).all()
+    for h in big + small:
+        h.close()
+
+
+@pytest.mark.parametrize("bg,Z,B", [(1, 384, 700), (2, 52, 3000), (1, 7, 1)])
+def test_decode64_pageable_host_path(capi, O, bg, Z, B):
+    """nrldpc_decode64 on ordinary (pageable) float64 memory with pageable outputs -- the call matlab/nrldpc_mex.cpp makes on
+    mxGetPr memory (NRLDPCDecoder.m:262-265): host threads narrow to float32 into the pinned ring.  Several chunks per call
+    (B above one persistent-grid wave), ragged last chunk; results equal the pinned float32 path and the oracle."""
+    rng = np.random.default_rng(B)
+    d = O.dims(bg, Z)
+    info, llr = make_llr(O, bg, Z, B, d["N"] // 2 * 2, 0.5 if bg == 1 else 1.0, rng, filler=Z if Z > 7 else 0)
+    llr64 = llr.astype(np.float64)
+    h = capi.Handle(bg, Z, 8, True)
+    a = h.decode(llr)                     # float32, numpy (pageable) buffers: staged copy
+    b = h.decode(llr64)                   # float64: staged narrowing
+    h.close()
+    n = min(B, 64)
+    ref = O.decode_nms(bg, Z, llr[:n], 8, early_term=True)
+    for r in (a, b):
+        assert (r["hard"][:n] == ref["hard"]).all() and (r["iters"][:n] == ref["iters"]).all() and (r["parity_ok"][:n] == ref["parity_ok"]).all()
+    assert (a["hard"] == b["hard"]).all() and (a["iters"] == b["iters"]).all() and (a["parity_ok"] == b["parity_ok"]).all()
+    # a payload-level property at full size: nearly every block decodes at this SNR
+    assert (a["hard"] != info).any(axis=1).mean() < 0.05
