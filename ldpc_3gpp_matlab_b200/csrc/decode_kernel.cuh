@@ -169,6 +169,16 @@ __device__ __forceinline__ void st_rec(uint32_t *p, int slot, uint4 v, uint64_t 
     st_word(p + (slot * 3 + 2) * kRecStride, v.z, pol);
 }
 
+// A-posteriori word of the degree-1 parity variable of extension row `row` for this thread's check: its channel value
+// (what shared memory holds) plus the row's latest message to it, rebuilt from the record the row wrote in the last
+// iteration (arg = 31: the degree-1 edge is the arg-min and receives alpha*min2, otherwise alpha*min1; sign = row sign
+// product ^ own sign).  Records of rows >= 1 live in slot `row`.
+__device__ __forceinline__ uint32_t ext_app(const uint32_t *my_rec, int row, uint64_t pol, uint32_t chan) {
+    const uint4 rec = ld_rec(my_rec, row, pol);
+    const uint32_t sel = ((rec.z & 31u) == 31u) ? rec.y : rec.x;
+    return __float_as_uint(__fadd_rn(__uint_as_float(chan), __uint_as_float(sel ^ (chan & 0x80000000u))));
+}
+
 // Integer multiply-add whose multiplier is the kernel parameter `one` (always 1): the compiler
 // cannot fold it, so it is emitted as IMAD, which issues on the FMA pipe -- address arithmetic
 // stays off the saturated ALU pipe.
@@ -215,8 +225,13 @@ __device__ __forceinline__ uint32_t edge_addr(const Lane &l, const uint2 d, cons
 // row's t values MSB-first above it (edge e at bit 5 + DEG-1-e): message e = (e == arg ? om2 : om1)
 // with its sign bit flipped by sign(t_e), i.e. sign(c_e) = sg ^ sign(t_e).
 // In the first iteration the record is all zeros (previous messages +0: x - (+0) = x exactly).
-// IDENT_LAST: the row's last edge is an identity circulant (extension parity column, shift 0 for
-// every lifting-size set: TS 38.212 tables) -> no wrap.
+// IDENT_LAST: the row's last edge is an identity circulant onto a DEGREE-1 variable (extension parity column: shift 0
+// for every lifting-size set and no other check touches it -- TS 38.212 tables).  Such a variable's
+// a-posteriori value is its channel value plus this check's own message, so t = app - c IS the channel value: the edge
+// enters the row with the value that sits in shared memory (never overwritten), no wrap, no message rebuild, no sign
+// record, no write-back (oracle A revision 2).  Its a-posteriori value chan + c' is formed only where it is read: the
+// last layer's parity filter, the syndrome's extension stage and the soft output (ext_app), from the row's record --
+// arg = 31 in a record means "no edge with other checks attains the minimum", i.e. the degree-1 edge is the arg-min.
 template <int DEG>
 struct RowState {
     float t[DEG];
@@ -229,6 +244,7 @@ struct RowState {
 template <int DEG, bool IDENT_LAST, bool ONE_CW>
 __device__ __forceinline__ void row_gather(const Lane &l, const uint2 *__restrict__ ed, const uint32_t om1,
                                            const uint32_t om2, const uint32_t ometa, RowState<DEG> &s) {
+    constexpr int NE = IDENT_LAST ? DEG - 1 : DEG;   // edges whose variable has other checks too
     float m1 = 0.f, m2 = 0.f;
     uint32_t sx = 0, ts = 0;
     const uint32_t oarg = ometa & 31u;
@@ -238,10 +254,13 @@ __device__ __forceinline__ void row_gather(const Lane &l, const uint2 *__restric
         const uint32_t a = edge_addr<ONE_CW>(l, d, IDENT_LAST && e == DEG - 1);
         s.addr[e] = a;
         const float x = lds_f32(a);
-        const uint32_t mag = (oarg == (uint32_t)e) ? om2 : om1;
-        // stored minimum (carries sg) with its sign bit flipped by sign(t_e) (meta bit 5 + DEG-1-e -> bit 31): one LOP3
-        const uint32_t c = mag ^ ((ometa << (26 - (DEG - 1 - e))) & 0x80000000u);
-        const float tt = __fsub_rn(x, __uint_as_float(c));
+        float tt = x;                                  // degree-1 variable: its channel value
+        if (e < NE) {
+            const uint32_t mag = (oarg == (uint32_t)e) ? om2 : om1;
+            // stored minimum (carries sg) with its sign bit flipped by sign(t_e) (meta bit 5 + NE-1-e -> bit 31): one LOP3
+            const uint32_t c = mag ^ ((ometa << (26 - (NE - 1 - e))) & 0x80000000u);
+            tt = __fsub_rn(x, __uint_as_float(c));
+        }
         s.t[e] = tt;
         const float ab = fabsf(tt);
         if (e == 0) {
@@ -254,7 +273,7 @@ __device__ __forceinline__ void row_gather(const Lane &l, const uint2 *__restric
             m1 = fminf(m1, ab);
         }
         sx ^= __float_as_uint(tt);
-        ts = __funnelshift_l(__float_as_uint(tt), ts, 1);  // ts = ts << 1 | signbit(tt)
+        if (e < NE) ts = __funnelshift_l(__float_as_uint(tt), ts, 1);  // ts = ts << 1 | signbit(tt)
     }
     s.m1 = m1; s.m2 = m2; s.sx = sx; s.ts = ts;
 }
@@ -262,17 +281,18 @@ __device__ __forceinline__ void row_gather(const Lane &l, const uint2 *__restric
 // second half: new messages, APP write-back, the row's new record.  PAR: also XOR the new APP values into `par` -- its sign
 // bit is this check's parity on the hard decisions just written (used for the last layer of an iteration, whose decisions
 // are final: see UnrolledRows)
-template <int DEG, bool PAR>
+template <int DEG, bool IDENT_LAST, bool PAR>
 __device__ __forceinline__ uint4 row_scatter_par(const RowState<DEG> &s, const float alpha, uint32_t &par) {
+    constexpr int NE = IDENT_LAST ? DEG - 1 : DEG;
     // both candidate magnitudes with the row's sign product folded in: multiply by alpha carrying the sign
     // (m >= 0, so the product's sign bit is sg also when m = 0: bit-identical to (alpha*m) | sg)
     const float alpha_s = __uint_as_float(bitselect(__float_as_uint(alpha), s.sx, 0x80000000u));
     uint32_t m1ss = __float_as_uint(__fmul_rn(alpha_s, s.m1));
     uint32_t m2ss = __float_as_uint(__fmul_rn(alpha_s, s.m2));
     asm volatile("" : "+r"(m1ss), "+r"(m2ss));  // keep the sign folded per row, not re-derived per edge
-    uint32_t arg = 0;
+    uint32_t arg = IDENT_LAST ? 31u : 0u;       // 31: none of the recorded edges attains the minimum (the degree-1 edge does)
 #pragma unroll
-    for (int e = 0; e < DEG; ++e) {
+    for (int e = 0; e < NE; ++e) {
         // the arg-min edge is found by value: on a tie min2 == min1, so every tied edge gets the same message
         const bool is_min = fabsf(s.t[e]) == s.m1;
         const uint32_t sel = is_min ? m2ss : m1ss;
@@ -282,12 +302,17 @@ __device__ __forceinline__ uint4 row_scatter_par(const RowState<DEG> &s, const f
         if (PAR) par ^= __float_as_uint(app);
         sts_f32(s.addr[e], app);
     }
+    if (PAR && IDENT_LAST) {   // the degree-1 variable's a-posteriori value takes part in the check's parity only
+        const float tp = s.t[DEG - 1];
+        const uint32_t sel = fabsf(tp) == s.m1 ? m2ss : m1ss;
+        par ^= __float_as_uint(__fadd_rn(tp, __uint_as_float(sel ^ (__float_as_uint(tp) & 0x80000000u))));
+    }
     return make_uint4(m1ss, m2ss, arg | (s.ts << 5), 0u);
 }
-template <int DEG>
+template <int DEG, bool IDENT_LAST>
 __device__ __forceinline__ uint4 row_scatter(const RowState<DEG> &s, const float alpha) {
     uint32_t unused = 0;
-    return row_scatter_par<DEG, false>(s, alpha, unused);
+    return row_scatter_par<DEG, IDENT_LAST, false>(s, alpha, unused);
 }
 
 template <int DEG, bool IDENT_LAST, bool ONE_CW>
@@ -295,7 +320,7 @@ __device__ __forceinline__ uint4 process_row(const Lane &l, const uint2 *__restr
                                              const uint32_t om2, const uint32_t ometa, const float alpha) {
     RowState<DEG> s;
     row_gather<DEG, IDENT_LAST, ONE_CW>(l, ed, om1, om2, ometa, s);
-    return row_scatter<DEG>(s, alpha);
+    return row_scatter<DEG, IDENT_LAST>(s, alpha);
 }
 
 // ---- pieces shared by all kernel variants --------------------------------------------------------
@@ -366,9 +391,12 @@ __device__ __forceinline__ uint32_t syndrome_fail(const DecArgs &a, const DecCtx
     uint32_t fail = 0;
     for (int r = r0; r < r1; ++r) {
         uint32_t par = 0;
-        for (int e = a.row_start[r]; e < a.row_start[r + 1]; ++e) {
+        const int e1 = a.row_start[r + 1];
+        for (int e = a.row_start[r]; e < e1; ++e) {
             const uint2 d = a.ed[e];
-            par ^= __float_as_uint(lds_f32(edge_addr<false>(c.l, d)));
+            uint32_t w = lds_u32(edge_addr<false>(c.l, d));
+            if (r >= 4 && e == e1 - 1) w = ext_app(c.my_rec, r, c.pol, w);   // degree-1 parity variable
+            par ^= w;
         }
         fail |= par;
     }
@@ -377,11 +405,21 @@ __device__ __forceinline__ uint32_t syndrome_fail(const DecArgs &a, const DecCtx
 
 // XOR of the a-posteriori words of check z of the LAST active base row (sign bit(s) = its parity); out of line so that the
 // layer code's register allocation does not see it
-__device__ __noinline__ uint32_t last_row_parity(const DecArgs &a, const Lane l) {
+// (EXT_APP: the float32 / packed-half routine that rebuilds the degree-1 parity variable's a-posteriori word)
+template <typename EXT_APP>
+__device__ __noinline__ uint32_t last_row_parity(const DecArgs &a, const Lane l, const uint32_t *my_rec, const uint64_t pol, EXT_APP ext) {
     uint32_t par = 0;
-    for (int e = a.row_start[a.n_rows - 1]; e < a.row_start[a.n_rows]; ++e) par ^= lds_u32(edge_addr<false>(l, a.ed[e]));
+    const int r = a.n_rows - 1, e1 = a.row_start[a.n_rows];
+    for (int e = a.row_start[r]; e < e1; ++e) {
+        uint32_t w = lds_u32(edge_addr<false>(l, a.ed[e]));
+        if (r >= 4 && e == e1 - 1) w = ext(my_rec, r, pol, w);
+        par ^= w;
+    }
     return par;
 }
+struct ExtAppF32 {
+    __device__ __forceinline__ uint32_t operator()(const uint32_t *my_rec, int row, uint64_t pol, uint32_t chan) const { return ext_app(my_rec, row, pol, chan); }
+};
 
 __device__ __forceinline__ void store_outputs(const DecArgs &a, const float *app, long long cw0, int n_here, int ncw, int K) {
     // hard decisions, four per 32-bit store (K = kcols*Z is a multiple of 4 for every even Z; odd Z stores bytes)
@@ -423,22 +461,25 @@ __device__ __forceinline__ void store_outputs(const DecArgs &a, const float *app
 // 'Parity check satisfied' (the reference's only setting, NRLDPCDecoder.m:120) this runs after EVERY iteration.
 template <int BG, int R, int REND, bool FULL>
 struct SyndromeRows {
-    static __device__ __forceinline__ uint32_t run(const DecArgs &a, const Lane &l, uint32_t fail) {
+    static __device__ __forceinline__ uint32_t run(const DecArgs &a, const Lane &l, const uint32_t *my_rec, const uint64_t pol, uint32_t fail) {
         if (R >= 4 && R >= a.n_rows) return fail;
         constexpr int DEG = BgShape<BG>::deg(R);
         constexpr int E0 = BgShape<BG>::start(R);
         uint32_t par = 0;
 #pragma unroll
-        for (int e = 0; e < DEG; ++e)
-            par ^= __float_as_uint(lds_f32(edge_addr<FULL>(l, a.ed[E0 + e], (R >= 4) && e == DEG - 1)));
+        for (int e = 0; e < DEG; ++e) {
+            uint32_t w = lds_u32(edge_addr<FULL>(l, a.ed[E0 + e], (R >= 4) && e == DEG - 1));
+            if (R >= 4 && e == DEG - 1) w = ext_app(my_rec, R, pol, w);   // degree-1 parity variable: channel value + latest message
+            par ^= w;
+        }
         fail |= par;
         asm volatile("" : "+r"(fail));   // one row's loads are consumed before the next row's are issued (register pressure)
-        return SyndromeRows<BG, R + 1, REND, FULL>::run(a, l, fail);
+        return SyndromeRows<BG, R + 1, REND, FULL>::run(a, l, my_rec, pol, fail);
     }
 };
 template <int BG, int REND, bool FULL>
 struct SyndromeRows<BG, REND, REND, FULL> {
-    static __device__ __forceinline__ uint32_t run(const DecArgs &, const Lane &, uint32_t fail) { return fail; }
+    static __device__ __forceinline__ uint32_t run(const DecArgs &, const Lane &, const uint32_t *, const uint64_t, uint32_t fail) { return fail; }
 };
 
 // Out of line on purpose: inlined into the decode kernel the 316 unrolled loads changed the register allocation of
@@ -449,11 +490,11 @@ struct SyndromeRows<BG, REND, REND, FULL> {
 // result of the full syndrome at a quarter of the loads in every iteration but a codeword's last.
 template <int BG, bool FULL>
 __device__ __noinline__ uint32_t syndrome_unrolled_core(const DecArgs &a, const Lane l) {
-    return SyndromeRows<BG, 0, 4, FULL>::run(a, l, 0u);
+    return SyndromeRows<BG, 0, 4, FULL>::run(a, l, nullptr, 0ull, 0u);
 }
 template <int BG, bool FULL>
-__device__ __noinline__ uint32_t syndrome_unrolled_ext(const DecArgs &a, const Lane l) {
-    return SyndromeRows<BG, 4, BgShape<BG>::kRows, FULL>::run(a, l, 0u);
+__device__ __noinline__ uint32_t syndrome_unrolled_ext(const DecArgs &a, const Lane l, const uint32_t *my_rec, const uint64_t pol) {
+    return SyndromeRows<BG, 4, BgShape<BG>::kRows, FULL>::run(a, l, my_rec, pol, 0u);
 }
 
 // Bit-sliced syndrome for the FULL kernels (Z a multiple of 32, one codeword per CTA).  After an iteration every warp
@@ -472,12 +513,17 @@ __device__ __noinline__ uint32_t syndrome_unrolled_ext(const DecArgs &a, const L
 // 25.4 against 21.6 Gb/s): DecArgs::bitsliced_min_rows.
 // All pointers are shared-window byte addresses (explicit LDS / STS: a generic pointer costs an address-space
 // resolution per access in an out-of-line routine).
-__device__ __forceinline__ void pack_hard_bits(uint32_t app_s, uint32_t hb_s, int Z, int col0, int col1, int z) {
+// ext_row0 >= 0: column col0 + i is the degree-1 parity column of extension row ext_row0 + i -- shared memory holds its
+// channel value, the hard decision comes from ext_app (thread z owns check z of that row: identity circulant)
+__device__ __forceinline__ void pack_hard_bits(uint32_t app_s, uint32_t hb_s, int Z, int col0, int col1, int z, int ext_row0 = -1,
+                                               const uint32_t *my_rec = nullptr, uint64_t pol = 0ull) {
     uint32_t src = app_s + (uint32_t)(col0 * Z + z) * 4u;
     uint32_t dst = hb_s + (uint32_t)(col0 * (Z >> 5) + (z >> 5)) * 4u;
 #pragma unroll 1   // code size: see syndrome_bitsliced
     for (int col = col0; col < col1; ++col, src += (uint32_t)Z * 4u, dst += (uint32_t)(Z >> 5) * 4u) {
-        const uint32_t word = __ballot_sync(0xffffffffu, lds_u32(src) >> 31);
+        uint32_t w = lds_u32(src);
+        if (ext_row0 >= 0) w = ext_app(my_rec, ext_row0 + (col - col0), pol, w);
+        const uint32_t word = __ballot_sync(0xffffffffu, w >> 31);
         if ((z & 31) == 0) sts_u32(dst, word);
     }
 }
@@ -508,7 +554,8 @@ __host__ __device__ constexpr unsigned long long core_row_starts() {
 // words behind it.  Scalars by value and the core rows' shape from BgShape: a reference to the kernel parameters would
 // be a generic pointer in this out-of-line routine (LD.E per field); only the rare extension stage reads row_start.
 template <int BG>
-__device__ __noinline__ int syndrome_bitsliced(uint32_t app_s, uint32_t hb_s, int Z, int n_rows, int z, const unsigned short *row_start) {
+__device__ __noinline__ int syndrome_bitsliced(uint32_t app_s, uint32_t hb_s, int Z, int n_rows, int z, const unsigned short *row_start,
+                                               const uint32_t *my_rec, const uint64_t pol) {
     using S = BgShape<BG>;
     const int W = Z >> 5, z0 = z & ~31, lane = z & 31;
     constexpr int kCore = S::kKcols + 4;
@@ -526,7 +573,7 @@ __device__ __noinline__ int syndrome_bitsliced(uint32_t app_s, uint32_t hb_s, in
     }
     if (__syncthreads_or(fail != 0u)) return 1;
     if (n_rows <= 4) return 0;
-    pack_hard_bits(app_s, hb_s, Z, kCore, min(S::kCols, S::kKcols + n_rows), z);
+    pack_hard_bits(app_s, hb_s, Z, kCore, min(S::kCols, S::kKcols + n_rows), z, 4, my_rec, pol);
     __syncthreads();
     for (int r = 4 + lane; r < n_rows; r += 32) {
         uint32_t acc = 0;
@@ -537,8 +584,8 @@ __device__ __noinline__ int syndrome_bitsliced(uint32_t app_s, uint32_t hb_s, in
 }
 
 // ---- one full iteration over the layers: looped (generic) --------------------------------------
-__device__ __forceinline__ void iteration_looped(const DecArgs &a, DecCtx &c, const int it) {
-    const bool store_rec = it + 1 < a.max_iters;
+__device__ __forceinline__ void iteration_looped(const DecArgs &a, DecCtx &c, const int it, const bool keep_last) {
+    const bool store_rec = it + 1 < a.max_iters || keep_last;
     for (int r = 0; r < a.n_rows; ++r) {
         // software prefetch of the next layer's record
         const bool ld = (r + 1 == a.n_rows) ? store_rec : (it > 0);
@@ -549,12 +596,14 @@ __device__ __forceinline__ void iteration_looped(const DecArgs &a, DecCtx &c, co
             const int deg = a.row_start[r + 1] - e0;
             const uint2 *ed = a.ed + e0;
             uint4 rec = make_uint4(0u, 0u, 0u, 0u);
-            switch (deg) {
-#define NRLDPC_ROW_CASE(D) case D: rec = process_row<D, false, false>(c.l, ed, c.cur.x, c.cur.y, c.cur.z, a.alpha); break;
+            // extension rows (r >= 4) end in their degree-1 identity column (checked at nrldpc_create)
+            switch (r >= 4 ? deg + 32 : deg) {
+#define NRLDPC_ROW_CASE(D) case D: rec = process_row<D, false, false>(c.l, ed, c.cur.x, c.cur.y, c.cur.z, a.alpha); break; \
+                           case D + 32: rec = process_row<D, true, false>(c.l, ed, c.cur.x, c.cur.y, c.cur.z, a.alpha); break;
                 NRLDPC_ROW_CASE(3) NRLDPC_ROW_CASE(4) NRLDPC_ROW_CASE(5) NRLDPC_ROW_CASE(6)
                 NRLDPC_ROW_CASE(7) NRLDPC_ROW_CASE(8) NRLDPC_ROW_CASE(9) NRLDPC_ROW_CASE(10)
-                NRLDPC_ROW_CASE(19)
 #undef NRLDPC_ROW_CASE
+                case 19: rec = process_row<19, false, false>(c.l, ed, c.cur.x, c.cur.y, c.cur.z, a.alpha); break;
                 default: break;
             }
             if (store_rec) st_rec(c.my_rec, r == 0 ? a.n_rows : r, rec, c.pol);
@@ -596,8 +645,8 @@ struct UnrolledRows {
                 RowState<DEG2> s1;
                 row_gather<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur.x, c.cur.y, c.cur.z, s0);
                 row_gather<DEG2, (R >= 4), FULL>(c.l, a.ed + E1, c.cur2.x, c.cur2.y, c.cur2.z, s1);
-                const uint4 rec0 = row_scatter_par<DEG, kLastPair>(s0, a.alpha, par);
-                const uint4 rec1 = row_scatter_par<DEG2, kLastPair>(s1, a.alpha, par);
+                const uint4 rec0 = row_scatter_par<DEG, (R >= 4), kLastPair>(s0, a.alpha, par);
+                const uint4 rec1 = row_scatter_par<DEG2, (R >= 4), kLastPair>(s1, a.alpha, par);
                 if (store_rec) {
                     st_rec(c.my_rec, R == 0 ? a.n_rows : R, rec0, c.pol);
                     st_rec(c.my_rec, R + 1, rec1, c.pol);
@@ -635,10 +684,12 @@ struct UnrolledRows<BG, BgShape<BG>::kRows, FULL> {
 };
 
 template <int BG, bool FULL>
-__device__ __forceinline__ void iteration_unrolled(const DecArgs &a, DecCtx &c, const int it) {
+__device__ __forceinline__ void iteration_unrolled(const DecArgs &a, DecCtx &c, const int it, const bool keep_last) {
     const bool first = it == 0, last = it + 1 == a.max_iters;
     c.last_fail = 0;   // set by the last layer when every base row is active
-    UnrolledRows<BG, 0, FULL>::run(a, c, first ? a.n_rows - 1 : 0, last ? a.n_rows - 1 : a.n_rows, !last);
+    // keep_last: the records of the final iteration are written too (they hold the messages to the degree-1 parity
+    // variables, from which the syndrome and the soft output rebuild those variables' a-posteriori values)
+    UnrolledRows<BG, 0, FULL>::run(a, c, first ? a.n_rows - 1 : 0, last ? a.n_rows - 1 : a.n_rows, !last || keep_last);
 }
 
 // BG = 0: generic looped variant; BG = 1 / 2: layer loop unrolled for that base graph.
@@ -672,6 +723,8 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
     const bool lane_ok = tid < a.cwpc * Z;
     const long long n_groups = (a.batch + a.cwpc - 1) / a.cwpc;
     const bool want_ok = a.ok != nullptr;
+    // the final iteration's records are needed whenever somebody reads the degree-1 parity variables afterwards
+    const bool keep_last = a.early_term || want_ok || a.soft != nullptr;
 
     DecCtx c;
     c.l.zoff = (uint32_t)z * 4u;
@@ -702,8 +755,8 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
         int my_ok = 0;
 
         for (int it = 0; it < a.max_iters; ++it) {
-            if (BG == 0) iteration_looped(a, c, it);
-            else iteration_unrolled<(BG == 0 ? 1 : BG), FULL>(a, c, it);
+            if (BG == 0) iteration_looped(a, c, it, keep_last);
+            else iteration_unrolled<(BG == 0 ? 1 : BG), FULL>(a, c, it, keep_last);
 
             if (!c.done) my_iters = it + 1;
             const bool last = it + 1 == a.max_iters;
@@ -713,9 +766,10 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
                     // trimmed row count: the last active row is only known at run time, so its Z checks (final as well) are
                     // re-read from shared memory -- a few loads per thread and one reducing barrier
                     if (a.n_rows < BgShape<(BG == 0 ? 1 : BG)>::kRows)
-                        c.last_fail = __syncthreads_or((int)(last_row_parity(a, c.l) >> 31));
+                        c.last_fail = __syncthreads_or((int)(last_row_parity(a, c.l, c.my_rec, c.pol, ExtAppF32()) >> 31));
                     my_ok = c.last_fail ? 0   // an unsatisfied check in the last layer: not converged, no syndrome needed
-                          : (syndrome_bitsliced<(BG == 0 ? 1 : BG)>(a.smem_base, (uint32_t)__cvta_generic_to_shared(bar + 1), Z, a.n_rows, tid, a.row_start) ? 0 : 1);
+                          : (syndrome_bitsliced<(BG == 0 ? 1 : BG)>(a.smem_base, (uint32_t)__cvta_generic_to_shared(bar + 1), Z, a.n_rows, tid, a.row_start,
+                                                                     c.my_rec, c.pol) ? 0 : 1);
                     if (a.early_term && my_ok) break;
                 } else {
                     constexpr int B = BG == 0 ? 1 : BG;
@@ -723,14 +777,14 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
                     const bool staged = a.n_rows >= a.staged_min_rows;
                     if (!c.done) {
                         uint32_t f = BG == 0 ? syndrome_fail(a, c, 0, 4) : syndrome_unrolled_core<B, FULL>(a, c.l);
-                        if (!staged) f |= BG == 0 ? syndrome_fail(a, c, 4, a.n_rows) : syndrome_unrolled_ext<B, FULL>(a, c.l);
+                        if (!staged) f |= BG == 0 ? syndrome_fail(a, c, 4, a.n_rows) : syndrome_unrolled_ext<B, FULL>(a, c.l, c.my_rec, c.pol);
                         if (f >> 31) s_flag[slot] = 1;
                     }
                     if (staged) {
                         // extension rows only for codewords whose core checks all hold
                         __syncthreads();
                         if (!c.done && !s_flag[slot]) {
-                            const uint32_t f = BG == 0 ? syndrome_fail(a, c, 4, a.n_rows) : syndrome_unrolled_ext<B, FULL>(a, c.l);
+                            const uint32_t f = BG == 0 ? syndrome_fail(a, c, 4, a.n_rows) : syndrome_unrolled_ext<B, FULL>(a, c.l, c.my_rec, c.pol);
                             if (f >> 31) s_flag2[slot] = 1;
                         }
                     }
@@ -747,6 +801,18 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
         }
         __syncthreads();
 
+        if (a.soft != nullptr) {
+            // soft output: the degree-1 parity variables of the active extension rows get their a-posteriori value
+            // (channel value + the row's last message) written into shared memory now that decoding is over
+            if (active) {
+                const uint32_t base = a.smem_base + c.l.slot_off + c.l.zoff + (uint32_t)((a.kcols + 4) * Z) * 4u;
+                for (int r = 4; r < a.n_rows; ++r) {
+                    const uint32_t addr = base + (uint32_t)((r - 4) * Z) * 4u;
+                    sts_u32(addr, ext_app(c.my_rec, r, c.pol, lds_u32(addr)));
+                }
+            }
+            __syncthreads();
+        }
         store_outputs(a, app, cw0, n_here, ncw, K);
         if (active && z == 0) {
             if (a.iters) a.iters[cw0 + slot] = my_iters;

@@ -31,45 +31,65 @@ __device__ __forceinline__ uint32_t as_u32(__half2 h) { return *reinterpret_cast
 
 __device__ __forceinline__ float clamp_llr_h2(float x) { return __fadd_rn(fmaxf(fminf(x, kH2LlrMax), -kH2LlrMax), 0.0f); }
 
+// Packed-half twin of ext_app (decode_kernel.cuh): a-posteriori word {A, B} of the degree-1 parity variable of extension
+// row `row` = channel values + the row's latest messages, rebuilt from the row's record (three-word records: every
+// extension row has degree <= 11).  Arg-min index 15 in a half = "the degree-1 edge is the arg-min" for that codeword.
+__device__ __forceinline__ uint32_t ext_app_h2(const uint32_t *my_rec, int row, uint64_t pol, uint32_t chan) {
+    const uint4 rec = ld_rec(my_rec, row, pol);
+    const uint32_t is_p = __heq2_mask(as_h2(rec.z & 0x000f000fu), as_h2(0x000f000fu));
+    const uint32_t sel = bitselect(rec.x, rec.y, is_p);
+    return as_u32(__hadd2(as_h2(chan), as_h2(sel ^ (chan & kH2Sign))));
+}
+struct ExtAppH2 {
+    __device__ __forceinline__ uint32_t operator()(const uint32_t *my_rec, int row, uint64_t pol, uint32_t chan) const { return ext_app_h2(my_rec, row, pol, chan); }
+};
+
 // One check row of degree DEG for check z of a codeword pair.  Record layout (uint4; three words
 // when DEG <= 11, i.e. every layer but the four degree-19 ones of base graph 1):
 //   x, y : alpha*min1, alpha*min2 of both codewords (packed fp16) with the row's sign product in their sign bits
-//   z    : sign bits of the row's t values (message sign = row sign ^ sign(t_e)) on edges 0..min(DEG,16)-1: edge e at bit 15-(n0-1-e) of each half;
-//          DEG <= 11: also the arg-min edge index of each codeword in bits 0..3 / 16..19
+//   z    : sign bits of the row's t values (message sign = row sign ^ sign(t_e)) on edges 0..min(NE,16)-1: edge e at bit 15-(n0-1-e) of each half
+//          (NE = DEG, or DEG - 1 for an extension row: its degree-1 edge keeps no record, see decode_kernel.cuh);
+//          DEG <= 11: also the arg-min edge index of each codeword in bits 0..3 / 16..19 (15: the degree-1 edge)
 //   w    : DEG > 11 only: arg-min edge indices in bits 0..4 / 16..20 and, for DEG > 16, the sign bits of
 //          edges 16..DEG-1 at the top of each half
 // Arg-min indices are compared as fp16 bit patterns (HSET2 without flush-to-zero).
 // syndrome with the base graph's shape known at compile time (see SyndromeRows in decode_kernel.cuh)
 template <int BG, int R, int REND, bool FULL>
 struct SyndromeRowsH2 {
-    static __device__ __forceinline__ uint32_t run(const DecArgs &a, const Lane &l, uint32_t fail) {
+    static __device__ __forceinline__ uint32_t run(const DecArgs &a, const Lane &l, const uint32_t *my_rec, const uint64_t pol, uint32_t fail) {
         if (R >= 4 && R >= a.n_rows) return fail;
         constexpr int DEG = BgShape<BG>::deg(R);
         constexpr int E0 = BgShape<BG>::start(R);
         uint32_t par = 0;
 #pragma unroll
-        for (int e = 0; e < DEG; ++e) par ^= lds_u32(edge_addr<FULL>(l, a.ed[E0 + e], (R >= 4) && e == DEG - 1));
+        for (int e = 0; e < DEG; ++e) {
+            uint32_t w = lds_u32(edge_addr<FULL>(l, a.ed[E0 + e], (R >= 4) && e == DEG - 1));
+            if (R >= 4 && e == DEG - 1) w = ext_app_h2(my_rec, R, pol, w);   // degree-1 parity variable
+            par ^= w;
+        }
         fail |= par;
         asm volatile("" : "+r"(fail));   // one row's loads are consumed before the next row's are issued (register pressure)
-        return SyndromeRowsH2<BG, R + 1, REND, FULL>::run(a, l, fail);
+        return SyndromeRowsH2<BG, R + 1, REND, FULL>::run(a, l, my_rec, pol, fail);
     }
 };
 template <int BG, int REND, bool FULL>
 struct SyndromeRowsH2<BG, REND, REND, FULL> {
-    static __device__ __forceinline__ uint32_t run(const DecArgs &, const Lane &, uint32_t fail) { return fail; }
+    static __device__ __forceinline__ uint32_t run(const DecArgs &, const Lane &, const uint32_t *, const uint64_t, uint32_t fail) { return fail; }
 };
 
 // Bit-sliced, two-stage syndrome of a codeword pair (see syndrome_bitsliced in decode_kernel.cuh): the hard
 // decisions of codeword A (bit 15 of every word) and B (bit 31) are packed into hb[0][col][Z/32] and hb[1][col][Z/32].
 // All pointers are shared-window byte addresses (explicit LDS / STS: a generic pointer costs an address-space
 // resolution per access in an out-of-line routine).
-__device__ __forceinline__ void pack_hard_bits_h2(uint32_t app_s, uint32_t hb_s, int Z, int col0, int col1, int n_cols_all, int z) {
+__device__ __forceinline__ void pack_hard_bits_h2(uint32_t app_s, uint32_t hb_s, int Z, int col0, int col1, int n_cols_all, int z,
+                                                  int ext_row0 = -1, const uint32_t *my_rec = nullptr, uint64_t pol = 0ull) {
     const uint32_t plane = (uint32_t)n_cols_all * (uint32_t)(Z >> 5) * 4u;
     uint32_t src = app_s + (uint32_t)(col0 * Z + z) * 4u;
     uint32_t dst = hb_s + (uint32_t)(col0 * (Z >> 5) + (z >> 5)) * 4u;
 #pragma unroll 1
     for (int col = col0; col < col1; ++col, src += (uint32_t)Z * 4u, dst += (uint32_t)(Z >> 5) * 4u) {
-        const uint32_t x = lds_u32(src);
+        uint32_t x = lds_u32(src);
+        if (ext_row0 >= 0) x = ext_app_h2(my_rec, ext_row0 + (col - col0), pol, x);   // degree-1 parity column (see pack_hard_bits)
         const uint32_t wa = __ballot_sync(0xffffffffu, (x >> 15) & 1u);
         const uint32_t wb = __ballot_sync(0xffffffffu, x >> 31);
         if ((z & 31) == 0) {
@@ -83,7 +103,7 @@ __device__ __forceinline__ void pack_hard_bits_h2(uint32_t app_s, uint32_t hb_s,
 // codeword passed the core stage.  Contains barriers: every thread of the CTA calls it.
 template <int BG>
 __device__ __noinline__ uint32_t syndrome_bitsliced_h2(uint32_t app_s, uint32_t hb_s, int Z, int n_rows, int z, const unsigned short *row_start,
-                                                       bool live_a, bool live_b) {
+                                                       bool live_a, bool live_b, const uint32_t *my_rec, const uint64_t pol) {
     using S = BgShape<BG>;
     const int W = Z >> 5, z0 = z & ~31, lane = z & 31;
     constexpr int kCore = S::kKcols + 4;
@@ -109,7 +129,7 @@ __device__ __noinline__ uint32_t syndrome_bitsliced_h2(uint32_t app_s, uint32_t 
     if (__syncthreads_or(fb != 0u)) f |= 0x80000000u;
     const bool need_ext = (live_a && !(f & 0x00008000u)) || (live_b && !(f & 0x80000000u));
     if (!need_ext || n_rows <= 4) return f;
-    pack_hard_bits_h2(app_s, hb_s, Z, kCore, min(S::kCols, S::kKcols + n_rows), S::kCols, z);
+    pack_hard_bits_h2(app_s, hb_s, Z, kCore, min(S::kCols, S::kKcols + n_rows), S::kCols, z, 4, my_rec, pol);
     __syncthreads();
     fa = 0; fb = 0;
     for (int r = 4 + lane; r < n_rows; r += 32) {
@@ -130,11 +150,11 @@ __device__ __noinline__ uint32_t syndrome_bitsliced_h2(uint32_t app_s, uint32_t 
 // out of line, two stages: see syndrome_unrolled_core / _ext in decode_kernel.cuh
 template <int BG, bool FULL>
 __device__ __noinline__ uint32_t syndrome_unrolled_core_h2(const DecArgs &a, const Lane l) {
-    return SyndromeRowsH2<BG, 0, 4, FULL>::run(a, l, 0u);
+    return SyndromeRowsH2<BG, 0, 4, FULL>::run(a, l, nullptr, 0ull, 0u);
 }
 template <int BG, bool FULL>
-__device__ __noinline__ uint32_t syndrome_unrolled_ext_h2(const DecArgs &a, const Lane l) {
-    return SyndromeRowsH2<BG, 4, BgShape<BG>::kRows, FULL>::run(a, l, 0u);
+__device__ __noinline__ uint32_t syndrome_unrolled_ext_h2(const DecArgs &a, const Lane l, const uint32_t *my_rec, const uint64_t pol) {
+    return SyndromeRowsH2<BG, 4, BgShape<BG>::kRows, FULL>::run(a, l, my_rec, pol, 0u);
 }
 
 template <int DEG>
@@ -148,7 +168,8 @@ struct RowStateH2 {
 // first half of a row update (see row_gather in decode_kernel.cuh)
 template <int DEG, bool IDENT_LAST, bool ONE_CW>
 __device__ __forceinline__ void row_gather_h2(const Lane &l, const uint2 *__restrict__ ed, const uint4 rec, RowStateH2<DEG> &s) {
-    constexpr int N0 = DEG < 16 ? DEG : 16;
+    constexpr int NE = IDENT_LAST ? DEG - 1 : DEG;   // edges whose variable has other checks too (recorded edges)
+    constexpr int N0 = NE < 16 ? NE : 16;
     __half2 m1 = as_h2(0u), m2 = as_h2(0u);
     uint32_t sx = 0, s0 = 0, s1 = 0;
     constexpr bool W3 = DEG <= 11;   // three-word record
@@ -159,12 +180,15 @@ __device__ __forceinline__ void row_gather_h2(const Lane &l, const uint2 *__rest
         const uint32_t a = edge_addr<ONE_CW>(l, d, IDENT_LAST && e == DEG - 1);
         s.addr[e] = a;
         const uint32_t x = lds_u32(a);
-        const uint32_t e2 = (uint32_t)e * 0x00010001u;
-        const uint32_t is_arg = __heq2_mask(as_h2(oargs), as_h2(e2));
-        const uint32_t mag = bitselect(rec.x, rec.y, is_arg);
-        const uint32_t sw = e < 16 ? rec.z << (N0 - 1 - e) : rec.w << (DEG - 1 - e);
-        const uint32_t c = mag ^ (sw & kH2Sign);
-        const __half2 tt = __hsub2(as_h2(x), as_h2(c));
+        __half2 tt = as_h2(x);                       // degree-1 variable: its channel value
+        if (e < NE) {
+            const uint32_t e2 = (uint32_t)e * 0x00010001u;
+            const uint32_t is_arg = __heq2_mask(as_h2(oargs), as_h2(e2));
+            const uint32_t mag = bitselect(rec.x, rec.y, is_arg);
+            const uint32_t sw = e < 16 ? rec.z << (N0 - 1 - e) : rec.w << (NE - 1 - e);
+            const uint32_t c = mag ^ (sw & kH2Sign);
+            tt = __hsub2(as_h2(x), as_h2(c));
+        }
         s.t[e] = as_u32(tt);
         const __half2 ab = __habs2(tt);
         if (e == 0) {
@@ -178,18 +202,22 @@ __device__ __forceinline__ void row_gather_h2(const Lane &l, const uint2 *__rest
         }
         sx ^= as_u32(tt);
         // (a shift on the ALU pipe: the FMA-pipe alternative mul.hi(s, 2^31) was measured 4 % slower)
-        if (e < 16) s0 = bitselect(s0 >> 1, as_u32(tt), kH2Sign);
-        else s1 = bitselect(s1 >> 1, as_u32(tt), kH2Sign);
+        if (e < NE) {
+            if (e < 16) s0 = bitselect(s0 >> 1, as_u32(tt), kH2Sign);
+            else s1 = bitselect(s1 >> 1, as_u32(tt), kH2Sign);
+        }
     }
     s.m1 = m1; s.m2 = m2; s.sx = sx; s.s0 = s0; s.s1 = s1;
 }
 
 // second half: new messages, APP write-back, the row's new record
-template <int DEG, bool PAR>
+template <int DEG, bool IDENT_LAST, bool PAR>
 __device__ __forceinline__ uint4 row_scatter_h2_par(const RowStateH2<DEG> &s, const uint32_t alpha2, uint32_t &par) {
-    constexpr int N0 = DEG < 16 ? DEG : 16;
-    constexpr int N1 = DEG - N0;
+    constexpr int NE = IDENT_LAST ? DEG - 1 : DEG;
+    constexpr int N0 = NE < 16 ? NE : 16;
+    constexpr int N1 = NE - N0;
     constexpr bool W3 = DEG <= 11;
+    static_assert(!IDENT_LAST || W3, "extension rows have three-word records");
     const __half2 m1raw = s.m1;
     const __half2 m1 = __hmin2(s.m1, as_h2(kH2MsgCap));
     const __half2 m2 = __hmin2(s.m2, as_h2(kH2MsgCap));
@@ -198,9 +226,9 @@ __device__ __forceinline__ uint4 row_scatter_h2_par(const RowStateH2<DEG> &s, co
     uint32_t m1ss = as_u32(__hmul2(as_h2(alpha_s), m1));
     uint32_t m2ss = as_u32(__hmul2(as_h2(alpha_s), m2));
     asm volatile("" : "+r"(m1ss), "+r"(m2ss));
-    uint32_t args = 0;
+    uint32_t args = IDENT_LAST ? 0x000f000fu : 0u;   // 15: no recorded edge attains the minimum (the degree-1 edge does)
 #pragma unroll
-    for (int e = 0; e < DEG; ++e) {
+    for (int e = 0; e < NE; ++e) {
         // arg-min edges found by value (ties: min2 == min1, every tied edge gets the same message)
         const uint32_t is_min = __heq2_mask(__habs2(as_h2(s.t[e])), m1raw);
         const uint32_t sel = bitselect(m1ss, m2ss, is_min);
@@ -210,16 +238,21 @@ __device__ __forceinline__ uint4 row_scatter_h2_par(const RowStateH2<DEG> &s, co
         if (PAR) par ^= app;   // sign bits (15 / 31) = parities of this check on the hard decisions just written
         sts_u32(s.addr[e], app);
     }
+    if (PAR && IDENT_LAST) {   // the degree-1 variable's a-posteriori value takes part in the check's parity only
+        const uint32_t tp = s.t[DEG - 1];
+        const uint32_t sel = bitselect(m1ss, m2ss, __heq2_mask(__habs2(as_h2(tp)), m1raw));
+        par ^= as_u32(__hadd2(as_h2(tp), as_h2(sel ^ (tp & kH2Sign))));
+    }
     constexpr uint32_t F0 = (((1u << N0) - 1u) << (16 - N0)) * 0x00010001u;
     constexpr uint32_t F1 = N1 > 0 ? (((1u << N1) - 1u) << (16 - N1)) * 0x00010001u : 0u;
     const uint32_t z = (s.s0 & F0) | (W3 ? args : 0u);
     const uint32_t w = W3 ? 0u : ((s.s1 & F1) | args);
     return make_uint4(m1ss, m2ss, z, w);
 }
-template <int DEG>
+template <int DEG, bool IDENT_LAST>
 __device__ __forceinline__ uint4 row_scatter_h2(const RowStateH2<DEG> &s, const uint32_t alpha2) {
     uint32_t unused = 0;
-    return row_scatter_h2_par<DEG, false>(s, alpha2, unused);
+    return row_scatter_h2_par<DEG, IDENT_LAST, false>(s, alpha2, unused);
 }
 
 template <int DEG, bool IDENT_LAST, bool ONE_CW>
@@ -227,7 +260,7 @@ __device__ __forceinline__ uint4 process_row_h2(const Lane &l, const uint2 *__re
                                                 const uint32_t alpha2) {
     RowStateH2<DEG> s;
     row_gather_h2<DEG, IDENT_LAST, ONE_CW>(l, ed, rec, s);
-    return row_scatter_h2<DEG>(s, alpha2);
+    return row_scatter_h2<DEG, IDENT_LAST>(s, alpha2);
 }
 
 // ---- pieces of the pair kernel ---------------------------------------------------------------------
@@ -265,8 +298,10 @@ __device__ __forceinline__ void load_pair(const float *__restrict__ rowA, const 
 }
 
 // Outputs of ONE codeword (half 0 = A, 1 = B) of a pair, written by the pair's own lanes.
+// Soft output: lane z handles position z of every block column (nlanes = Z), so for the degree-1 parity columns of the
+// active extension rows it owns the row's record and rebuilds the a-posteriori value on the fly (ext_app_h2).
 __device__ __forceinline__ void store_half(const DecArgs &a, const uint32_t *app, long long cw, int half, int ncw, int K,
-                                           int lane, int nlanes) {
+                                           int lane, int nlanes, const uint32_t *my_rec, const uint64_t pol) {
     const int sh = half ? 31 : 15;
     uint8_t *hard = a.hard + cw * K;
     if ((K & 3) == 0 && (reinterpret_cast<uintptr_t>(app) & 15) == 0) {
@@ -281,8 +316,11 @@ __device__ __forceinline__ void store_half(const DecArgs &a, const uint32_t *app
     }
     if (a.soft) {
         float *dst = a.soft + cw * ncw;
-        for (int i = lane; i < ncw; i += nlanes) {
-            const float2 f = __half22float2(as_h2(app[i]));
+        const int ext0 = a.kcols + 4, ext1 = a.kcols + a.n_rows;
+        for (int i = lane, col = 0; i < ncw; i += nlanes, ++col) {
+            uint32_t w = app[i];
+            if (col >= ext0 && col < ext1) w = ext_app_h2(my_rec, col - a.kcols, pol, w);
+            const float2 f = __half22float2(as_h2(w));
             __stcs(dst + i, half ? f.y : f.x);
         }
     }
@@ -293,7 +331,12 @@ __device__ __forceinline__ uint32_t syndrome_fail_h2(const DecArgs &a, const Dec
     uint32_t fail = 0;
     for (int r = 0; r < a.n_rows; ++r) {
         uint32_t par = 0;
-        for (int e = a.row_start[r]; e < a.row_start[r + 1]; ++e) par ^= lds_u32(edge_addr<false>(c.l, a.ed[e]));
+        const int e1 = a.row_start[r + 1];
+        for (int e = a.row_start[r]; e < e1; ++e) {
+            uint32_t w = lds_u32(edge_addr<false>(c.l, a.ed[e]));
+            if (r >= 4 && e == e1 - 1) w = ext_app_h2(c.my_rec, r, c.pol, w);
+            par ^= w;
+        }
         fail |= par;
     }
     return fail & kH2Sign;
@@ -326,8 +369,8 @@ struct UnrolledRowsH2 {
                 RowStateH2<DEG2> s1;
                 row_gather_h2<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur, s0);
                 row_gather_h2<DEG2, (R >= 4), FULL>(c.l, a.ed + E1, c.cur2, s1);
-                const uint4 rec0 = row_scatter_h2_par<DEG, kLastPair>(s0, a.alpha_h2, par);
-                const uint4 rec1 = row_scatter_h2_par<DEG2, kLastPair>(s1, a.alpha_h2, par);
+                const uint4 rec0 = row_scatter_h2_par<DEG, (R >= 4), kLastPair>(s0, a.alpha_h2, par);
+                const uint4 rec1 = row_scatter_h2_par<DEG2, (R >= 4), kLastPair>(s1, a.alpha_h2, par);
                 if (store_rec) {
                     st_rec(c.my_rec, R, rec0, c.pol);
                     st_rec(c.my_rec, R + 1, rec1, c.pol);
@@ -404,6 +447,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
     const int per_group = 2 * a.cwpc;
     const long long n_groups = (a.batch + per_group - 1) / per_group;
     const bool want_ok = a.ok != nullptr;
+    const bool keep_last = a.early_term || want_ok || a.soft != nullptr;   // see decode_nms_kernel
 
     DecCtxH2 c;
     c.l.zoff = (uint32_t)z * 4u;
@@ -439,7 +483,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
         for (int it = 0; it < a.max_iters; ++it) {
             const bool first = it == 0, last = it + 1 == a.max_iters;
             c.last_fail = 0u;   // set by the last layer when every base row is active
-            UnrolledRowsH2<BG, 0, FULL>::run(a, c, first ? a.n_rows - 1 : 0, last ? a.n_rows - 1 : a.n_rows, !last);
+            UnrolledRowsH2<BG, 0, FULL>::run(a, c, first ? a.n_rows - 1 : 0, last ? a.n_rows - 1 : a.n_rows, !last || keep_last);
             if (!fin_a) it_a = it + 1;
             if (!fin_b) it_b = it + 1;
             if (a.early_term || (want_ok && last)) {
@@ -448,14 +492,15 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
                     // codewords with an unsatisfied check in the last layer have not converged; the syndrome runs only if
                     // a live codeword of the pair is still undecided (it is exact for both)
                     if (a.n_rows < BgShape<BG>::kRows) {   // trimmed row count: re-read the last active row (see decode_kernel.cuh)
-                        const uint32_t par = last_row_parity(a, c.l);
+                        const uint32_t par = last_row_parity(a, c.l, c.my_rec, c.pol, ExtAppH2());
                         const int fa = __syncthreads_or((int)((par >> 15) & 1u));
                         const int fb = __syncthreads_or((int)(par >> 31));
                         c.last_fail = (fa ? 0x00008000u : 0u) | (fb ? 0x80000000u : 0u);
                     }
                     const uint32_t lf = c.last_fail;
                     if ((!fin_a && !(lf & 0x00008000u)) || (!fin_b && !(lf & 0x80000000u)))
-                        fu = syndrome_bitsliced_h2<BG>(a.smem_base, h2_hard_bits(s_flag, a.cwpc), Z, a.n_rows, tid, a.row_start, !fin_a, !fin_b);
+                        fu = syndrome_bitsliced_h2<BG>(a.smem_base, h2_hard_bits(s_flag, a.cwpc), Z, a.n_rows, tid, a.row_start, !fin_a, !fin_b,
+                                                       c.my_rec, c.pol);
                     else
                         fu = 0x80008000u;
                 } else {
@@ -463,7 +508,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
                     int *s_flag2 = s_flag + 2 * a.cwpc;
                     if (!c.done) {
                         uint32_t f = syndrome_unrolled_core_h2<BG, FULL>(a, c.l);
-                        if (!staged) f |= syndrome_unrolled_ext_h2<BG, FULL>(a, c.l);
+                        if (!staged) f |= syndrome_unrolled_ext_h2<BG, FULL>(a, c.l, c.my_rec, c.pol);
                         if (f & 0x00008000u) s_flag[2 * slot] = 1;
                         if (f & 0x80000000u) s_flag[2 * slot + 1] = 1;
                     }
@@ -471,7 +516,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
                         // extension rows only for pairs with a live codeword whose core checks all hold
                         __syncthreads();
                         if (!c.done && ((!fin_a && !s_flag[2 * slot]) || (!fin_b && !s_flag[2 * slot + 1]))) {
-                            const uint32_t f = syndrome_unrolled_ext_h2<BG, FULL>(a, c.l);
+                            const uint32_t f = syndrome_unrolled_ext_h2<BG, FULL>(a, c.l, c.my_rec, c.pol);
                             if (f & 0x00008000u) s_flag2[2 * slot] = 1;
                             if (f & 0x80000000u) s_flag2[2 * slot + 1] = 1;
                         }
@@ -482,14 +527,14 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
                 if (!fin_a) {
                     ok_a = (fu & 0x00008000u) ? 0 : 1;
                     if (ok_a && a.early_term) {   // converged: freeze this codeword's outputs now
-                        store_half(a, my_app, cwA, 0, ncw, K, z, Z);
+                        store_half(a, my_app, cwA, 0, ncw, K, z, Z, c.my_rec, c.pol);
                         fin_a = true;
                     }
                 }
                 if (!fin_b) {
                     ok_b = (fu & 0x80000000u) ? 0 : 1;
                     if (ok_b && a.early_term) {
-                        store_half(a, my_app, cwB, 1, ncw, K, z, Z);
+                        store_half(a, my_app, cwB, 1, ncw, K, z, Z, c.my_rec, c.pol);
                         fin_b = true;
                     }
                 }
@@ -501,8 +546,8 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
         }
         __syncthreads();
 
-        if (active && !fin_a) store_half(a, my_app, cwA, 0, ncw, K, z, Z);
-        if (has_b && !fin_b) store_half(a, my_app, cwB, 1, ncw, K, z, Z);
+        if (active && !fin_a) store_half(a, my_app, cwA, 0, ncw, K, z, Z, c.my_rec, c.pol);
+        if (has_b && !fin_b) store_half(a, my_app, cwB, 1, ncw, K, z, Z, c.my_rec, c.pol);
         if (active && z == 0) {
             if (a.iters) a.iters[cwA] = it_a;
             if (a.ok) a.ok[cwA] = (uint8_t)ok_a;

@@ -624,15 +624,24 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
         h->h_row_start[r] = e;
     }
     memset(&h->dec_args, 0, sizeof(h->dec_args));
+    bool bad_structure = false;
     for (int r = 0; r <= v.rows; ++r) h->dec_args.row_start[r] = (unsigned short)h->h_row_start[r];
     for (int e = 0; e < v.edges; ++e) {
         const int sft = v.sh(ils, e) % Z;
         ed[e] = ((uint32_t)(v.col[e] * Z) << 16) | (uint32_t)sft;
         h->dec_args.ed[e] = make_uint2((uint32_t)sft * 4u, (uint32_t)(v.col[e] * Z) * 4u);
-        // the unrolled kernels rely on the extension parity columns being identity circulants
+        // every kernel relies on the structure of the extension part (TS 38.212 Tables 5.3.2-2/-3): row r >= 4 ends in an
+        // identity circulant in column kcols + r
         if (v.row[e] >= 4 && (e + 1 == v.edges || v.row[e + 1] != v.row[e]) && (sft != 0 || v.col[e] != v.kcols + v.row[e]))
-            h->dec_variant = 0;
+            bad_structure = true;
     }
+    // ... and that column belongs to no other row (a degree-1 variable: DESIGN.md section 2, oracle A revision 2)
+    for (int c = v.kcols + 4; c < v.cols; ++c) {
+        int cnt = 0;
+        for (int e = 0; e < v.edges; ++e) cnt += v.col[e] == c;
+        if (cnt != 1) bad_structure = true;
+    }
+    if (bad_structure) { delete h; return fail(nullptr, NRLDPC_EUNSUPPORTED, "unexpected extension-parity structure in the base graph table"); }
     // encoder structure: shifts of the first core-parity column in rows 0..3
     int vals[3], nv = 0;
     for (int r = 0; r < 4; ++r) h->enc_s0[r] = -1;

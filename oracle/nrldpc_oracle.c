@@ -290,6 +290,13 @@ ORC_API long orc_syndrome_weight(int bg, int Z, int n_rows, const uint8_t *cw) {
  *                NRLDPCDecoder.m:264), LLR_MAX = 2^20: keeps inf-inf out of the recursion; -0 -> +0.
  *   schedule     base rows 0..n_rows-1 in order, all Z checks of a row independent.
  *   per check    t_e   = app[v_e] - c_e            (c_e = previous message, +0 in iteration 1)
+ *                REVISION 2 (default): a variable that belongs to ONE check of the whole H -- the extension parity
+ *                columns Kc+4 .. C-1, TS 38.212 tables -- has nothing but its channel value and this check's own
+ *                message in its a-posteriori value, so in exact arithmetic app - c_e IS the channel value; revision 2
+ *                takes t_e = (clamped) channel value for those edges in every iteration instead of re-deriving it
+ *                through two float32 roundings.  Their a-posteriori value app = t_e + c_e' is still formed (hard
+ *                decisions, syndrome, soft output) but never fed back.  Revision 1 (orc_set_nms_revision(1)) is the
+ *                round-1 definition without this rule; tests/test_oracle.py compares the two.
  *                m1,m2 = two smallest |t_e| (strict '<' updates, first index wins ties)
  *                c_e'  = sgn * (e == argmin ? alpha*m2 : alpha*m1), sgn = XOR of sign BITS of the
  *                        other t's; every product/sum individually rounded (no FMA)
@@ -298,6 +305,10 @@ ORC_API long orc_syndrome_weight(int bg, int Z, int n_rows, const uint8_t *cw) {
  *                active rows is satisfied, stop.  iters_out = iterations executed.
  * ---------------------------------------------------------------------------------------- */
 #define ORC_LLR_MAX 1048576.0f
+
+static int orc_nms_revision_ = 2;
+ORC_API void orc_set_nms_revision(int rev) { orc_nms_revision_ = rev == 1 ? 1 : 2; }
+ORC_API int orc_get_nms_revision(void) { return orc_nms_revision_; }
 
 static inline uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
@@ -312,6 +323,17 @@ static int *build_vidx(int bg, int Z, int ils) {
     return v;
 }
 
+/* First block column from which on every column of the base graph holds exactly one entry (22+4 = 26 for BG1, 10+4 = 14 for
+ * BG2): counted from the table, not assumed. */
+static int first_single_column(int bg) {
+    int R, C, Kc, E, cnt[68] = {0};
+    bg_dims(bg, &R, &C, &Kc, &E);
+    for (int e = 0; e < E; ++e) ++cnt[bg_col(bg)[e]];
+    int c = C;
+    while (c > 0 && cnt[c - 1] == 1) --c;
+    return c;
+}
+
 static int decode_nms_one(int bg, int Z, int ils, int n_rows, int max_iters, int early_term, float alpha,
                           const int *vidx, const float *llr, uint8_t *hard_info, float *app_out, uint8_t *parity_ok) {
     int R, C, Kc, E;
@@ -321,12 +343,16 @@ static int decode_nms_one(int bg, int Z, int ils, int n_rows, int max_iters, int
     for (int r = 0, e = 0; r <= R; ++r) { while (e < E && er[e] < r) ++e; row_start[r] = e; }
     const int nV = C * Z;
     float *app = (float *)malloc(sizeof(float) * nV);
+    float *chan = (float *)malloc(sizeof(float) * nV);
     float *c2v = (float *)calloc((size_t)E * Z, sizeof(float)); /* uncompressed; same values */
     for (int i = 0; i < nV; ++i) {
         float x = llr[i];
         app[i] = (x != x) ? ORC_LLR_MAX : (x > ORC_LLR_MAX ? ORC_LLR_MAX : (x < -ORC_LLR_MAX ? -ORC_LLR_MAX : x));
         app[i] += 0.0f; /* -0 -> +0: from here on no APP value is ever -0, so (app < 0) == sign bit */
+        chan[i] = app[i];
     }
+    /* column degrees over the WHOLE H: the degree-1 variables are the extension parity columns */
+    const int single_from = orc_nms_revision_ >= 2 ? first_single_column(bg) * Z : nV;
     int it = 0, ok = 0;
     while (it < max_iters) {
         for (int r = 0; r < n_rows; ++r) {
@@ -337,7 +363,7 @@ static int decode_nms_one(int bg, int Z, int ils, int n_rows, int max_iters, int
                 for (int k = 0; k < deg; ++k) {
                     int e = e0 + k;
                     v[k] = vidx[(size_t)e * Z + z];
-                    t[k] = app[v[k]] - c2v[(size_t)e * Z + z];
+                    t[k] = v[k] >= single_from ? chan[v[k]] : app[v[k]] - c2v[(size_t)e * Z + z];
                     float a = fabsf(t[k]);
                     if (a < m1) { m2 = m1; m1 = a; arg = k; } else if (a < m2) { m2 = a; }
                     sgn ^= f2u(t[k]) & 0x80000000u;
@@ -367,7 +393,7 @@ static int decode_nms_one(int bg, int Z, int ils, int n_rows, int max_iters, int
     for (int k = 0; k < Kc * Z; ++k) hard_info[k] = app[k] < 0.0f;
     if (app_out) memcpy(app_out, app, sizeof(float) * nV);
     if (parity_ok) *parity_ok = (uint8_t)ok;
-    free(app); free(c2v);
+    free(app); free(chan); free(c2v);
     return it;
 }
 
@@ -446,6 +472,7 @@ static int decode_nms_f16_one(int bg, int Z, int ils, int n_rows, int max_iters,
     for (int r = 0, e = 0; r <= R; ++r) { while (e < E && er[e] < r) ++e; row_start[r] = e; }
     const int nV = C * Z;
     uint16_t *app = (uint16_t *)malloc(sizeof(uint16_t) * nV);
+    uint16_t *chan = (uint16_t *)malloc(sizeof(uint16_t) * nV);
     uint16_t *c2v = (uint16_t *)calloc((size_t)E * Z, sizeof(uint16_t));
     const double alpha_h = h2d(d2h((double)alpha));
     for (int i = 0; i < nV; ++i) {
@@ -453,7 +480,9 @@ static int decode_nms_f16_one(int bg, int Z, int ils, int n_rows, int max_iters,
         x = (x != x) ? ORC_H_LLR_MAX : (x > ORC_H_LLR_MAX ? ORC_H_LLR_MAX : (x < -ORC_H_LLR_MAX ? -ORC_H_LLR_MAX : x));
         x += 0.0f;
         app[i] = d2h((double)x);
+        chan[i] = app[i];
     }
+    const int single_from = orc_nms_revision_ >= 2 ? first_single_column(bg) * Z : nV;   /* revision 2, see oracle A */
     int it = 0, ok = 0;
     while (it < max_iters) {
         for (int r = 0; r < n_rows; ++r) {
@@ -464,7 +493,7 @@ static int decode_nms_f16_one(int bg, int Z, int ils, int n_rows, int max_iters,
                 for (int k = 0; k < deg; ++k) {
                     const int e = e0 + k;
                     v[k] = vidx[(size_t)e * Z + z];
-                    t[k] = d2h(h2d(app[v[k]]) - h2d(c2v[(size_t)e * Z + z]));
+                    t[k] = v[k] >= single_from ? chan[v[k]] : d2h(h2d(app[v[k]]) - h2d(c2v[(size_t)e * Z + z]));
                     const uint16_t a = t[k] & 0x7fffu;
                     if (a < m1) { m2 = m1; m1 = a; } else if (a < m2) { m2 = a; }
                     sgn ^= t[k] & 0x8000u;
@@ -494,7 +523,7 @@ static int decode_nms_f16_one(int bg, int Z, int ils, int n_rows, int max_iters,
     for (int k = 0; k < Kc * Z; ++k) hard_info[k] = h2d(app[k]) < 0.0;
     if (app_out) for (int i = 0; i < nV; ++i) app_out[i] = (float)h2d(app[i]);
     if (parity_ok) *parity_ok = (uint8_t)ok;
-    free(app); free(c2v);
+    free(app); free(chan); free(c2v);
     return it;
 }
 

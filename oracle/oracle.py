@@ -126,6 +126,12 @@ def decode_nms(bg, Z, llr, max_iters=8, early_term=False, alpha=0.75, n_rows=0, 
     return dict(hard=hard, app=app, iters=iters, parity_ok=ok)
 
 
+def set_nms_revision(rev: int):
+    """Oracle A / A16 revision: 2 (default) = degree-1 variables enter their check with the channel value; 1 = the round-1
+    definition.  See the header of orc_decode_nms in nrldpc_oracle.c."""
+    lib().orc_set_nms_revision(int(rev))
+
+
 def f16_round(x):
     """binary16 bit patterns of float64 values, as oracle A16 rounds them (round to nearest even)."""
     x = np.ascontiguousarray(x, dtype=np.float64).ravel()

@@ -151,7 +151,7 @@ def _clamp_f32(llr):
     return (x + np.float32(0.0)).astype(np.float32)                 # -0 -> +0
 
 
-def nms_layered(bg, Z, llr, max_iters, early_term=False, n_rows=0, alpha=0.75, deg1_shortcut=False):
+def nms_layered(bg, Z, llr, max_iters, early_term=False, n_rows=0, alpha=0.75, deg1_shortcut=True):
     """Oracle A's definition on one codeword (llr: [cols*Z] in cw_tilde layout).  Returns hard[K], app, iters, ok.
 
     deg1_shortcut (oracle A revision 2): a variable that belongs to exactly ONE check row of the
@@ -202,7 +202,7 @@ def _h(x):
     return np.asarray(x, dtype=np.float64).astype(np.float16).astype(np.float64)
 
 
-def nms_layered_f16(bg, Z, llr, max_iters, early_term=False, n_rows=0, alpha=0.75, deg1_shortcut=False):
+def nms_layered_f16(bg, Z, llr, max_iters, early_term=False, n_rows=0, alpha=0.75, deg1_shortcut=True):
     """Oracle A16's definition (binary16 after every operation, minima capped at 2048 before the scaling)."""
     g = graph(bg, Z)
     n_rows = n_rows or g.rows

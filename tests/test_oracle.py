@@ -261,3 +261,30 @@ def test_core_checks_hold_extension_check_fails(O, bg, Z, n_rows):
         ext_fail = syn[:, 4 * Z:n_rows * Z].any(axis=1)
         assert not core_fail[kind == 1].any() and ext_fail[kind == 1].all()
         assert not core_fail[kind == 0].any() and not ext_fail[kind == 0].any()
+
+
+def test_nms_revision_2_tracks_revision_1(O):
+    """Oracle A revision 2 (degree-1 parity variables enter their check with the channel value) against
+    the round-1 definition on identical noise: the two differ only by float rounding of app - c on those edges, so block
+    decisions and iteration counts agree (stated tolerance: at most 1 block in 1000 differs in float32, 5 in binary16);
+    both revisions also equal the independent numpy twin bit for bit."""
+    from conftest import make_llr
+    from oracle import twin as T
+    rng = np.random.default_rng(21)
+    try:
+        for bg, Z, E, esn0, B, fill, rows in ((2, 6, 100, 2.0, 4000, 24, 13), (2, 52, 2000, -2.0, 1000, 104, 33), (1, 96, 6336, 0.0, 300, 0, 46)):
+            info, llr = make_llr(O, bg, Z, B, E, esn0, rng, filler=fill)
+            for f16, tol in ((False, 1e-3), (True, 5e-3)):
+                err, its = {}, {}
+                for rev in (1, 2):
+                    O.set_nms_revision(rev)
+                    r = O.decode_nms(bg, Z, llr, 8, early_term=True, n_rows=rows, f16=f16)
+                    err[rev], its[rev] = (r["hard"] != info).any(axis=1), r["iters"]
+                    dec = T.nms_layered_f16 if f16 else T.nms_layered
+                    hard, app, it, ok = dec(bg, Z, llr[0], 8, True, rows, deg1_shortcut=(rev == 2))
+                    assert (hard == r["hard"][0]).all() and it == r["iters"][0]
+                    assert (app.astype(np.float32).view(np.uint32) == r["app"][0].view(np.uint32)).all()
+                assert (err[1] != err[2]).mean() <= tol, (bg, Z, f16)
+                assert abs(its[1].mean() - its[2].mean()) < 0.01
+    finally:
+        O.set_nms_revision(2)

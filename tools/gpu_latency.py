@@ -26,4 +26,35 @@ for name, kw in (("nms_f32", {}), ("nms_f16x2", dict(llr_dtype=capi.F16X2)), ("b
         rows.append({"mode": name, "batch": B, "median_us": round(1e6 * float(np.median(ts)), 1), "min_us": round(1e6 * min(ts), 1)})
         print(rows[-1], flush=True)
     h.close()
+
+# where the time of a one-codeword call goes: the kernel alone on device buffers (CUDA events over back-to-back launches),
+# and the reference's whole per-block RX chain (NRLDPCDecoder.m:133-140: rate recovery -> decode -> CRC) on device buffers
+h = capi.Handle(w["bg"], w["Z"], 8, False)
+hard = torch.empty((256, h.K), dtype=torch.uint8, device="cuda")
+for B in (1, 8):
+    for _ in range(10):
+        h.decode_raw(llr, B, hard, n_rows=46, mem=capi.MEM_DEVICE, stream=st)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(200):
+        h.decode_raw(llr, B, hard, n_rows=46, mem=capi.MEM_DEVICE, stream=st)
+    e1.record(); torch.cuda.synchronize()
+    rows.append({"mode": "nms_f32 kernel only (device buffers, back-to-back)", "batch": B, "us_per_launch": round(1e3 * e0.elapsed_time(e1) / 200, 1)})
+    print(rows[-1], flush=True)
+E = w["E"]
+rm = capi.Rm(E, 0, h.N, h.K, 2)
+fl = torch.randn((1, E), dtype=torch.float32, device="cuda") * 3 + 2
+out = torch.empty((1, h.n_cw), dtype=torch.float32, device="cuda")
+ok = torch.zeros(1, dtype=torch.uint8, device="cuda")
+ts = []
+for i in range(120):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    h.rate_recover_raw(fl, 1, rm, None, out, mem=capi.MEM_DEVICE, stream=st)
+    h.decode_raw(out, 1, hard, n_rows=46, mem=capi.MEM_DEVICE, stream=st)
+    h.crc_raw(hard, 1, h.K, h.K, capi.CRC24A, ok=ok, stream=st)
+    torch.cuda.synchronize(); ts.append(time.perf_counter() - t0)
+rows.append({"mode": "one-block RX chain on device buffers: rate_recover + decode + crc, 3 launches + sync", "batch": 1,
+             "median_us": round(1e6 * float(np.median(ts[20:])), 1)})
+print(rows[-1], flush=True)
+h.close()
 json.dump(rows, open("gpurun_out/latency.json", "w"), indent=1)
