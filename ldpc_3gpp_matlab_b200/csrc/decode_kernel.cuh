@@ -74,7 +74,8 @@ struct DecArgs {
     int one;                 // = 1 (see mad_u32)
     uint32_t smem_base;      // shared-window address of the kernel's dynamic shared memory
     uint32_t alpha_h2;       // {fp16(alpha), fp16(alpha)} for the packed-half kernel
-    uint32_t *c2v;           // [grid][kRecWords][kRecStride]; float32 record = {alpha*min1|sgn, alpha*min2|sgn, argmin | signbits << 5}
+    int rec_group;           // CTAs that share one [kRecWords][kRecStride] scratch block (CTA b uses thread columns (b % rec_group) * blockDim.x ...)
+    uint32_t *c2v;           // [ceil(grid / rec_group)][kRecWords][kRecStride]; float32 record = {alpha*min1|sgn, alpha*min2|sgn, argmin | signbits << 5}
     int *work_counter;
     unsigned short row_start[kMaxRows + 2];
     uint2 ed[kMaxEdges];
@@ -282,7 +283,7 @@ __device__ __forceinline__ void row_gather(const Lane &l, const uint2 *__restric
 // bit is this check's parity on the hard decisions just written (used for the last layer of an iteration, whose decisions
 // are final: see UnrolledRows)
 template <int DEG, bool IDENT_LAST, bool PAR>
-__device__ __forceinline__ uint4 row_scatter_par(const RowState<DEG> &s, const float alpha, uint32_t &par) {
+__device__ __forceinline__ uint4 row_scatter_par(const RowState<DEG> &s, const float alpha, uint32_t &par, const bool live = true) {
     constexpr int NE = IDENT_LAST ? DEG - 1 : DEG;
     // both candidate magnitudes with the row's sign product folded in: multiply by alpha carrying the sign
     // (m >= 0, so the product's sign bit is sg also when m = 0: bit-identical to (alpha*m) | sg)
@@ -300,7 +301,7 @@ __device__ __forceinline__ uint4 row_scatter_par(const RowState<DEG> &s, const f
         const float c = __uint_as_float(sel ^ (__float_as_uint(s.t[e]) & 0x80000000u));
         const float app = __fadd_rn(s.t[e], c);
         if (PAR) par ^= __float_as_uint(app);
-        sts_f32(s.addr[e], app);
+        if (live) sts_f32(s.addr[e], app);
     }
     if (PAR && IDENT_LAST) {   // the degree-1 variable's a-posteriori value takes part in the check's parity only
         const float tp = s.t[DEG - 1];
@@ -310,17 +311,17 @@ __device__ __forceinline__ uint4 row_scatter_par(const RowState<DEG> &s, const f
     return make_uint4(m1ss, m2ss, arg | (s.ts << 5), 0u);
 }
 template <int DEG, bool IDENT_LAST>
-__device__ __forceinline__ uint4 row_scatter(const RowState<DEG> &s, const float alpha) {
+__device__ __forceinline__ uint4 row_scatter(const RowState<DEG> &s, const float alpha, const bool live = true) {
     uint32_t unused = 0;
-    return row_scatter_par<DEG, IDENT_LAST, false>(s, alpha, unused);
+    return row_scatter_par<DEG, IDENT_LAST, false>(s, alpha, unused, live);
 }
 
 template <int DEG, bool IDENT_LAST, bool ONE_CW>
 __device__ __forceinline__ uint4 process_row(const Lane &l, const uint2 *__restrict__ ed, const uint32_t om1,
-                                             const uint32_t om2, const uint32_t ometa, const float alpha) {
+                                             const uint32_t om2, const uint32_t ometa, const float alpha, const bool live = true) {
     RowState<DEG> s;
     row_gather<DEG, IDENT_LAST, ONE_CW>(l, ed, om1, om2, ometa, s);
-    return row_scatter<DEG, IDENT_LAST>(s, alpha);
+    return row_scatter<DEG, IDENT_LAST>(s, alpha, live);
 }
 
 // ---- pieces shared by all kernel variants --------------------------------------------------------
@@ -330,7 +331,10 @@ struct DecCtx {
     uint64_t pol;
     uint4 cur, cur2; // prefetched records of the next layer (and of its partner when the next layer is a pair)
     bool done;       // this thread does no row work (inactive lane, or its codeword has converged)
+    bool live;       // MASKED kernels: this lane owns a check (tid < Z); the lanes that pad the last warp shadow lanes 0.. and never store
     int last_fail;   // FULL kernels, every base row active: some check of the iteration's last layer is unsatisfied (CTA-uniform)
+    uint4 last_rec;  // FULL kernels, trimmed row count: the record the last ACTIVE row wrote in this iteration (kept in registers
+                     // for last_row_parity: reloading it from the L2 scratch cost one L2 round trip per iteration)
 };
 
 // TMA staging of a codeword group: the group's rows are contiguous in HBM, so ONE bulk asynchronous copy
@@ -405,20 +409,25 @@ __device__ __forceinline__ uint32_t syndrome_fail(const DecArgs &a, const DecCtx
 
 // XOR of the a-posteriori words of check z of the LAST active base row (sign bit(s) = its parity); out of line so that the
 // layer code's register allocation does not see it
-// (EXT_APP: the float32 / packed-half routine that rebuilds the degree-1 parity variable's a-posteriori word)
+// rec: the record that row wrote in this iteration (DecCtx::last_rec); EXT_APP: the float32 / packed-half routine that
+// rebuilds the degree-1 parity variable's a-posteriori word from it
 template <typename EXT_APP>
-__device__ __noinline__ uint32_t last_row_parity(const DecArgs &a, const Lane l, const uint32_t *my_rec, const uint64_t pol, EXT_APP ext) {
+__device__ __noinline__ uint32_t last_row_parity(const DecArgs &a, const Lane l, const uint4 rec, EXT_APP ext) {
     uint32_t par = 0;
     const int r = a.n_rows - 1, e1 = a.row_start[a.n_rows];
     for (int e = a.row_start[r]; e < e1; ++e) {
         uint32_t w = lds_u32(edge_addr<false>(l, a.ed[e]));
-        if (r >= 4 && e == e1 - 1) w = ext(my_rec, r, pol, w);
+        if (r >= 4 && e == e1 - 1) w = ext(rec, w);
         par ^= w;
     }
     return par;
 }
+__device__ __forceinline__ uint32_t ext_app_rec(const uint4 rec, uint32_t chan) {
+    const uint32_t sel = ((rec.z & 31u) == 31u) ? rec.y : rec.x;
+    return __float_as_uint(__fadd_rn(__uint_as_float(chan), __uint_as_float(sel ^ (chan & 0x80000000u))));
+}
 struct ExtAppF32 {
-    __device__ __forceinline__ uint32_t operator()(const uint32_t *my_rec, int row, uint64_t pol, uint32_t chan) const { return ext_app(my_rec, row, pol, chan); }
+    __device__ __forceinline__ uint32_t operator()(const uint4 rec, uint32_t chan) const { return ext_app_rec(rec, chan); }
 };
 
 __device__ __forceinline__ void store_outputs(const DecArgs &a, const float *app, long long cw0, int n_here, int ncw, int K) {
@@ -620,12 +629,17 @@ __device__ __forceinline__ void iteration_looped(const DecArgs &a, DecCtx &c, co
 // last row is R iff ld_from <= R < ld_to (first iteration: only across the iteration boundary; last: never
 // across).  (Prefetching unconditionally over zeroed records was measured 0.5-1 % slower in this kernel and
 // 7 % slower in the packed-half kernel.)
-// FULL: every thread of the CTA owns a check for the whole decode (one codeword per CTA, Z a
-// multiple of 32): no per-thread activity test.
-template <int BG, int R, bool FULL>
+// FULL: every thread of the CTA runs the row code for the whole decode (one codeword per CTA): no per-thread activity
+// test.  MASKED (FULL only): Z is not a multiple of 32, the lanes that pad the last warp shadow lanes 0.. (same loads,
+// same arithmetic) and only their stores are predicated off -- the CTA-uniform code serves every one-codeword CTA.
+template <int BG, int R, bool FULL, bool MASKED = false>
 struct UnrolledRows {
-    static __device__ __forceinline__ void run(const DecArgs &a, DecCtx &c, const int ld_from, const int ld_to, const bool store_rec) {
-        if (R >= 4 && R >= a.n_rows) return;   // n_rows >= 4 is validated by the host
+    static __device__ __forceinline__ void run(const DecArgs &a, DecCtx &c, const int ld_from, const int ld_to, const bool store_rec,
+                                               const uint4 prev = make_uint4(0u, 0u, 0u, 0u)) {
+        if (R >= 4 && R >= a.n_rows) {         // n_rows >= 4 is validated by the host
+            if (FULL) c.last_rec = prev;       // the previous row was the last active one (trimmed row count)
+            return;
+        }
         constexpr int DEG = BgShape<BG>::deg(R);
         constexpr int E0 = BgShape<BG>::start(R);
         constexpr bool PAIR = pair_first<BG>(R);
@@ -635,6 +649,7 @@ struct UnrolledRows {
             constexpr int E1 = BgShape<BG>::start(PAIR ? R + 1 : R);
             constexpr bool kLastPair = FULL && PAIR && R + 2 == BgShape<BG>::kRows;
             uint32_t par = 0;
+            uint4 rec_last = make_uint4(0u, 0u, 0u, 0u);
             if (FULL || !c.done) {
                 uint4 nxt = make_uint4(0u, 0u, 0u, 0u), nxt2 = nxt;
                 if ((R + 1 >= ld_from && R + 1 < ld_to)) {
@@ -645,56 +660,61 @@ struct UnrolledRows {
                 RowState<DEG2> s1;
                 row_gather<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur.x, c.cur.y, c.cur.z, s0);
                 row_gather<DEG2, (R >= 4), FULL>(c.l, a.ed + E1, c.cur2.x, c.cur2.y, c.cur2.z, s1);
-                const uint4 rec0 = row_scatter_par<DEG, (R >= 4), kLastPair>(s0, a.alpha, par);
-                const uint4 rec1 = row_scatter_par<DEG2, (R >= 4), kLastPair>(s1, a.alpha, par);
-                if (store_rec) {
+                const uint4 rec0 = row_scatter_par<DEG, (R >= 4), kLastPair>(s0, a.alpha, par, !MASKED || c.live);
+                const uint4 rec1 = row_scatter_par<DEG2, (R >= 4), kLastPair>(s1, a.alpha, par, !MASKED || c.live);
+                if (store_rec && (!MASKED || c.live)) {
                     st_rec(c.my_rec, R == 0 ? a.n_rows : R, rec0, c.pol);
                     st_rec(c.my_rec, R + 1, rec1, c.pol);
                 }
                 c.cur = nxt;
                 c.cur2 = nxt2;
+                if (FULL && R >= 4) rec_last = rec1;   // only an extension row's record is ever needed (rows 0..3 have no degree-1 variable)
             }
             // The hard decisions written by the LAST layer of an iteration are final, so an unsatisfied check there
             // proves that the codeword has not converged: with every base row active the layer's barrier doubles as the
             // CTA-wide OR of those parities and the kernel skips the syndrome after most iterations (exact either way).
-            if (kLastPair) c.last_fail = __syncthreads_or((int)(par >> 31));
+            if (kLastPair) c.last_fail = __syncthreads_or((int)(par >> 31) & (int)(!MASKED || c.live));
             else __syncthreads();
-            UnrolledRows<BG, (PAIR ? R + 2 : BgShape<BG>::kRows), FULL>::run(a, c, ld_from, ld_to, store_rec);
+            UnrolledRows<BG, (PAIR ? R + 2 : BgShape<BG>::kRows), FULL, MASKED>::run(a, c, ld_from, ld_to, store_rec, rec_last);
         } else {
+            uint4 rec_last = make_uint4(0u, 0u, 0u, 0u);
             if (FULL || !c.done) {
                 uint4 nxt = make_uint4(0u, 0u, 0u, 0u), nxt2 = nxt;
                 if ((R >= ld_from && R < ld_to)) {
                     nxt = ld_rec(c.my_rec, R + 1, c.pol);   // slot R+1; slot n_rows holds layer 0
                     if (!PAIR && pair_first<BG>(R + 1)) nxt2 = ld_rec(c.my_rec, R + 2, c.pol);
                 }
-                const uint4 rec = process_row<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur.x, c.cur.y, c.cur.z, a.alpha);
-                if (store_rec) st_rec(c.my_rec, R == 0 ? a.n_rows : R, rec, c.pol);
+                const uint4 rec = process_row<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur.x, c.cur.y, c.cur.z, a.alpha, !MASKED || c.live);
+                if (store_rec && (!MASKED || c.live)) st_rec(c.my_rec, R == 0 ? a.n_rows : R, rec, c.pol);
                 c.cur = nxt;
                 c.cur2 = nxt2;
+                if (FULL && R >= 4) rec_last = rec;
             }
             __syncthreads();
             // a pair opener running alone means R + 1 == n_rows: the iteration ends here
-            if (!PAIR) UnrolledRows<BG, R + 1, FULL>::run(a, c, ld_from, ld_to, store_rec);
+            if (!PAIR) UnrolledRows<BG, R + 1, FULL, MASKED>::run(a, c, ld_from, ld_to, store_rec, rec_last);
+            else if (FULL) c.last_rec = rec_last;
         }
     }
 };
-template <int BG, bool FULL>
-struct UnrolledRows<BG, BgShape<BG>::kRows, FULL> {
-    static __device__ __forceinline__ void run(const DecArgs &, DecCtx &, int, int, bool) {}
+template <int BG, bool FULL, bool MASKED>
+struct UnrolledRows<BG, BgShape<BG>::kRows, FULL, MASKED> {
+    static __device__ __forceinline__ void run(const DecArgs &, DecCtx &, int, int, bool, const uint4 = make_uint4(0u, 0u, 0u, 0u)) {}
 };
 
-template <int BG, bool FULL>
+template <int BG, bool FULL, bool MASKED>
 __device__ __forceinline__ void iteration_unrolled(const DecArgs &a, DecCtx &c, const int it, const bool keep_last) {
     const bool first = it == 0, last = it + 1 == a.max_iters;
     c.last_fail = 0;   // set by the last layer when every base row is active
     // keep_last: the records of the final iteration are written too (they hold the messages to the degree-1 parity
     // variables, from which the syndrome and the soft output rebuild those variables' a-posteriori values)
-    UnrolledRows<BG, 0, FULL>::run(a, c, first ? a.n_rows - 1 : 0, last ? a.n_rows - 1 : a.n_rows, !last || keep_last);
+    UnrolledRows<BG, 0, FULL, MASKED>::run(a, c, first ? a.n_rows - 1 : 0, last ? a.n_rows - 1 : a.n_rows, !last || keep_last);
 }
 
 // BG = 0: generic looped variant; BG = 1 / 2: layer loop unrolled for that base graph.
-template <int BG, bool FULL>
+template <int BG, bool FULL, bool MASKED = false>
 __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(const __grid_constant__ DecArgs a) {
+    static_assert(FULL || !MASKED, "MASKED is a flavour of the one-codeword (FULL) kernels");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Z = a.Z;
     const int ncw = a.ncols * Z;
@@ -713,13 +733,13 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
     }
     // the edge descriptors carry absolute shared addresses (DecArgs::ed): fail loudly if the window moved
     if ((uint32_t)__cvta_generic_to_shared(smem_raw) != a.smem_base) __trap();
-    const bool bitsliced = FULL && a.n_rows >= a.bitsliced_min_rows;
+    const bool bitsliced = FULL && !MASKED && a.n_rows >= a.bitsliced_min_rows;
     if (bitsliced && (a.early_term || a.ok != nullptr))   // ordered by the barriers below
         fill_syndrome_edges(a, (uint32_t)__cvta_generic_to_shared(bar + 1) + (uint32_t)(a.ncols * (Z >> 5)) * 8u);
 
     const int tid = threadIdx.x;
     const int slot = tid / Z;
-    const int z = tid - slot * Z;
+    const int z = tid - slot * Z;   // MASKED: the padding lanes (slot 1) shadow lanes 0.. of the codeword
     const bool lane_ok = tid < a.cwpc * Z;
     const long long n_groups = (a.batch + a.cwpc - 1) / a.cwpc;
     const bool want_ok = a.ok != nullptr;
@@ -731,8 +751,9 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
     c.l.nZ4 = 0u - (uint32_t)Z * 4u;
     c.l.slot_off = FULL ? 0u : (uint32_t)(slot * a.slot_stride) * 4u;
     c.l.one = (uint32_t)a.one;
-    c.my_rec = a.c2v + (size_t)blockIdx.x * (kRecWords * kRecStride) + tid;
+    c.my_rec = a.c2v + (size_t)(blockIdx.x / a.rec_group) * (kRecWords * kRecStride) + (blockIdx.x % a.rec_group) * blockDim.x + tid;
     c.pol = make_l2_policy(a.l2_pin);
+    c.live = tid < Z;
 
     while (true) {
         __syncthreads();  // previous group's outputs are out of smem
@@ -756,17 +777,17 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
 
         for (int it = 0; it < a.max_iters; ++it) {
             if (BG == 0) iteration_looped(a, c, it, keep_last);
-            else iteration_unrolled<(BG == 0 ? 1 : BG), FULL>(a, c, it, keep_last);
+            else iteration_unrolled<(BG == 0 ? 1 : BG), FULL, MASKED>(a, c, it, keep_last);
 
             if (!c.done) my_iters = it + 1;
             const bool last = it + 1 == a.max_iters;
             if (a.early_term || (want_ok && last)) {
-                if (FULL && bitsliced) {
+                if (FULL && !MASKED && bitsliced) {
                     // one codeword per CTA: the verdict is CTA-uniform, no flags
                     // trimmed row count: the last active row is only known at run time, so its Z checks (final as well) are
                     // re-read from shared memory -- a few loads per thread and one reducing barrier
                     if (a.n_rows < BgShape<(BG == 0 ? 1 : BG)>::kRows)
-                        c.last_fail = __syncthreads_or((int)(last_row_parity(a, c.l, c.my_rec, c.pol, ExtAppF32()) >> 31));
+                        c.last_fail = __syncthreads_or((int)(last_row_parity(a, c.l, c.last_rec, ExtAppF32()) >> 31));
                     my_ok = c.last_fail ? 0   // an unsatisfied check in the last layer: not converged, no syndrome needed
                           : (syndrome_bitsliced<(BG == 0 ? 1 : BG)>(a.smem_base, (uint32_t)__cvta_generic_to_shared(bar + 1), Z, a.n_rows, tid, a.row_start,
                                                                      c.my_rec, c.pol) ? 0 : 1);

@@ -40,8 +40,11 @@ __device__ __forceinline__ uint32_t ext_app_h2(const uint32_t *my_rec, int row, 
     const uint32_t sel = bitselect(rec.x, rec.y, is_p);
     return as_u32(__hadd2(as_h2(chan), as_h2(sel ^ (chan & kH2Sign))));
 }
+// last_row_parity of the pair kernel: the last active row's record is reloaded from the L2 scratch (holding it in registers
+// through the layer loop, as the float32 kernel does, made ptxas spill inside the BG1 loop: 25 spill instructions)
 struct ExtAppH2 {
-    __device__ __forceinline__ uint32_t operator()(const uint32_t *my_rec, int row, uint64_t pol, uint32_t chan) const { return ext_app_h2(my_rec, row, pol, chan); }
+    const uint32_t *my_rec; int row; uint64_t pol;
+    __device__ __forceinline__ uint32_t operator()(const uint4, uint32_t chan) const { return ext_app_h2(my_rec, row, pol, chan); }
 };
 
 // One check row of degree DEG for check z of a codeword pair.  Record layout (uint4; three words
@@ -212,7 +215,7 @@ __device__ __forceinline__ void row_gather_h2(const Lane &l, const uint2 *__rest
 
 // second half: new messages, APP write-back, the row's new record
 template <int DEG, bool IDENT_LAST, bool PAR>
-__device__ __forceinline__ uint4 row_scatter_h2_par(const RowStateH2<DEG> &s, const uint32_t alpha2, uint32_t &par) {
+__device__ __forceinline__ uint4 row_scatter_h2_par(const RowStateH2<DEG> &s, const uint32_t alpha2, uint32_t &par, const bool live = true) {
     constexpr int NE = IDENT_LAST ? DEG - 1 : DEG;
     constexpr int N0 = NE < 16 ? NE : 16;
     constexpr int N1 = NE - N0;
@@ -236,7 +239,7 @@ __device__ __forceinline__ uint4 row_scatter_h2_par(const RowStateH2<DEG> &s, co
         const uint32_t c = sel ^ (s.t[e] & kH2Sign);
         const uint32_t app = as_u32(__hadd2(as_h2(s.t[e]), as_h2(c)));
         if (PAR) par ^= app;   // sign bits (15 / 31) = parities of this check on the hard decisions just written
-        sts_u32(s.addr[e], app);
+        if (live) sts_u32(s.addr[e], app);
     }
     if (PAR && IDENT_LAST) {   // the degree-1 variable's a-posteriori value takes part in the check's parity only
         const uint32_t tp = s.t[DEG - 1];
@@ -250,17 +253,17 @@ __device__ __forceinline__ uint4 row_scatter_h2_par(const RowStateH2<DEG> &s, co
     return make_uint4(m1ss, m2ss, z, w);
 }
 template <int DEG, bool IDENT_LAST>
-__device__ __forceinline__ uint4 row_scatter_h2(const RowStateH2<DEG> &s, const uint32_t alpha2) {
+__device__ __forceinline__ uint4 row_scatter_h2(const RowStateH2<DEG> &s, const uint32_t alpha2, const bool live = true) {
     uint32_t unused = 0;
-    return row_scatter_h2_par<DEG, IDENT_LAST, false>(s, alpha2, unused);
+    return row_scatter_h2_par<DEG, IDENT_LAST, false>(s, alpha2, unused, live);
 }
 
 template <int DEG, bool IDENT_LAST, bool ONE_CW>
 __device__ __forceinline__ uint4 process_row_h2(const Lane &l, const uint2 *__restrict__ ed, const uint4 rec,
-                                                const uint32_t alpha2) {
+                                                const uint32_t alpha2, const bool live = true) {
     RowStateH2<DEG> s;
     row_gather_h2<DEG, IDENT_LAST, ONE_CW>(l, ed, rec, s);
-    return row_scatter_h2<DEG, IDENT_LAST>(s, alpha2);
+    return row_scatter_h2<DEG, IDENT_LAST>(s, alpha2, live);
 }
 
 // ---- pieces of the pair kernel ---------------------------------------------------------------------
@@ -270,6 +273,7 @@ struct DecCtxH2 {
     uint64_t pol;
     uint4 cur, cur2;   // prefetched records of the next layer (and of its partner when the next layer is a row pair)
     bool done;   // this thread does no row work (inactive lane, or both codewords of its pair are finished)
+    bool live;   // MASKED kernels: this lane owns a check (tid < Z), see decode_kernel.cuh
     uint32_t last_fail;   // FULL, every base row active: bit 15 / 31 = codeword A / B has an unsatisfied check in the last layer
 };
 
@@ -345,7 +349,7 @@ __device__ __forceinline__ uint32_t syndrome_fail_h2(const DecArgs &a, const Dec
 // Layer loop, unrolled per base graph.  As in decode_kernel.cuh: ld_from / ld_to gate the prefetch of the next
 // layer's record, and two consecutive base rows that touch disjoint block columns (pair_first<BG>) run as one layer
 // with one barrier.  Row pairs only occur among rows of degree <= 11, i.e. with three-word records.
-template <int BG, int R, bool FULL>
+template <int BG, int R, bool FULL, bool MASKED = false>
 struct UnrolledRowsH2 {
     static __device__ __forceinline__ void run(const DecArgs &a, DecCtxH2 &c, const int ld_from, const int ld_to, const bool store_rec) {
         if (R >= 4 && R >= a.n_rows) return;   // n_rows >= 4 is validated by the host
@@ -369,9 +373,9 @@ struct UnrolledRowsH2 {
                 RowStateH2<DEG2> s1;
                 row_gather_h2<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur, s0);
                 row_gather_h2<DEG2, (R >= 4), FULL>(c.l, a.ed + E1, c.cur2, s1);
-                const uint4 rec0 = row_scatter_h2_par<DEG, (R >= 4), kLastPair>(s0, a.alpha_h2, par);
-                const uint4 rec1 = row_scatter_h2_par<DEG2, (R >= 4), kLastPair>(s1, a.alpha_h2, par);
-                if (store_rec) {
+                const uint4 rec0 = row_scatter_h2_par<DEG, (R >= 4), kLastPair>(s0, a.alpha_h2, par, !MASKED || c.live);
+                const uint4 rec1 = row_scatter_h2_par<DEG2, (R >= 4), kLastPair>(s1, a.alpha_h2, par, !MASKED || c.live);
+                if (store_rec && (!MASKED || c.live)) {
                     st_rec(c.my_rec, R, rec0, c.pol);
                     st_rec(c.my_rec, R + 1, rec1, c.pol);
                 }
@@ -381,13 +385,14 @@ struct UnrolledRowsH2 {
             // last layer of an iteration with every base row active: its hard decisions are final, the barrier doubles as
             // the CTA-wide OR of its parities (see decode_kernel.cuh); one reduction per codeword of the pair
             if (kLastPair) {
+                if (MASKED && !c.live) par = 0u;
                 const int fa = __syncthreads_or((int)((par >> 15) & 1u));
                 const int fb = __syncthreads_or((int)(par >> 31));
                 c.last_fail = (fa ? 0x00008000u : 0u) | (fb ? 0x80000000u : 0u);
             } else {
                 __syncthreads();
             }
-            UnrolledRowsH2<BG, (PAIR ? R + 2 : BgShape<BG>::kRows), FULL>::run(a, c, ld_from, ld_to, store_rec);
+            UnrolledRowsH2<BG, (PAIR ? R + 2 : BgShape<BG>::kRows), FULL, MASKED>::run(a, c, ld_from, ld_to, store_rec);
         } else {
             if (FULL || !c.done) {
                 constexpr bool kNextW4 = R + 1 < BgShape<BG>::kRows && BgShape<BG>::deg(R + 1 < BgShape<BG>::kRows ? R + 1 : R) > 11;
@@ -399,8 +404,8 @@ struct UnrolledRowsH2 {
                 }
                 // layer 0's 4th word is not prefetched across the iteration boundary: fetch it on entry
                 if (R == 0 && kW4 && (ld_from == 0)) c.cur.w = ld_word(w4, c.pol);
-                const uint4 rec = process_row_h2<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur, a.alpha_h2);
-                if (store_rec) {
+                const uint4 rec = process_row_h2<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur, a.alpha_h2, !MASKED || c.live);
+                if (store_rec && (!MASKED || c.live)) {
                     st_rec(c.my_rec, R == 0 ? a.n_rows : R, rec, c.pol);
                     if (kW4) st_word(w4 + R * kRecStride, rec.w, c.pol);
                 }
@@ -408,12 +413,12 @@ struct UnrolledRowsH2 {
                 c.cur2 = nxt2;
             }
             __syncthreads();
-            if (!PAIR) UnrolledRowsH2<BG, R + 1, FULL>::run(a, c, ld_from, ld_to, store_rec);
+            if (!PAIR) UnrolledRowsH2<BG, R + 1, FULL, MASKED>::run(a, c, ld_from, ld_to, store_rec);
         }
     }
 };
-template <int BG, bool FULL>
-struct UnrolledRowsH2<BG, BgShape<BG>::kRows, FULL> {
+template <int BG, bool FULL, bool MASKED>
+struct UnrolledRowsH2<BG, BgShape<BG>::kRows, FULL, MASKED> {
     static __device__ __forceinline__ void run(const DecArgs &, DecCtxH2 &, int, int, bool) {}
 };
 
@@ -424,8 +429,9 @@ __device__ __forceinline__ uint32_t h2_hard_bits(int *s_flag, int cwpc) {
 }
 
 // Here cwpc counts codeword PAIRS per CTA; FULL = one pair per CTA and every thread owns a check.
-template <int BG, bool FULL>
+template <int BG, bool FULL, bool MASKED = false>
 __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kernel(const __grid_constant__ DecArgs a) {
+    static_assert(FULL || !MASKED, "MASKED is a flavour of the one-pair (FULL) kernels");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Z = a.Z;
     const int ncw = a.ncols * Z;
@@ -436,7 +442,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
     int *s_flag = reinterpret_cast<int *>(app + (size_t)a.cwpc * a.slot_stride);
     int &s_group = s_flag[4 * a.cwpc];
     if ((uint32_t)__cvta_generic_to_shared(smem_raw) != a.smem_base) __trap();
-    const bool bitsliced = FULL && a.n_rows >= a.bitsliced_min_rows;
+    const bool bitsliced = FULL && !MASKED && a.n_rows >= a.bitsliced_min_rows;
     if (bitsliced && (a.early_term || a.ok != nullptr))   // ordered by the barriers below
         fill_syndrome_edges(a, h2_hard_bits(s_flag, a.cwpc) + (uint32_t)(a.ncols * (Z >> 5)) * 8u);
 
@@ -454,8 +460,9 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
     c.l.nZ4 = 0u - (uint32_t)Z * 4u;
     c.l.slot_off = FULL ? 0u : (uint32_t)(slot * a.slot_stride) * 4u;
     c.l.one = (uint32_t)a.one;
-    c.my_rec = a.c2v + (size_t)blockIdx.x * (kRecWords * kRecStride) + tid;
+    c.my_rec = a.c2v + (size_t)(blockIdx.x / a.rec_group) * (kRecWords * kRecStride) + (blockIdx.x % a.rec_group) * blockDim.x + tid;
     c.pol = make_l2_policy(a.l2_pin);
+    c.live = tid < Z;
     uint32_t *my_app = app + (size_t)(lane_ok ? slot : 0) * a.slot_stride;
 
     while (true) {
@@ -483,16 +490,16 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
         for (int it = 0; it < a.max_iters; ++it) {
             const bool first = it == 0, last = it + 1 == a.max_iters;
             c.last_fail = 0u;   // set by the last layer when every base row is active
-            UnrolledRowsH2<BG, 0, FULL>::run(a, c, first ? a.n_rows - 1 : 0, last ? a.n_rows - 1 : a.n_rows, !last || keep_last);
+            UnrolledRowsH2<BG, 0, FULL, MASKED>::run(a, c, first ? a.n_rows - 1 : 0, last ? a.n_rows - 1 : a.n_rows, !last || keep_last);
             if (!fin_a) it_a = it + 1;
             if (!fin_b) it_b = it + 1;
             if (a.early_term || (want_ok && last)) {
                 uint32_t fu = 0;   // bit 15: codeword A fails, bit 31: B fails
-                if (FULL && bitsliced) {
+                if (FULL && !MASKED && bitsliced) {
                     // codewords with an unsatisfied check in the last layer have not converged; the syndrome runs only if
                     // a live codeword of the pair is still undecided (it is exact for both)
                     if (a.n_rows < BgShape<BG>::kRows) {   // trimmed row count: re-read the last active row (see decode_kernel.cuh)
-                        const uint32_t par = last_row_parity(a, c.l, c.my_rec, c.pol, ExtAppH2());
+                        const uint32_t par = last_row_parity(a, c.l, make_uint4(0u, 0u, 0u, 0u), ExtAppH2{c.my_rec, a.n_rows - 1, c.pol});
                         const int fa = __syncthreads_or((int)((par >> 15) & 1u));
                         const int fb = __syncthreads_or((int)(par >> 31));
                         c.last_fail = (fa ? 0x00008000u : 0u) | (fb ? 0x80000000u : 0u);

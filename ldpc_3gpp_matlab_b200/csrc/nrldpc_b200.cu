@@ -110,6 +110,11 @@ struct nrldpc_handle {
     // codeword (NRLDPCDecoder.m:265), so no launcher may pay a runtime query per call
     struct OccEntry { const void *kern; int threads; size_t smem; int occ; };
     std::vector<OccEntry> occ_cache;
+    int cwpc = 1;                    // codewords (pairs) per decode CTA, chosen at create (choose_decode_cwpc)
+    int cwpc_override = 0;           // NRLDPC_CWPC (experiments)
+    int occ_cap = 4;                 // resident decode CTAs per SM are capped here (NRLDPC_OCC_CAP)
+    int shape_model = 1;             // NRLDPC_SHAPE_MODEL=0: the default rule only (ignore the measured shape table)
+    int occ_cap_forced = 0;
     int grid_cap = 0;                // NRLDPC_GRID_CAP (experiments), read once at create
     int no_tma = 0;                  // NRLDPC_NO_TMA
     cudaStream_t last_dev_stream = nullptr;  // stream of the last NRLDPC_MEM_DEVICE decode (its scratch is shared)
@@ -215,27 +220,58 @@ BgView bg_view(int bg) {
 // collide in the shared-memory banks (BG1, Z = 8: stride 544 = 0 mod 32, four slots per warp -> 4-way conflicts; ncu:
 // shared-memory wavefronts at 74 % of peak, ALU pipe at 59 %).  With stride = Z (mod 32) the banks of a warp follow the
 // lane index through every circulant rotation, so whole slots never collide.
-int decode_slot_stride(int cols, int Z) {
+int decode_slot_stride(int cols, int Z, int cwpc) {
     const int ncw = cols * Z;
-    if (Z >= nrldpc::kDecThreads / 2 + 1) return ncw;   // one codeword per CTA
+    if (cwpc == 1) return ncw;   // one codeword per CTA
     return ncw + (((Z - ncw) % 32) + 32) % 32;
 }
-// Codewords (pairs) per CTA: as many as fit in 384 threads, and in the shared memory two CTAs per SM can have.
-int decode_cwpc(int cols, int Z) {
-    const int by_threads = std::max(1, nrldpc::kDecThreads / Z);
-    const int by_smem = std::max(1, (108 * 1024 / 4) / decode_slot_stride(cols, Z));
-    return std::min(by_threads, by_smem);
-}
-int decode_threads(int cols, int Z) { return std::max(32, (decode_cwpc(cols, Z) * Z + 31) / 32 * 32); }
+int decode_threads_for(int cwpc, int Z) { return std::max(32, (cwpc * Z + 31) / 32 * 32); }
 
-size_t decode_smem_bytes(const nrldpc_handle *h, int n_rows) {
-    const int cwpc = decode_cwpc(h->d.cols, h->d.Z);
-    (void)n_rows;
+size_t decode_smem_for(const nrldpc_dims &d, int cwpc) {
     // APP arrays, syndrome flags of both stages (float32: [2][cwpc], packed half: [2][2*cwpc]) + work slot, mbarrier, and
     // (one codeword per CTA, Z a multiple of 32) the packed hard decisions of the bit-sliced syndrome -- two words per
     // (column, warp) cover the float32 and the packed-half kernel -- followed by its lane-indexed edge table
-    const size_t hb = (cwpc == 1 && h->d.Z % 32 == 0) ? (size_t)h->d.cols * (h->d.Z / 32) * 8 + (size_t)h->d.edges * 4 : 0;
-    return (size_t)cwpc * decode_slot_stride(h->d.cols, h->d.Z) * 4 + (size_t)(4 * cwpc + 1) * 4 + 16 + hb;
+    const size_t hb = (cwpc == 1 && d.Z % 32 == 0) ? (size_t)d.cols * (d.Z / 32) * 8 + (size_t)d.edges * 4 : 0;
+    return (size_t)cwpc * decode_slot_stride(d.cols, d.Z, cwpc) * 4 + (size_t)(4 * cwpc + 1) * 4 + 16 + hb;
+}
+
+// CTA shape of the decode kernels: codewords (float32) or codeword pairs (packed half) per CTA and the cap on resident
+// CTAs per SM.  Default rule: as many codewords as fit in 384 threads (and in the shared memory of two CTAs per SM), at
+// most 4 CTAs per SM.  Where the B200 scan (tools/gpu_shape_scan.py -> decode_shapes.inc) measured another shape at least
+// 2 % faster, that shape is used.  What the scan showed (profiles/r02_shape_scan_*.jsonl):
+//   * warps are bound to the SM's four schedulers by (warp index in the CTA) mod 4: Z = 224 (three 7-warp CTAs per SM)
+//     runs at exactly 7/8 of the Z = 384 rate per lane, so CTAs of 4k warps are preferred when lanes are not wasted;
+//   * many narrow one-codeword CTAs per SM lose on base graph 1 (BG1 Z = 128: 6 x 4 warps 8.4 Gb/s against 2 x 12 warps
+//     10.5): the CTAs de-phase and each needs its own pass through the ~100 KB unrolled layer loop (instruction
+//     fetch); on base graph 2 (66 KB loop) the same shape wins (Z = 128: 13.2 against 11.8 Gb/s).
+// Every shape is bit-identical (the scan checks it; tests/test_gpu_parity.py runs forced shapes).
+#include "decode_shapes.inc"
+int lifting_index(int Z) {
+    int idx = 0;
+    for (int z = 2; z <= 384; ++z) {
+        bool valid = false;
+        for (int s = 0; s < 8 && !valid; ++s)
+            for (int j = 0; j < kSetN[s]; ++j) valid = valid || (kSetA[s] << j) == z;
+        if (!valid) continue;
+        if (z == Z) return idx;
+        ++idx;
+    }
+    return -1;
+}
+void choose_decode_shape(nrldpc_handle *h) {
+    const nrldpc_dims &d = h->d;
+    const int cmax = std::max(1, nrldpc::kDecThreads / d.Z);
+    const int legacy = std::min(cmax, std::max(1, (108 * 1024 / 4) / decode_slot_stride(d.cols, d.Z, 2)));
+    h->cwpc = legacy;
+    if (h->shape_model) {
+        const int zi = lifting_index(d.Z);
+        const unsigned char *e = nrldpc_decode_shape[h->cfg.llr_dtype == NRLDPC_F16X2 ? 1 : 0][d.bg - 1][zi < 0 ? 0 : zi];
+        if (zi >= 0 && e[0] > 0 && e[0] <= cmax && decode_smem_for(d, e[0]) <= 227 * 1024) {
+            h->cwpc = e[0];
+            if (!h->occ_cap_forced) h->occ_cap = e[1];
+        }
+    }
+    if (h->cwpc_override > 0) h->cwpc = std::min(h->cwpc_override, cmax);
 }
 
 int ensure_scratch(nrldpc_handle *h, PipeSlot &s, size_t recs) {
@@ -254,39 +290,44 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
     const int Z = h->d.Z;
     const bool h2 = h->cfg.llr_dtype == NRLDPC_F16X2;
     // cwpc: codewords (float32) or codeword pairs (packed half) resident per CTA
-    const int cwpc = decode_cwpc(h->d.cols, Z), threads = decode_threads(h->d.cols, Z);
+    const int cwpc = h->cwpc, threads = decode_threads_for(cwpc, Z);
     const int per_group = h2 ? 2 * cwpc : cwpc;
     const int64_t n_groups = (batch + per_group - 1) / per_group;
-    const size_t smem = decode_smem_bytes(h, n_rows);
+    const size_t smem = decode_smem_for(h->d, cwpc);
+    (void)n_rows;
     // variant 0: generic looped layers (float32 only); otherwise the layer loop is unrolled for the base graph.
-    // FULL: one codeword (pair) per CTA and every thread owns a check (Z a multiple of the warp size)
+    // FULL: one codeword (pair) per CTA, CTA-uniform code; MASKED: the same with a partially filled last warp (Z not a
+    // multiple of 32), stores predicated on the lane
     using Kern = void (*)(const nrldpc::DecArgs);
-    const bool full = cwpc == 1 && threads == Z;
+    const bool full = cwpc == 1, masked = full && threads != Z;
     const bool bg1 = h->d.bg == 1;
     Kern kern;
     if (h2)
-        kern = bg1 ? (full ? (Kern)nrldpc::decode_nms_h2_kernel<1, true> : (Kern)nrldpc::decode_nms_h2_kernel<1, false>)
-                   : (full ? (Kern)nrldpc::decode_nms_h2_kernel<2, true> : (Kern)nrldpc::decode_nms_h2_kernel<2, false>);
+        kern = bg1 ? (masked ? (Kern)nrldpc::decode_nms_h2_kernel<1, true, true> : full ? (Kern)nrldpc::decode_nms_h2_kernel<1, true> : (Kern)nrldpc::decode_nms_h2_kernel<1, false>)
+                   : (masked ? (Kern)nrldpc::decode_nms_h2_kernel<2, true, true> : full ? (Kern)nrldpc::decode_nms_h2_kernel<2, true> : (Kern)nrldpc::decode_nms_h2_kernel<2, false>);
     else if (h->dec_variant == 0)
         kern = (Kern)nrldpc::decode_nms_kernel<0, false>;
     else
-        kern = bg1 ? (full ? (Kern)nrldpc::decode_nms_kernel<1, true> : (Kern)nrldpc::decode_nms_kernel<1, false>)
-                   : (full ? (Kern)nrldpc::decode_nms_kernel<2, true> : (Kern)nrldpc::decode_nms_kernel<2, false>);
+        kern = bg1 ? (masked ? (Kern)nrldpc::decode_nms_kernel<1, true, true> : full ? (Kern)nrldpc::decode_nms_kernel<1, true> : (Kern)nrldpc::decode_nms_kernel<1, false>)
+                   : (masked ? (Kern)nrldpc::decode_nms_kernel<2, true, true> : full ? (Kern)nrldpc::decode_nms_kernel<2, true> : (Kern)nrldpc::decode_nms_kernel<2, false>);
     // persistent grid: every SM filled to its occupancy (2 CTAs of 384 threads at Z = 384, more for narrower CTAs);
     // attribute and occupancy are looked up once per (kernel, CTA width, shared-memory size)
     int occ = 1;
     if (int rc = cached_occupancy(h, reinterpret_cast<const void *>(kern), threads, smem, &occ)) return rc;
-    occ = std::min(occ, 4);
+    occ = std::min(occ, h->occ_cap);
     int grid = (int)std::min<int64_t>(n_groups, (int64_t)h->num_sms * occ);
     if (h->grid_cap > 0) grid = std::max(1, std::min(grid, h->grid_cap));  // experiments only
-    if (int rc = ensure_scratch(h, s, (size_t)grid * nrldpc::kRecWords * nrldpc::kRecStride)) return rc;
+    // c2v scratch: [kRecWords][kRecStride = 384 thread columns] blocks; narrow CTAs share a block side by side, so the
+    // scratch stays about (threads resident on the device) x 145 words whatever the CTA width (it has to fit the L2)
+    const int rec_group = std::max(1, nrldpc::kRecStride / threads);
+    if (int rc = ensure_scratch(h, s, (size_t)((grid + rec_group - 1) / rec_group) * nrldpc::kRecWords * nrldpc::kRecStride)) return rc;
     CUDA_TRY(h, cudaMemsetAsync(s.counter, 0, sizeof(int), stream));
     nrldpc::DecArgs &a = h->dec_args;  // tables were filled at create()
     a.llr = llr; a.hard = hard; a.soft = soft; a.iters = iters; a.ok = ok;
     a.batch = batch; a.Z = Z; a.ncols = h->d.cols; a.kcols = h->d.kcols; a.n_rows = n_rows;
     a.n_edges = h->h_row_start[n_rows]; a.max_iters = h->cfg.max_iters; a.early_term = h->cfg.early_term;
-    a.slot_stride = cwpc == 1 ? h->d.n_cw : decode_slot_stride(h->d.cols, Z);
-    a.cwpc = cwpc; a.alpha = h->cfg.alpha; a.l2_pin = h->l2_pin; a.one = 1;
+    a.slot_stride = decode_slot_stride(h->d.cols, Z, cwpc);
+    a.cwpc = cwpc; a.rec_group = rec_group; a.alpha = h->cfg.alpha; a.l2_pin = h->l2_pin; a.one = 1;
     a.bitsliced_min_rows = h->bitsliced_min_rows; a.staged_min_rows = h->staged_min_rows;
     a.c2v = s.c2v; a.work_counter = s.counter;
     const uint32_t ah = __half_as_ushort(__float2half_rn(h->cfg.alpha));
@@ -613,11 +654,15 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
     if (const char *v = getenv("NRLDPC_GRID_CAP")) h->grid_cap = std::max(0, atoi(v));
     if (getenv("NRLDPC_NO_TMA")) h->no_tma = 1;
     if (getenv("NRLDPC_NO_STAGING")) h->no_staging = 1;
+    if (const char *v = getenv("NRLDPC_CWPC")) h->cwpc_override = std::max(0, atoi(v));
+    if (const char *v = getenv("NRLDPC_OCC_CAP")) { h->occ_cap = std::max(1, std::min(16, atoi(v))); h->occ_cap_forced = 1; }
+    if (const char *v = getenv("NRLDPC_SHAPE_MODEL")) h->shape_model = atoi(v) ? 1 : 0;
     h->host_threads = nrldpc::default_host_threads();
 
     const BgView v = bg_view(cfg->bg);
     const int Z = cfg->Z;
     h->d = nrldpc_dims{cfg->bg, Z, ils, v.rows, v.cols, v.kcols, v.edges, v.kcols * Z, (v.cols - 2) * Z, v.cols * Z};
+    choose_decode_shape(h);
     std::vector<uint32_t> ed(v.edges);
     for (int r = 0, e = 0; r <= v.rows; ++r) {
         while (e < v.edges && v.row[e] < r) ++e;
@@ -828,7 +873,7 @@ int decode_impl(nrldpc_t *h, const void *llr, int in_kind, int64_t batch, int32_
     // persistent-grid wave of codewords (doubled while small) so the un-overlapped tail stays short.
     if (int rc = ensure_pipe(h)) return rc;
     if (h->dev_used) CUDA_TRY(h, cudaStreamWaitEvent(h->pipe[0].stream, h->dev_done, 0));
-    const int cwpc = decode_cwpc(h->d.cols, h->d.Z);
+    const int cwpc = h->cwpc;
     const int64_t wave = bp ? (int64_t)h->num_sms
                             : (int64_t)h->num_sms * nrldpc::kDecCtasPerSm * cwpc *
                                   (h->cfg.llr_dtype == NRLDPC_F16X2 ? 2 : 1);  // codewords per full grid

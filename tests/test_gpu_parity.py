@@ -716,3 +716,28 @@ def test_decode64_pageable_host_path(capi, O, bg, Z, B):
     assert (a["hard"] == b["hard"]).all() and (a["iters"] == b["iters"]).all() and (a["parity_ok"] == b["parity_ok"]).all()
     # a payload-level property at full size: nearly every block decodes at this SNR
     assert (a["hard"] != info).any(axis=1).mean() < 0.05
+
+
+@pytest.mark.parametrize("f16", [False, True])
+def test_forced_cta_shapes_are_bit_identical(capi, O, f16, monkeypatch):
+    """Every CTA shape the library may pick (codewords per CTA, resident CTAs per SM: decode_shapes.inc) is the same
+    arithmetic: forced shapes -- one codeword per CTA with a partially filled last warp (the lane-masked CTA-uniform
+    kernel), narrow CTAs sharing a scratch block, eight CTAs per SM -- against the oracle, fixed iterations and the
+    parity-check stop, trimmed rows, soft output."""
+    rng = np.random.default_rng(31)
+    for bg, Z, rows in ((1, 52, 46), (2, 52, 33), (1, 208, 46), (2, 240, 20), (1, 20, 46), (2, 112, 42)):
+        d = O.dims(bg, Z)
+        B = 2 * max(3, 600 // Z) + 1
+        info, llr = make_llr(O, bg, Z, B, (d["kcols"] - 2 + rows) * Z, rng.uniform(0.0, 2.5), rng, filler=Z)
+        for et in (False, True):
+            ref = O.decode_nms(bg, Z, llr, 6, early_term=et, n_rows=rows, f16=f16)
+            for cw, cap in ((1, 8), (1, 2), (2, 4), (max(1, 384 // Z), 4), (max(1, 128 // Z), 8)):
+                if cw > max(1, 384 // Z):
+                    continue
+                monkeypatch.setenv("NRLDPC_CWPC", str(cw))
+                monkeypatch.setenv("NRLDPC_OCC_CAP", str(cap))
+                h = capi.Handle(bg, Z, 6, et, llr_dtype=capi.F16X2 if f16 else capi.F32)
+                out = h.decode(llr, n_rows=rows, want_soft=True)
+                h.close()
+                assert (out["hard"] == ref["hard"]).all() and _same_bits(out["app"], ref["app"]), (bg, Z, et, cw, cap)
+                assert (out["iters"] == ref["iters"]).all() and (out["parity_ok"] == ref["parity_ok"]).all(), (bg, Z, et, cw, cap)
