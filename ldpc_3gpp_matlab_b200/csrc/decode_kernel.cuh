@@ -39,8 +39,12 @@
 
 namespace nrldpc {
 
-constexpr int kDecThreads = 384;     // max threads per decode CTA (= largest lifting size)
-constexpr int kDecCtasPerSm = 2;
+#ifndef NRLDPC_DEC_THREADS           // build-time experiment knobs (make EXTRA="-DNRLDPC_DEC_THREADS=768 -DNRLDPC_DEC_CTAS=1")
+#define NRLDPC_DEC_THREADS 384
+#define NRLDPC_DEC_CTAS 2
+#endif
+constexpr int kDecThreads = NRLDPC_DEC_THREADS;     // max threads per decode CTA (= largest lifting size)
+constexpr int kDecCtasPerSm = NRLDPC_DEC_CTAS;
 constexpr float kLlrMax = 1048576.0f;
 constexpr int kMaxEdges = 316;
 constexpr int kMaxRows = 46;

@@ -121,6 +121,7 @@ struct nrldpc_handle {
     bool dev_used = false;
     nrldpc::HostPool *pool = nullptr;        // worker threads of the staged host path (created on first use)
     int host_threads = 0;
+    long long l2_window = 0;                 // bytes of the persisting access-policy window over the c2v scratch (0: none; NRLDPC_L2_WINDOW=0/1)
     int no_staging = 0;                      // NRLDPC_NO_STAGING=1: hand pageable buffers to cudaMemcpyAsync as they are (A/B)
     int bp_threads = 1024;           // CTA width of the sum-product kernel (NRLDPC_BP_THREADS=512 selects the 128-register build)
 };
@@ -261,7 +262,7 @@ int lifting_index(int Z) {
 void choose_decode_shape(nrldpc_handle *h) {
     const nrldpc_dims &d = h->d;
     const int cmax = std::max(1, nrldpc::kDecThreads / d.Z);
-    const int legacy = std::min(cmax, std::max(1, (108 * 1024 / 4) / decode_slot_stride(d.cols, d.Z, 2)));
+    const int legacy = std::min(cmax, std::max(1, (216 * 1024 / nrldpc::kDecCtasPerSm / 4) / decode_slot_stride(d.cols, d.Z, 2)));
     h->cwpc = legacy;
     if (h->shape_model) {
         const int zi = lifting_index(d.Z);
@@ -336,7 +337,24 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
         for (int e = 0; e < h->d.edges; ++e) a.ed[e].y += h->smem_base - a.smem_base;
         a.smem_base = h->smem_base;
     }
-    kern<<<grid, threads, smem, stream>>>(a);
+    if (h->l2_window > 0) {
+        // the c2v scratch also gets a persisting access-policy window for this launch: lines of the window go to the L2's
+        // persisting set-aside (sized at create), which the streamed LLR input cannot claim -- the evict_last hints
+        // alone still let 3-5 % of the record stores leak out to HBM (profiles/r01_v7_dram_f16x2.csv)
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = s.c2v;
+        attr[0].val.accessPolicyWindow.num_bytes = std::min<size_t>(s.scratch_recs * sizeof(uint32_t), (size_t)h->l2_window);
+        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        CUDA_TRY(h, cudaLaunchKernelEx(&cfg, kern, a));
+    } else {
+        kern<<<grid, threads, smem, stream>>>(a);
+    }
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
     return 0;
@@ -646,6 +664,17 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
         return fail(nullptr, NRLDPC_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", dev, prop.major, prop.minor);
     }
     h->num_sms = prop.multiProcessorCount;
+    {
+        // persisting L2 set-aside for the c2v scratch (a device-wide limit: it is only ever raised, never lowered)
+        const char *v = getenv("NRLDPC_L2_WINDOW");
+        if (!(v && atoi(v) == 0) && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+            size_t cur = 0;
+            cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize);
+            if (cur < (size_t)prop.persistingL2CacheMaxSize) cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, prop.persistingL2CacheMaxSize);
+            cudaGetLastError();
+            h->l2_window = std::min<long long>(prop.persistingL2CacheMaxSize, prop.accessPolicyMaxWindowSize);
+        }
+    }
     if (const char *v = getenv("NRLDPC_DECODE_VARIANT")) h->dec_variant = strcmp(v, "loop") == 0 ? 0 : 1;
     if (const char *v = getenv("NRLDPC_L2_PIN")) h->l2_pin = atoi(v) ? 1 : 0;
     if (const char *v = getenv("NRLDPC_BITSLICED_MIN_ROWS")) h->bitsliced_min_rows = std::max(4, atoi(v));
