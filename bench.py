@@ -45,6 +45,8 @@ WORKLOADS = {
     "bg1_z384_r13_it8_b16384": dict(bg=1, Z=384, E=25272, n_rows=46, iters=8, early_term=0, batch=16384, esn0=-0.3, filler=0),
     "bg1_z384_r13_it8et_b16384": dict(bg=1, Z=384, E=25272, n_rows=46, iters=8, early_term=1, batch=16384, esn0=-0.3, filler=0),
     "bg2_z52_r15_it8et_b65536": dict(bg=2, Z=52, E=2000, n_rows=33, iters=8, early_term=1, batch=65536, esn0=-2.0, filler=104),
+    # config 3 with the stop armed but never taken (nothing converges at -6 dB): 8 iterations + 8 failing syndromes per block
+    "bg2_z52_r15_it8et_lowsnr_b65536": dict(bg=2, Z=52, E=2000, n_rows=33, iters=8, early_term=1, batch=65536, esn0=-6.0, filler=104),
     "bg1_z384_r89_it20et_b4096": dict(bg=1, Z=384, E=9478, n_rows=5, iters=20, early_term=1, batch=4096, esn0=6.3, filler=0),
 }
 DEFAULT_WORKLOAD = "bg1_z384_r13_it8_b4096"
@@ -390,6 +392,7 @@ def main():
     torch.cuda.synchronize()
     bler = float((hard != info).any(dim=1).float().mean())
     mean_iters = float(iters_t.float().mean()) if w["early_term"] else float(w["iters"])
+    iters_hist = torch.bincount(iters_t, minlength=w["iters"] + 1).tolist() if w["early_term"] else None
 
     # ---- timed region: K steps, CUDA events on the launching stream, barrier + sync both sides ----
     sampler = ClockSampler(local_rank if "CUDA_VISIBLE_DEVICES" not in os.environ else
@@ -603,7 +606,7 @@ def main():
                        "rate": round(K / w["E"], 4), "n_rows": w["n_rows"], "iters": w["iters"], "early_term": w["early_term"],
                        "alpha": 0.75, "algorithm": "layered normalized min-sum", "batch_per_gpu": B,
                        "global_batch": B * world, "parallelism": f"dp{world} (independent codeword shards, no data-path collective)",
-                       "esn0_db": w["esn0"], "bler_at_esn0": bler, "mean_iters": mean_iters,
+                       "esn0_db": w["esn0"], "bler_at_esn0": bler, "mean_iters": mean_iters, "iters_hist": iters_hist,
                        "l2": f"inputs larger than L2 ({B * h.n_cw * 4 / 2**20:.0f} MiB LLRs per step vs 126 MB L2)"},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
         }

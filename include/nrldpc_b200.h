@@ -168,6 +168,13 @@ int nrldpc_qpsk_awgn_llr(nrldpc_t *h, const uint8_t *f_bits, int64_t batch, int3
                          float variance, uint64_t seed, uint64_t stream_id, float *f_llr,
                          void *stream);
 
+/* The same channel leg fused into rate recovery: f_bits [batch][E] -> decoder input llr_cw [batch][n_cw] (and the HARQ
+ * buffer), bit-identical to nrldpc_qpsk_awgn_llr followed by nrldpc_rate_recover with the same (seed, stream_id), without
+ * the E received LLRs of every block going through HBM (plot_BLER_vs_SNR.m:130-133 up to NRLDPCDecoder's
+ * bit_selection, :200-242).  QPSK (rm->Q_m = 2), E % 4 == 0, E floats must fit in shared memory.  Device memory only. */
+int nrldpc_qpsk_awgn_rate_recover(nrldpc_t *h, const uint8_t *f_bits, int64_t batch, const nrldpc_rm *rm, float variance,
+                                  uint64_t seed, uint64_t stream_id, float *harq, float *llr_cw, void *stream);
+
 /* ---- channel leg for every modulation of the reference (device memory only) --------------------
  * Q_m = 1, 2, 4, 6, 8 <-> 'BPSK', 'QPSK', '16QAM', '64QAM', '256QAM' (NRModulator.m:47-63); bits are taken
  * Q_m at a time, first bit = b0 of TS 38.211 section 5.1; symbols are interleaved (re, im) float32 pairs.
@@ -200,6 +207,19 @@ int nrldpc_mod_awgn_llr(nrldpc_t *h, const uint8_t *bits, int64_t n_bits, int32_
 #define NRLDPC_CRC24B 2
 int nrldpc_crc(nrldpc_t *h, const uint8_t *bits, int64_t batch, int32_t n_bits, int64_t stride, int32_t kind,
                uint8_t *parity, int64_t parity_stride, uint8_t *ok, void *stream);
+
+/* ---- block-error bookkeeping of the Monte-Carlo loop on device (plot_BLER_vs_SNR.m:139-155; a_hat = [] unless the CRCs
+ * pass, NRLDPCDecoder.m:296-309,336-339; a block error is ~isequal(a, a_hat)), one decoding attempt of n_tb transport
+ * blocks of C code blocks each.  All buffers are device memory.
+ *   do_latch: ok = tb_ok[b] && all cb_passed[b*C..] (NULL: C = 1) && tb_hat[b][0:A] == tb[b][0:A]; latch[b] |= ok;
+ *             counters[3] += iterations of the attempt's C decodes (iters [n_tb*C])
+ *   finalize: counters[0] += 1; counters[1] += !latch[b]; counters[2] += wrong bits among the first K_prime bits of the C
+ *             decoded blocks (hard vs info, both [n_tb*C][K]) of a transport block in error
+ *   counters  [4] uint64: {blocks, block errors, bit errors, iterations}: what the ranks sum with one all-reduce */
+int nrldpc_bler_count(nrldpc_t *h, const uint8_t *hard, const uint8_t *info, const uint8_t *tb_hat, int64_t tb_hat_stride,
+                      const uint8_t *tb, int64_t tb_stride, const uint8_t *tb_ok, const uint8_t *cb_passed, const int32_t *iters,
+                      int64_t n_tb, int32_t C, int32_t K_prime, int32_t A, uint8_t *latch, uint64_t *counters, int32_t do_latch,
+                      int32_t finalize, void *stream);
 
 /* Pinned host allocations for callers that want truly asynchronous NRLDPC_MEM_HOST transfers. */
 void *nrldpc_host_alloc(uint64_t bytes);

@@ -89,93 +89,126 @@ class BlerSimulator:
         self.tb_flag = torch.zeros(self.B, dtype=torch.uint8, device=dev)
         self.f = torch.empty((self.B, Emax), dtype=torch.uint8, device=dev)
         self.fl = torch.empty((self.B, Emax), dtype=torch.float32, device=dev)
+        self.counters = torch.zeros(4, dtype=torch.int64, device=dev)      # blocks, block errors, bit errors, iterations
+        self.latch = torch.zeros(self.B, dtype=torch.uint8, device=dev)    # block decoded by some transmission so far
+        self.cb_passed = torch.zeros(n, dtype=torch.uint8, device=dev)     # code_block_CRC_passed (NRLDPCDecoder.m:93)
 
     def close(self):
         self.h.close()
 
+    def _channel_and_recover(self, f, E, rm, var, harq, llr_out, st):
+        """f bits [B][E] -> decoder input llr_out [B][n_cw] (+ HARQ accumulate): modulate, AWGN, demodulate
+        (plot_BLER_vs_SNR.m:130-132) and rate recovery (NRLDPCDecoder.m:172-242).  QPSK with the exact LLR runs as ONE kernel
+        (nrldpc_qpsk_awgn_rate_recover): the received LLRs never go through HBM; bit-identical to the separate stages."""
+        h, B = self.h, self.B
+        self.stream_id += 1
+        seed = D.rank_seed(self.seed, self.rank)
+        if self.Q_m == 2 and self.method == capi.DEMOD_LLR and E % 4 == 0 and E * 4 <= 200 * 1024 and not os.environ.get("NRLDPC_BLER_UNFUSED"):
+            h.qpsk_awgn_rate_recover_raw(f, B, rm, var, seed, self.stream_id, harq, llr_out, stream=st)
+            return
+        fl = self.fl[:, :E]
+        if E != self.fl.shape[1]:
+            fl = fl.contiguous()
+        if self.Q_m == 2 and self.method == capi.DEMOD_LLR and (B * E) % 4 == 0:
+            h.qpsk_awgn_llr_raw(f, B, E, var, seed, self.stream_id, fl, stream=st)
+        else:                                    # modulate + AWGN + demodulate fused, any NRModulator setting
+            h.mod_awgn_llr_raw(f, B * E, self.Q_m, var, self.method, seed, self.stream_id, fl, stream=st)
+        h.rate_recover_raw(fl, B, rm, harq, llr_out, mem=capi.MEM_DEVICE, stream=st)
+
     def run_batch(self, esn0_db: float):
-        """One batch of B transport blocks at Es/N0.  Returns [blocks, block_errors, bit_errors, iterations]."""
+        """One batch of B transport blocks at Es/N0.  Returns [blocks, block_errors, bit_errors, iterations].
+        Every stage is a C-ABI launch on device buffers; the block-error bookkeeping is one kernel per decoding attempt
+        (nrldpc_bler_count) with a device-side latch, and the host reads four counters once per batch."""
         torch, h, B, C = self.torch, self.h, self.B, self.C
         st = torch.cuda.current_stream().cuda_stream
         var = 10 ** (-esn0_db / 10)                      # plot_BLER_vs_SNR.m:105-106
+        A, Kp, Lcb, K = self.A, self.Kp, self.L_cb, self.K
         if self.use_crc:
-            # a -> b = [a ; TB CRC] (NRLDPCEncoder.m:70-89) -> C blocks of K'-L_cb bits + CB CRC24B (:92-124), on device
-            A, Kp, Lcb = self.A, self.Kp, self.L_cb
-            self.tb[:, :A] = torch.randint(0, 2, (B, A), dtype=torch.uint8, device="cuda", generator=self.gen)
-            h.crc_raw(self.tb, B, A, self.Bsz, self.tb_kind, parity=self.tb.data_ptr() + A, parity_stride=self.Bsz, stream=st)
-            if C == 1:
-                self.info[:, :Kp] = self.tb
-            else:
+            # a -> b = [a ; TB CRC] (NRLDPCEncoder.m:70-89) -> C blocks of K'-L_cb bits + CB CRC24B (:92-124), on device.
+            # One code block: the transport block IS the head of the code block row, so it is drawn and CRC'd in place.
+            tb, tb_stride = (self.info, K) if C == 1 else (self.tb, self.Bsz)
+            tb[:, :A] = torch.randint(0, 2, (B, A), dtype=torch.uint8, device="cuda", generator=self.gen)
+            h.crc_raw(tb, B, A, tb_stride, self.tb_kind, parity=tb.data_ptr() + A, parity_stride=tb_stride, stream=st)
+            if C > 1:
                 self.info.view(B, C, -1)[:, :, :Kp - Lcb] = self.tb.view(B, C, Kp - Lcb)
-                h.crc_raw(self.info, B * C, Kp - Lcb, self.K, capi.CRC24B, parity=self.info.data_ptr() + Kp - Lcb,
-                          parity_stride=self.K, stream=st)
+                h.crc_raw(self.info, B * C, Kp - Lcb, K, capi.CRC24B, parity=self.info.data_ptr() + Kp - Lcb,
+                          parity_stride=K, stream=st)
         else:
-            self.info[:, :self.Kp] = torch.randint(0, 2, (B * C, self.Kp), dtype=torch.uint8, device="cuda", generator=self.gen)
+            self.info[:, :Kp] = torch.randint(0, 2, (B * C, Kp), dtype=torch.uint8, device="cuda", generator=self.gen)
         h.encode_raw(self.info, B * C, self.cw, mem=capi.MEM_DEVICE, stream=st)
         if self.harq is not None:
             self.harq.zero_()                            # reset(hDec), plot_BLER_vs_SNR.m:122
-        ok_latched = torch.zeros(B, dtype=torch.bool, device="cuda")
-        cb_passed = torch.zeros((B, C), dtype=torch.bool, device="cuda")   # reset(hDec): NRLDPCDecoder.m:353-354
+        self.counters.zero_()
+        self.latch.zero_()
         if self.use_crc and C > 1:
+            self.cb_passed.zero_()                       # reset(hDec): NRLDPCDecoder.m:353-354
             self.tb_hat.zero_()
-        iters_total = 0
         # code blocks are interleaved frame-major: block r of frame b sits at row b*C + r
         cw3 = self.cw.view(B, C, -1)
         llr3 = self.llr.view(B, C, -1)
         harq3 = self.harq.view(B, C, -1) if self.harq is not None else None
-        for rv in self.rvs:                              # HARQ loop, :124-137
+        for i_rv, rv in enumerate(self.rvs):             # HARQ loop, :124-137
+            last = i_rv + 1 == len(self.rvs)
             self.p.rv_id = rv
             for r in range(C):
                 E = self.E_r[r]
-                rm = capi.Rm(E, int(self.p.k_0), int(self.p.N_cb), int(self.Kp), self.Q_m)
+                rm = capi.Rm(E, int(self.p.k_0), int(self.p.N_cb), int(Kp), self.Q_m)
                 cw_r = cw3[:, r].contiguous() if C > 1 else self.cw
-                f, fl = self.f[:, :E], self.fl[:, :E]
+                f = self.f[:, :E]
                 if E != self.f.shape[1]:
-                    f, fl = f.contiguous(), fl.contiguous()
+                    f = f.contiguous()
                 h.rate_match_raw(cw_r, B, rm, f, mem=capi.MEM_DEVICE, stream=st)
-                self.stream_id += 1
-                if self.Q_m == 2 and self.method == capi.DEMOD_LLR and (B * E) % 4 == 0:
-                    h.qpsk_awgn_llr_raw(f, B, E, var, D.rank_seed(self.seed, self.rank), self.stream_id, fl, stream=st)
-                else:                                    # modulate + AWGN + demodulate fused, any NRModulator setting
-                    h.mod_awgn_llr_raw(f, B * E, self.Q_m, var, self.method, D.rank_seed(self.seed, self.rank),
-                                       self.stream_id, fl, stream=st)
                 if C > 1:
                     llr_r = torch.empty((B, h.n_cw), dtype=torch.float32, device="cuda")
                     hq = harq3[:, r].contiguous() if harq3 is not None else None
-                    h.rate_recover_raw(fl, B, rm, hq, llr_r, mem=capi.MEM_DEVICE, stream=st)
+                    self._channel_and_recover(f, E, rm, var, hq, llr_r, st)
                     llr3[:, r] = llr_r
                     if hq is not None:
                         harq3[:, r] = hq
                 else:
-                    h.rate_recover_raw(fl, B, rm, self.harq, self.llr, mem=capi.MEM_DEVICE, stream=st)
+                    self._channel_and_recover(f, E, rm, var, self.harq, self.llr, st)
             h.decode_raw(self.llr, B * C, self.hard, iters=self.iters, n_rows=self.n_rows, mem=capi.MEM_DEVICE, stream=st)
             if self.use_crc:
                 # a_hat = [] unless every CB CRC and the TB CRC pass (NRLDPCDecoder.m:300,336-339); a block error is
                 # ~isequal(a, a_hat) (plot_BLER_vs_SNR.m:146)
-                A, Kp, Lcb = self.A, self.Kp, self.L_cb
                 if C == 1:
-                    self.tb_hat.copy_(self.hard[:, :Kp])
-                    cb_pass = torch.ones(B, dtype=torch.bool, device="cuda")
+                    tb_hat, tb_hat_stride, cb_passed = self.hard, K, None
                 else:
                     # per code block, latched over the retransmissions (NRLDPCDecoder.m:296-309): a block whose CB CRC
                     # passes overwrites its part of b_hat_buffer and sets code_block_CRC_passed; block 0 may pass on rv0
                     # and block 1 on rv1
-                    h.crc_raw(self.hard, B * C, Kp, self.K, capi.CRC24B, ok=self.cb_flag, stream=st)
+                    h.crc_raw(self.hard, B * C, Kp, K, capi.CRC24B, ok=self.cb_flag, stream=st)
                     pass_now = self.cb_flag.view(B, C).bool()
                     tb3 = self.tb_hat.view(B, C, Kp - Lcb)
                     torch.where(pass_now[:, :, None], self.hard.view(B, C, -1)[:, :, :Kp - Lcb], tb3, out=tb3)
-                    cb_passed |= pass_now
-                    cb_pass = cb_passed.all(dim=1)
-                h.crc_raw(self.tb_hat, B, self.Bsz, self.Bsz, self.tb_kind, ok=self.tb_flag, stream=st)
-                cb_ok = cb_pass & self.tb_flag.bool() & (self.tb_hat[:, :A] == self.tb[:, :A]).all(dim=1)
+                    self.cb_passed |= self.cb_flag
+                    tb_hat, tb_hat_stride, cb_passed = self.tb_hat, self.Bsz, self.cb_passed
+                h.crc_raw(tb_hat, B, self.Bsz, tb_hat_stride, self.tb_kind, ok=self.tb_flag, stream=st)
+                h.bler_count_raw(self.hard, self.info, tb_hat, tb_hat_stride, tb, tb_stride, self.tb_flag, cb_passed, self.iters,
+                                 B, C, Kp, A, self.latch, self.counters, do_latch=True, finalize=last, stream=st)
             else:
-                cb_ok = (self.hard[:, :self.Kp] == self.info[:, :self.Kp]).all(dim=1).view(B, C).all(dim=1)
-            iters_total += int(self.iters.sum())
-            ok_latched |= cb_ok
-            if bool(ok_latched.all()):
+                # no CRCs: a block is decoded when the first K' bits of all its code blocks are right
+                cb_ok = (self.hard[:, :Kp] == self.info[:, :Kp]).all(dim=1).view(B, C).all(dim=1)
+                self.latch |= cb_ok.to(torch.uint8)
+                self.counters[3] += self.iters.sum()
+                if last:
+                    self._finalize_torch()
+            if not last and bool(self.latch.all()):      # every block decoded: no further retransmission (:124)
+                if self.use_crc:
+                    h.bler_count_raw(self.hard, self.info, None, 0, None, 0, None, None, None, B, C, Kp, A, self.latch, self.counters,
+                                     do_latch=False, finalize=True, stream=st)
+                else:
+                    self._finalize_torch()
                 break
-        bit_err = int(((self.hard[:, :self.Kp] != self.info[:, :self.Kp]).view(B, C, -1).sum(dim=(1, 2)) * (~ok_latched)).sum())
-        return np.array([B, int((~ok_latched).sum()), bit_err, iters_total], dtype=np.int64), bool(ok_latched.any())
+        c = self.counters.cpu().numpy().astype(np.int64)     # the one host read of the batch
+        return c, bool(c[1] < B)
+
+    def _finalize_torch(self):
+        B, C, Kp = self.B, self.C, self.Kp
+        bad = self.latch == 0
+        self.counters[0] += B
+        self.counters[1] += bad.sum()
+        self.counters[2] += ((self.hard[:, :Kp] != self.info[:, :Kp]).view(B, C, -1).sum(dim=(1, 2)) * bad).sum()
 
     def run_point(self, esn0_db, target_block_errors, max_blocks=None, found_start=True):
         """Batches until `target_block_errors` errors were seen across all ranks (plot_BLER_vs_SNR.m:116)."""

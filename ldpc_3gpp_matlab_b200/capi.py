@@ -41,6 +41,7 @@ SYMBOLS = (
     "nrldpc_rate_match", "nrldpc_rate_recover", "nrldpc_qpsk_awgn_llr", "nrldpc_host_alloc",
     "nrldpc_host_free", "nrldpc_launch_count", "nrldpc_version",
     "nrldpc_modulate", "nrldpc_awgn", "nrldpc_demodulate", "nrldpc_mod_awgn_llr", "nrldpc_crc", "nrldpc_decode16", "nrldpc_decode64",
+    "nrldpc_qpsk_awgn_rate_recover", "nrldpc_bler_count",
 )
 
 
@@ -102,6 +103,8 @@ def load():
     lib.nrldpc_rate_match.argtypes = [vp, vp, i64, C.POINTER(Rm), vp, i32, vp]
     lib.nrldpc_rate_recover.argtypes = [vp, vp, i64, C.POINTER(Rm), vp, vp, i32, vp]
     lib.nrldpc_qpsk_awgn_llr.argtypes = [vp, vp, i64, i32, C.c_float, u64, u64, vp, vp]
+    lib.nrldpc_qpsk_awgn_rate_recover.argtypes = [vp, vp, i64, C.POINTER(Rm), C.c_float, u64, u64, vp, vp, vp]
+    lib.nrldpc_bler_count.argtypes = [vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, i64, i32, i32, i32, vp, vp, i32, i32, vp]
     lib.nrldpc_modulate.argtypes = [vp, vp, i64, i32, vp, vp]
     lib.nrldpc_awgn.argtypes = [vp, vp, i64, C.c_float, u64, u64, vp]
     lib.nrldpc_demodulate.argtypes = [vp, vp, i64, i32, C.c_float, i32, vp, vp]
@@ -232,6 +235,16 @@ class Handle:
     def qpsk_awgn_llr_raw(self, f_bits, batch, E, variance, seed, stream_id, f_llr, stream=None):
         self._check(self._lib.nrldpc_qpsk_awgn_llr(self._h, _ptr(f_bits), int(batch), int(E), float(variance),
                                                    int(seed), int(stream_id), _ptr(f_llr), stream))
+
+    def qpsk_awgn_rate_recover_raw(self, f_bits, batch, rm: Rm, variance, seed, stream_id, harq, llr_cw, stream=None):
+        self._check(self._lib.nrldpc_qpsk_awgn_rate_recover(self._h, _ptr(f_bits), int(batch), C.byref(rm), float(variance), int(seed),
+                                                            int(stream_id), _ptr(harq), _ptr(llr_cw), stream))
+
+    def bler_count_raw(self, hard, info, tb_hat, tb_hat_stride, tb, tb_stride, tb_ok, cb_passed, iters, n_tb, C_, K_prime, A, latch,
+                       counters, do_latch=True, finalize=True, stream=None):
+        self._check(self._lib.nrldpc_bler_count(self._h, _ptr(hard), _ptr(info), _ptr(tb_hat), int(tb_hat_stride), _ptr(tb), int(tb_stride),
+                                                _ptr(tb_ok), _ptr(cb_passed), _ptr(iters), int(n_tb), int(C_), int(K_prime), int(A),
+                                                _ptr(latch), _ptr(counters), int(bool(do_latch)), int(bool(finalize)), stream))
 
     def modulate_raw(self, bits, n_bits, Q_m, sym, stream=None):
         self._check(self._lib.nrldpc_modulate(self._h, _ptr(bits), int(n_bits), int(Q_m), _ptr(sym), stream))

@@ -184,6 +184,36 @@ __device__ __forceinline__ uint32_t ext_app(const uint32_t *my_rec, int row, uin
     return __float_as_uint(__fadd_rn(__uint_as_float(chan), __uint_as_float(sel ^ (chan & 0x80000000u))));
 }
 
+// The same for ALL active extension rows at once, as a bit mask (bit r = hard decision of row r's degree-1 parity variable,
+// r = 4 .. n_rows-1).  The records are fetched eight rows at a time (24 loads in flight): taken one row after the other,
+// each record is an L2 round trip, and 42 of them in sequence cost about 15 us per call -- several per cent of a codeword
+// under the parity-check stop (measured: BASELINE config 3 with the stop ran SLOWER at its operating point than with the
+// stop never taken).  p_addr: shared-window address of this thread's entry of row 4's parity column; col_bytes = 4*Z.
+__device__ __noinline__ unsigned long long ext_hard_mask(const uint32_t *my_rec, const uint64_t pol, const int n_rows, const uint32_t p_addr,
+                                                         const uint32_t col_bytes) {
+    unsigned long long m = 0ull;
+    for (int r0 = 4; r0 < n_rows; r0 += 8) {
+        uint32_t x[8], y[8], meta[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = min(r0 + i, n_rows - 1);       // clamped: the surplus loads of the last chunk repeat its last row
+            x[i] = ld_word(my_rec + (r * 3 + 0) * kRecStride, pol);
+            y[i] = ld_word(my_rec + (r * 3 + 1) * kRecStride, pol);
+            meta[i] = ld_word(my_rec + (r * 3 + 2) * kRecStride, pol);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (r0 + i < n_rows) {
+                const uint32_t chan = lds_u32(p_addr + (uint32_t)(r0 + i - 4) * col_bytes);
+                const uint32_t sel = ((meta[i] & 31u) == 31u) ? y[i] : x[i];
+                const uint32_t app = __float_as_uint(__fadd_rn(__uint_as_float(chan), __uint_as_float(sel ^ (chan & 0x80000000u))));
+                m |= (unsigned long long)(app >> 31) << (r0 + i);
+            }
+        }
+    }
+    return m;
+}
+
 // Integer multiply-add whose multiplier is the kernel parameter `one` (always 1): the compiler
 // cannot fold it, so it is emitted as IMAD, which issues on the FMA pipe -- address arithmetic
 // stays off the saturated ALU pipe.
@@ -286,8 +316,12 @@ __device__ __forceinline__ void row_gather(const Lane &l, const uint2 *__restric
 // second half: new messages, APP write-back, the row's new record.  PAR: also XOR the new APP values into `par` -- its sign
 // bit is this check's parity on the hard decisions just written (used for the last layer of an iteration, whose decisions
 // are final: see UnrolledRows)
-template <int DEG, bool IDENT_LAST, bool PAR>
-__device__ __forceinline__ uint4 row_scatter_par(const RowState<DEG> &s, const float alpha, uint32_t &par, const bool live = true) {
+// TRACK >= 0 (extension rows of the multi-codeword kernels under the parity-check stop): the hard decision of the row's
+// degree-1 parity variable is kept as bit TRACK of `ext_word`, so that the extension stage of the syndrome needs no record
+// from the L2 scratch (with several codewords per CTA that stage runs in most passes, and every other slot waits for it)
+template <int DEG, bool IDENT_LAST, bool PAR, int TRACK = -1>
+__device__ __forceinline__ uint4 row_scatter_par(const RowState<DEG> &s, const float alpha, uint32_t &par, const bool live = true,
+                                                 uint32_t *ext_word = nullptr) {
     constexpr int NE = IDENT_LAST ? DEG - 1 : DEG;
     // both candidate magnitudes with the row's sign product folded in: multiply by alpha carrying the sign
     // (m >= 0, so the product's sign bit is sg also when m = 0: bit-identical to (alpha*m) | sg)
@@ -307,10 +341,12 @@ __device__ __forceinline__ uint4 row_scatter_par(const RowState<DEG> &s, const f
         if (PAR) par ^= __float_as_uint(app);
         if (live) sts_f32(s.addr[e], app);
     }
-    if (PAR && IDENT_LAST) {   // the degree-1 variable's a-posteriori value takes part in the check's parity only
+    if ((PAR || TRACK >= 0) && IDENT_LAST) {   // the degree-1 variable's a-posteriori value: for the check's parity / its hard decision only
         const float tp = s.t[DEG - 1];
         const uint32_t sel = fabsf(tp) == s.m1 ? m2ss : m1ss;
-        par ^= __float_as_uint(__fadd_rn(tp, __uint_as_float(sel ^ (__float_as_uint(tp) & 0x80000000u))));
+        const uint32_t app_p = __float_as_uint(__fadd_rn(tp, __uint_as_float(sel ^ (__float_as_uint(tp) & 0x80000000u))));
+        if (PAR) par ^= app_p;
+        if (TRACK >= 0) *ext_word = bitselect(*ext_word, app_p >> (31 - (TRACK >= 0 ? TRACK : 0)), 1u << (TRACK >= 0 ? TRACK : 0));
     }
     return make_uint4(m1ss, m2ss, arg | (s.ts << 5), 0u);
 }
@@ -320,12 +356,14 @@ __device__ __forceinline__ uint4 row_scatter(const RowState<DEG> &s, const float
     return row_scatter_par<DEG, IDENT_LAST, false>(s, alpha, unused, live);
 }
 
-template <int DEG, bool IDENT_LAST, bool ONE_CW>
+template <int DEG, bool IDENT_LAST, bool ONE_CW, int TRACK = -1>
 __device__ __forceinline__ uint4 process_row(const Lane &l, const uint2 *__restrict__ ed, const uint32_t om1,
-                                             const uint32_t om2, const uint32_t ometa, const float alpha, const bool live = true) {
+                                             const uint32_t om2, const uint32_t ometa, const float alpha, const bool live = true,
+                                             uint32_t *ext_word = nullptr) {
     RowState<DEG> s;
     row_gather<DEG, IDENT_LAST, ONE_CW>(l, ed, om1, om2, ometa, s);
-    return row_scatter<DEG, IDENT_LAST>(s, alpha, live);
+    uint32_t unused = 0;
+    return row_scatter_par<DEG, IDENT_LAST, false, TRACK>(s, alpha, unused, live, ext_word);
 }
 
 // ---- pieces shared by all kernel variants --------------------------------------------------------
@@ -337,6 +375,7 @@ struct DecCtx {
     bool done;       // this thread does no row work (inactive lane, or its codeword has converged)
     bool live;       // MASKED kernels: this lane owns a check (tid < Z); the lanes that pad the last warp shadow lanes 0.. and never store
     int last_fail;   // FULL kernels, every base row active: some check of the iteration's last layer is unsatisfied (CTA-uniform)
+    uint32_t ext_lo, ext_hi;   // TRACK kernels: hard decisions of the degree-1 parity variables, bit (r - 4) of the pair = extension row r
     uint4 last_rec;  // FULL kernels, trimmed row count: the record the last ACTIVE row wrote in this iteration (kept in registers
                      // for last_row_parity: reloading it from the L2 scratch cost one L2 round trip per iteration)
 };
@@ -397,15 +436,13 @@ __device__ __forceinline__ void load_group(const DecArgs &a, float *app, long lo
 // exact syndrome of hard = (app < 0) over the active rows r0 <= r < r1 ('Parity check satisfied', NRLDPCDecoder.m:120)
 __device__ __forceinline__ uint32_t syndrome_fail(const DecArgs &a, const DecCtx &c, int r0, int r1) {
     uint32_t fail = 0;
+    unsigned long long mask = 0ull;
+    if (r1 > 4) mask = ext_hard_mask(c.my_rec, c.pol, a.n_rows, a.smem_base + c.l.slot_off + c.l.zoff + (uint32_t)((a.kcols + 4) * a.Z) * 4u, (uint32_t)a.Z * 4u);
     for (int r = r0; r < r1; ++r) {
         uint32_t par = 0;
-        const int e1 = a.row_start[r + 1];
-        for (int e = a.row_start[r]; e < e1; ++e) {
-            const uint2 d = a.ed[e];
-            uint32_t w = lds_u32(edge_addr<false>(c.l, d));
-            if (r >= 4 && e == e1 - 1) w = ext_app(c.my_rec, r, c.pol, w);   // degree-1 parity variable
-            par ^= w;
-        }
+        const int e1 = a.row_start[r + 1] - (r >= 4 ? 1 : 0);
+        for (int e = a.row_start[r]; e < e1; ++e) par ^= lds_u32(edge_addr<false>(c.l, a.ed[e]));
+        if (r >= 4) par ^= (uint32_t)((mask >> r) & 1ull) << 31;   // degree-1 parity variable
         fail |= par;
     }
     return fail;
@@ -474,25 +511,23 @@ __device__ __forceinline__ void store_outputs(const DecArgs &a, const float *app
 // 'Parity check satisfied' (the reference's only setting, NRLDPCDecoder.m:120) this runs after EVERY iteration.
 template <int BG, int R, int REND, bool FULL>
 struct SyndromeRows {
-    static __device__ __forceinline__ uint32_t run(const DecArgs &a, const Lane &l, const uint32_t *my_rec, const uint64_t pol, uint32_t fail) {
+    // ext_mask: hard decisions of the degree-1 parity variables (ext_hard_mask), bit r for row r
+    static __device__ __forceinline__ uint32_t run(const DecArgs &a, const Lane &l, const unsigned long long ext_mask, uint32_t fail) {
         if (R >= 4 && R >= a.n_rows) return fail;
         constexpr int DEG = BgShape<BG>::deg(R);
+        constexpr int NE = R >= 4 ? DEG - 1 : DEG;
         constexpr int E0 = BgShape<BG>::start(R);
-        uint32_t par = 0;
+        uint32_t par = R >= 4 ? (uint32_t)((ext_mask >> R) & 1ull) << 31 : 0u;
 #pragma unroll
-        for (int e = 0; e < DEG; ++e) {
-            uint32_t w = lds_u32(edge_addr<FULL>(l, a.ed[E0 + e], (R >= 4) && e == DEG - 1));
-            if (R >= 4 && e == DEG - 1) w = ext_app(my_rec, R, pol, w);   // degree-1 parity variable: channel value + latest message
-            par ^= w;
-        }
+        for (int e = 0; e < NE; ++e) par ^= lds_u32(edge_addr<FULL>(l, a.ed[E0 + e]));
         fail |= par;
         asm volatile("" : "+r"(fail));   // one row's loads are consumed before the next row's are issued (register pressure)
-        return SyndromeRows<BG, R + 1, REND, FULL>::run(a, l, my_rec, pol, fail);
+        return SyndromeRows<BG, R + 1, REND, FULL>::run(a, l, ext_mask, fail);
     }
 };
 template <int BG, int REND, bool FULL>
 struct SyndromeRows<BG, REND, REND, FULL> {
-    static __device__ __forceinline__ uint32_t run(const DecArgs &, const Lane &, const uint32_t *, const uint64_t, uint32_t fail) { return fail; }
+    static __device__ __forceinline__ uint32_t run(const DecArgs &, const Lane &, const unsigned long long, uint32_t fail) { return fail; }
 };
 
 // Out of line on purpose: inlined into the decode kernel the 316 unrolled loads changed the register allocation of
@@ -503,12 +538,23 @@ struct SyndromeRows<BG, REND, REND, FULL> {
 // result of the full syndrome at a quarter of the loads in every iteration but a codeword's last.
 template <int BG, bool FULL>
 __device__ __noinline__ uint32_t syndrome_unrolled_core(const DecArgs &a, const Lane l) {
-    return SyndromeRows<BG, 0, 4, FULL>::run(a, l, nullptr, 0ull, 0u);
+    return SyndromeRows<BG, 0, 4, FULL>::run(a, l, 0ull, 0u);
 }
 template <int BG, bool FULL>
 __device__ __noinline__ uint32_t syndrome_unrolled_ext(const DecArgs &a, const Lane l, const uint32_t *my_rec, const uint64_t pol) {
-    return SyndromeRows<BG, 4, BgShape<BG>::kRows, FULL>::run(a, l, my_rec, pol, 0u);
+    const unsigned long long mask = ext_hard_mask(my_rec, pol, a.n_rows, a.smem_base + l.slot_off + l.zoff + (uint32_t)((a.kcols + 4) * a.Z) * 4u, (uint32_t)a.Z * 4u);
+    return SyndromeRows<BG, 4, BgShape<BG>::kRows, FULL>::run(a, l, mask, 0u);
 }
+
+// TRACK kernels: the parity variables' hard decisions are already in registers (DecCtx::ext_lo / ext_hi)
+template <int BG, bool FULL>
+__device__ __noinline__ uint32_t syndrome_unrolled_ext_bits(const DecArgs &a, const Lane l, const unsigned long long ext_mask) {
+    return SyndromeRows<BG, 4, BgShape<BG>::kRows, FULL>::run(a, l, ext_mask, 0u);
+}
+struct ExtFromBit {   // last_row_parity with the parity variable's hard decision given (bit 31 of `word`)
+    uint32_t word;
+    __device__ __forceinline__ uint32_t operator()(const uint4, uint32_t) const { return word; }
+};
 
 // Bit-sliced syndrome for the FULL kernels (Z a multiple of 32, one codeword per CTA).  After an iteration every warp
 // packs the hard decisions of its 32 variables of a block column into one word (ballot), giving hb[col][Z/32];
@@ -527,16 +573,16 @@ __device__ __noinline__ uint32_t syndrome_unrolled_ext(const DecArgs &a, const L
 // All pointers are shared-window byte addresses (explicit LDS / STS: a generic pointer costs an address-space
 // resolution per access in an out-of-line routine).
 // ext_row0 >= 0: column col0 + i is the degree-1 parity column of extension row ext_row0 + i -- shared memory holds its
-// channel value, the hard decision comes from ext_app (thread z owns check z of that row: identity circulant)
+// channel value, the hard decision is bit (ext_row0 + i) of ext_mask (ext_hard_mask; thread z owns check z of that row:
+// identity circulant)
 __device__ __forceinline__ void pack_hard_bits(uint32_t app_s, uint32_t hb_s, int Z, int col0, int col1, int z, int ext_row0 = -1,
-                                               const uint32_t *my_rec = nullptr, uint64_t pol = 0ull) {
+                                               const unsigned long long ext_mask = 0ull) {
     uint32_t src = app_s + (uint32_t)(col0 * Z + z) * 4u;
     uint32_t dst = hb_s + (uint32_t)(col0 * (Z >> 5) + (z >> 5)) * 4u;
 #pragma unroll 1   // code size: see syndrome_bitsliced
     for (int col = col0; col < col1; ++col, src += (uint32_t)Z * 4u, dst += (uint32_t)(Z >> 5) * 4u) {
-        uint32_t w = lds_u32(src);
-        if (ext_row0 >= 0) w = ext_app(my_rec, ext_row0 + (col - col0), pol, w);
-        const uint32_t word = __ballot_sync(0xffffffffu, w >> 31);
+        const uint32_t bit = ext_row0 >= 0 ? (uint32_t)((ext_mask >> (ext_row0 + (col - col0))) & 1ull) : lds_u32(src) >> 31;
+        const uint32_t word = __ballot_sync(0xffffffffu, bit);
         if ((z & 31) == 0) sts_u32(dst, word);
     }
 }
@@ -586,7 +632,8 @@ __device__ __noinline__ int syndrome_bitsliced(uint32_t app_s, uint32_t hb_s, in
     }
     if (__syncthreads_or(fail != 0u)) return 1;
     if (n_rows <= 4) return 0;
-    pack_hard_bits(app_s, hb_s, Z, kCore, min(S::kCols, S::kKcols + n_rows), z, 4, my_rec, pol);
+    pack_hard_bits(app_s, hb_s, Z, kCore, min(S::kCols, S::kKcols + n_rows), z, 4,
+                   ext_hard_mask(my_rec, pol, n_rows, app_s + (uint32_t)(kCore * Z + z) * 4u, (uint32_t)Z * 4u));
     __syncthreads();
     for (int r = 4 + lane; r < n_rows; r += 32) {
         uint32_t acc = 0;
@@ -636,8 +683,12 @@ __device__ __forceinline__ void iteration_looped(const DecArgs &a, DecCtx &c, co
 // FULL: every thread of the CTA runs the row code for the whole decode (one codeword per CTA): no per-thread activity
 // test.  MASKED (FULL only): Z is not a multiple of 32, the lanes that pad the last warp shadow lanes 0.. (same loads,
 // same arithmetic) and only their stores are predicated off -- the CTA-uniform code serves every one-codeword CTA.
-template <int BG, int R, bool FULL, bool MASKED = false>
+// MODE: 0 plain, 1 MASKED (FULL only), 2 TRACK (multi-codeword kernels under the stop: see row_scatter_par)
+template <int BG, int R, bool FULL, int MODE = 0>
 struct UnrolledRows {
+    static constexpr bool MASKED = MODE == 1, TRACK = MODE == 2;
+    static constexpr int kPos0 = (TRACK && R >= 4) ? ((R - 4) & 31) : -1;            // bit of row R in ext_lo / ext_hi
+    static constexpr int kPos1 = (TRACK && R + 1 >= 4) ? ((R + 1 - 4) & 31) : -1;    // bit of row R + 1 (row pairs)
     static __device__ __forceinline__ void run(const DecArgs &a, DecCtx &c, const int ld_from, const int ld_to, const bool store_rec,
                                                const uint4 prev = make_uint4(0u, 0u, 0u, 0u)) {
         if (R >= 4 && R >= a.n_rows) {         // n_rows >= 4 is validated by the host
@@ -664,8 +715,8 @@ struct UnrolledRows {
                 RowState<DEG2> s1;
                 row_gather<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur.x, c.cur.y, c.cur.z, s0);
                 row_gather<DEG2, (R >= 4), FULL>(c.l, a.ed + E1, c.cur2.x, c.cur2.y, c.cur2.z, s1);
-                const uint4 rec0 = row_scatter_par<DEG, (R >= 4), kLastPair>(s0, a.alpha, par, !MASKED || c.live);
-                const uint4 rec1 = row_scatter_par<DEG2, (R >= 4), kLastPair>(s1, a.alpha, par, !MASKED || c.live);
+                const uint4 rec0 = row_scatter_par<DEG, (R >= 4), kLastPair, kPos0>(s0, a.alpha, par, !MASKED || c.live, (R - 4) < 32 ? &c.ext_lo : &c.ext_hi);
+                const uint4 rec1 = row_scatter_par<DEG2, (R >= 4), kLastPair, kPos1>(s1, a.alpha, par, !MASKED || c.live, (R + 1 - 4) < 32 ? &c.ext_lo : &c.ext_hi);
                 if (store_rec && (!MASKED || c.live)) {
                     st_rec(c.my_rec, R == 0 ? a.n_rows : R, rec0, c.pol);
                     st_rec(c.my_rec, R + 1, rec1, c.pol);
@@ -679,7 +730,7 @@ struct UnrolledRows {
             // CTA-wide OR of those parities and the kernel skips the syndrome after most iterations (exact either way).
             if (kLastPair) c.last_fail = __syncthreads_or((int)(par >> 31) & (int)(!MASKED || c.live));
             else __syncthreads();
-            UnrolledRows<BG, (PAIR ? R + 2 : BgShape<BG>::kRows), FULL, MASKED>::run(a, c, ld_from, ld_to, store_rec, rec_last);
+            UnrolledRows<BG, (PAIR ? R + 2 : BgShape<BG>::kRows), FULL, MODE>::run(a, c, ld_from, ld_to, store_rec, rec_last);
         } else {
             uint4 rec_last = make_uint4(0u, 0u, 0u, 0u);
             if (FULL || !c.done) {
@@ -688,7 +739,8 @@ struct UnrolledRows {
                     nxt = ld_rec(c.my_rec, R + 1, c.pol);   // slot R+1; slot n_rows holds layer 0
                     if (!PAIR && pair_first<BG>(R + 1)) nxt2 = ld_rec(c.my_rec, R + 2, c.pol);
                 }
-                const uint4 rec = process_row<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur.x, c.cur.y, c.cur.z, a.alpha, !MASKED || c.live);
+                const uint4 rec = process_row<DEG, (R >= 4), FULL, kPos0>(c.l, a.ed + E0, c.cur.x, c.cur.y, c.cur.z, a.alpha, !MASKED || c.live,
+                                                                             (R - 4) < 32 ? &c.ext_lo : &c.ext_hi);
                 if (store_rec && (!MASKED || c.live)) st_rec(c.my_rec, R == 0 ? a.n_rows : R, rec, c.pol);
                 c.cur = nxt;
                 c.cur2 = nxt2;
@@ -696,29 +748,31 @@ struct UnrolledRows {
             }
             __syncthreads();
             // a pair opener running alone means R + 1 == n_rows: the iteration ends here
-            if (!PAIR) UnrolledRows<BG, R + 1, FULL, MASKED>::run(a, c, ld_from, ld_to, store_rec, rec_last);
+            if (!PAIR) UnrolledRows<BG, R + 1, FULL, MODE>::run(a, c, ld_from, ld_to, store_rec, rec_last);
             else if (FULL) c.last_rec = rec_last;
         }
     }
 };
-template <int BG, bool FULL, bool MASKED>
-struct UnrolledRows<BG, BgShape<BG>::kRows, FULL, MASKED> {
+template <int BG, bool FULL, int MODE>
+struct UnrolledRows<BG, BgShape<BG>::kRows, FULL, MODE> {
     static __device__ __forceinline__ void run(const DecArgs &, DecCtx &, int, int, bool, const uint4 = make_uint4(0u, 0u, 0u, 0u)) {}
 };
 
-template <int BG, bool FULL, bool MASKED>
+template <int BG, bool FULL, int MODE>
 __device__ __forceinline__ void iteration_unrolled(const DecArgs &a, DecCtx &c, const int it, const bool keep_last) {
     const bool first = it == 0, last = it + 1 == a.max_iters;
     c.last_fail = 0;   // set by the last layer when every base row is active
     // keep_last: the records of the final iteration are written too (they hold the messages to the degree-1 parity
     // variables, from which the syndrome and the soft output rebuild those variables' a-posteriori values)
-    UnrolledRows<BG, 0, FULL, MASKED>::run(a, c, first ? a.n_rows - 1 : 0, last ? a.n_rows - 1 : a.n_rows, !last || keep_last);
+    UnrolledRows<BG, 0, FULL, MODE>::run(a, c, first ? a.n_rows - 1 : 0, last ? a.n_rows - 1 : a.n_rows, !last || keep_last);
 }
 
 // BG = 0: generic looped variant; BG = 1 / 2: layer loop unrolled for that base graph.
-template <int BG, bool FULL, bool MASKED = false>
+template <int BG, bool FULL, int MODE = 0>
 __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(const __grid_constant__ DecArgs a) {
+    constexpr bool MASKED = MODE == 1, TRACK = MODE == 2;
     static_assert(FULL || !MASKED, "MASKED is a flavour of the one-codeword (FULL) kernels");
+    static_assert(!FULL || !TRACK, "TRACK is a flavour of the multi-codeword kernels");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int Z = a.Z;
     const int ncw = a.ncols * Z;
@@ -776,12 +830,13 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
         c.done = !active;
         c.cur = make_uint4(0u, 0u, 0u, 0u);
         c.cur2 = c.cur;
+        c.ext_lo = c.ext_hi = 0u;
         int my_iters = 0;
         int my_ok = 0;
 
         for (int it = 0; it < a.max_iters; ++it) {
             if (BG == 0) iteration_looped(a, c, it, keep_last);
-            else iteration_unrolled<(BG == 0 ? 1 : BG), FULL, MASKED>(a, c, it, keep_last);
+            else iteration_unrolled<(BG == 0 ? 1 : BG), FULL, MODE>(a, c, it, keep_last);
 
             if (!c.done) my_iters = it + 1;
             const bool last = it + 1 == a.max_iters;
@@ -800,16 +855,29 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
                     constexpr int B = BG == 0 ? 1 : BG;
                     int *s_flag2 = s_flag + a.cwpc;
                     const bool staged = a.n_rows >= a.staged_min_rows;
-                    if (!c.done) {
+                    // bit r = hard decision of extension row r's parity variable (TRACK: kept up to date by the row updates)
+                    const unsigned long long ext_bits = TRACK ? ((((unsigned long long)c.ext_hi << 32) | c.ext_lo) << 4) : 0ull;
+                    if (TRACK) {
+                        // per-slot last-layer filter: the decisions written by the last active row are final, so an unsatisfied
+                        // check there proves the codeword has not converged and the syndrome is skipped for this slot
+                        if (!c.done) {
+                            const uint32_t pbit = (uint32_t)((ext_bits >> (a.n_rows - 1)) & 1ull) << 31;
+                            if (last_row_parity(a, c.l, make_uint4(0u, 0u, 0u, 0u), ExtFromBit{pbit}) >> 31) s_flag[slot] = 1;
+                        }
+                        __syncthreads();
+                    }
+                    if (!c.done && !(TRACK && s_flag[slot])) {
                         uint32_t f = BG == 0 ? syndrome_fail(a, c, 0, 4) : syndrome_unrolled_core<B, FULL>(a, c.l);
-                        if (!staged) f |= BG == 0 ? syndrome_fail(a, c, 4, a.n_rows) : syndrome_unrolled_ext<B, FULL>(a, c.l, c.my_rec, c.pol);
+                        if (!staged) f |= BG == 0 ? syndrome_fail(a, c, 4, a.n_rows)
+                                        : TRACK ? syndrome_unrolled_ext_bits<B, FULL>(a, c.l, ext_bits) : syndrome_unrolled_ext<B, FULL>(a, c.l, c.my_rec, c.pol);
                         if (f >> 31) s_flag[slot] = 1;
                     }
                     if (staged) {
                         // extension rows only for codewords whose core checks all hold
                         __syncthreads();
                         if (!c.done && !s_flag[slot]) {
-                            const uint32_t f = BG == 0 ? syndrome_fail(a, c, 4, a.n_rows) : syndrome_unrolled_ext<B, FULL>(a, c.l, c.my_rec, c.pol);
+                            const uint32_t f = BG == 0 ? syndrome_fail(a, c, 4, a.n_rows)
+                                             : TRACK ? syndrome_unrolled_ext_bits<B, FULL>(a, c.l, ext_bits) : syndrome_unrolled_ext<B, FULL>(a, c.l, c.my_rec, c.pol);
                             if (f >> 31) s_flag2[slot] = 1;
                         }
                     }
@@ -831,6 +899,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
             // (channel value + the row's last message) written into shared memory now that decoding is over
             if (active) {
                 const uint32_t base = a.smem_base + c.l.slot_off + c.l.zoff + (uint32_t)((a.kcols + 4) * Z) * 4u;
+#pragma unroll 4   // independent records: several L2 round trips in flight
                 for (int r = 4; r < a.n_rows; ++r) {
                     const uint32_t addr = base + (uint32_t)((r - 4) * Z) * 4u;
                     sts_u32(addr, ext_app(c.my_rec, r, c.pol, lds_u32(addr)));
@@ -843,6 +912,162 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
             if (a.iters) a.iters[cw0 + slot] = my_iters;
             if (a.ok) a.ok[cw0 + slot] = (uint8_t)my_ok;
         }
+    }
+}
+
+// ---- multi-codeword CTAs under the parity-check stop: per-slot refill ---------------------------------------------
+// In decode_nms_kernel a CTA's codewords form a group: a codeword that converges early idles until the slowest one of
+// its group is done (BASELINE config 3 with the reference's stop, NRLDPCDecoder.m:120: 5.4 mean iterations in the time of
+// about 8).  Here every slot (Z threads, one codeword) is its own pipeline:
+//     RUN --converged or max_iters--> outputs written, next codeword fetched (device work counter, per codeword),
+//         its LLRs requested with per-thread asynchronous copies (cp.async, 4 bytes: any Z, any alignment)
+//     LOAD  the slot sits out ONE pass over the layers while the copies land (waiting for them inside the pass that
+//           issued them would stall the whole CTA at the next barrier: measured 4.27 -> 6.22 ms in round 1)
+//     RUN   at the end of that pass: wait_group, clamp in place (each thread clamps what it copied), iteration 0.
+// The passes over the layers stay CTA-wide (one barrier per layer); slots differ only in which iteration they are in, so
+// the record prefetch gate (first iteration: nothing to load) is per thread.  Arithmetic and outputs are those of
+// decode_nms_kernel bit for bit (tests/test_gpu_parity.py); only the order in which codewords are started differs.
+__device__ __forceinline__ void cp_async_4(uint32_t smem_addr, const float *gptr) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int BG>
+__global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_refill_kernel(const __grid_constant__ DecArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    enum { ST_RUN = 0, ST_LOAD = 1, ST_IDLE = 2 };
+    const int Z = a.Z;
+    const int ncw = a.ncols * Z;
+    const int K = a.kcols * Z;
+    float *app = reinterpret_cast<float *>(smem_raw);
+    int *s_flag = reinterpret_cast<int *>(app + (size_t)a.cwpc * a.slot_stride);   // [cwpc] core stage, [cwpc] extension stage,
+    int *s_flag2 = s_flag + a.cwpc;
+    int *s_cw = s_flag + 2 * a.cwpc;                                                // [cwpc] next codeword of the slot
+    if ((uint32_t)__cvta_generic_to_shared(smem_raw) != a.smem_base) __trap();
+
+    const int tid = threadIdx.x;
+    const int slot = tid / Z;
+    const int z = tid - slot * Z;
+    const bool lane_ok = tid < a.cwpc * Z;
+    const int batch = (int)a.batch;              // the host uses this kernel for batches below 2^31 only
+
+    DecCtx c;
+    c.l.zoff = (uint32_t)z * 4u;
+    c.l.nZ4 = 0u - (uint32_t)Z * 4u;
+    c.l.slot_off = (uint32_t)(slot * a.slot_stride) * 4u;
+    c.l.one = (uint32_t)a.one;
+    c.my_rec = a.c2v + (size_t)(blockIdx.x / a.rec_group) * (kRecWords * kRecStride) + (blockIdx.x % a.rec_group) * blockDim.x + tid;
+    c.pol = make_l2_policy(a.l2_pin);
+    c.live = true;
+    c.last_fail = 0;
+    const uint32_t my_app_s = a.smem_base + c.l.slot_off + c.l.zoff;   // element z of block column 0 of this slot's APP array
+    const uint32_t col_bytes = (uint32_t)Z * 4u;
+
+    auto request = [&](int cw) {      // this thread's share of codeword cw: position z of every block column
+        const float *src = a.llr + (long long)cw * ncw + z;
+        uint32_t dst = my_app_s;
+        for (int col = 0; col < a.ncols; ++col, src += Z, dst += col_bytes) cp_async_4(dst, src);
+        cp_async_commit();
+    };
+    auto land = [&]() {               // copies done -> clamp in place (+-LLR_MAX, NaN filler, -0)
+        cp_async_wait_all();
+        uint32_t p = my_app_s;
+        for (int col = 0; col < a.ncols; ++col, p += col_bytes) sts_f32(p, clamp_llr(lds_f32(p)));
+    };
+
+    int st = ST_IDLE, my_cw = -1, my_it = 0;
+    if (lane_ok && z == 0) {
+        const int n = atomicAdd(a.work_counter, 1);
+        s_cw[slot] = n < batch ? n : -1;
+    }
+    if (tid < 2 * a.cwpc) s_flag[tid] = 0;
+    __syncthreads();
+    if (lane_ok) {
+        my_cw = s_cw[slot];
+        if (my_cw >= 0) { request(my_cw); land(); st = ST_RUN; }   // the first codeword of a slot is waited for at once
+    }
+    c.cur = make_uint4(0u, 0u, 0u, 0u);
+    c.cur2 = c.cur;
+    c.ext_lo = c.ext_hi = 0u;
+    if (__syncthreads_and(st == ST_IDLE)) return;
+
+    const bool staged = a.n_rows >= a.staged_min_rows;
+    while (true) {
+        // one pass over the layers: iteration my_it of every running slot
+        c.done = st != ST_RUN;
+        UnrolledRows<BG, 0, false, 2>::run(a, c, my_it == 0 ? a.n_rows - 1 : 0, a.n_rows, true);
+
+        const bool was_run = st == ST_RUN, was_load = st == ST_LOAD;
+        const unsigned long long ext_bits = (((unsigned long long)c.ext_hi << 32) | c.ext_lo) << 4;   // see decode_nms_kernel (TRACK)
+        if (was_run) {
+            const uint32_t pbit = (uint32_t)((ext_bits >> (a.n_rows - 1)) & 1ull) << 31;
+            if (last_row_parity(a, c.l, make_uint4(0u, 0u, 0u, 0u), ExtFromBit{pbit}) >> 31) s_flag[slot] = 1;
+        }
+        __syncthreads();
+        if (was_run && !s_flag[slot]) {
+            uint32_t f = syndrome_unrolled_core<BG, false>(a, c.l);
+            if (!staged) f |= syndrome_unrolled_ext_bits<BG, false>(a, c.l, ext_bits);
+            if (f >> 31) s_flag[slot] = 1;
+        }
+        if (staged) {
+            __syncthreads();
+            if (was_run && !s_flag[slot]) {
+                const uint32_t f = syndrome_unrolled_ext_bits<BG, false>(a, c.l, ext_bits);
+                if (f >> 31) s_flag2[slot] = 1;
+            }
+        }
+        __syncthreads();
+        bool fin = false;
+        if (was_run) {
+            ++my_it;
+            const int ok = (s_flag[slot] | s_flag2[slot]) ? 0 : 1;
+            fin = ok || my_it == a.max_iters;
+            if (fin) {
+                // outputs of this slot's codeword, written by its own Z threads
+                const uint32_t base_s = a.smem_base + c.l.slot_off;
+                uint8_t *hard = a.hard + (long long)my_cw * K;
+                if ((K & 3) == 0 && (a.slot_stride & 3) == 0) {
+                    for (int k4 = z; k4 < (K >> 2); k4 += Z) {
+                        const uint32_t p = base_s + (uint32_t)k4 * 16u;
+                        reinterpret_cast<uint32_t *>(hard)[k4] = (lds_u32(p) >> 31) | ((lds_u32(p + 4) >> 31) << 8) |
+                                                                 ((lds_u32(p + 8) >> 31) << 16) | ((lds_u32(p + 12) >> 31) << 24);
+                    }
+                } else {
+                    for (int k = z; k < K; k += Z) hard[k] = (uint8_t)(lds_u32(base_s + (uint32_t)k * 4u) >> 31);
+                }
+                if (a.soft != nullptr) {   // thread z owns position z of every column, and the records of its checks (ext_app)
+                    float *soft = a.soft + (long long)my_cw * ncw + z;
+                    uint32_t p = my_app_s;
+                    for (int col = 0; col < a.ncols; ++col, p += col_bytes, soft += Z) {
+                        uint32_t w = lds_u32(p);
+                        if (col >= a.kcols + 4 && col < a.kcols + a.n_rows) w = ext_app(c.my_rec, col - a.kcols, c.pol, w);
+                        __stcs(soft, __uint_as_float(w));
+                    }
+                }
+                if (z == 0) {
+                    if (a.iters) a.iters[my_cw] = my_it;
+                    if (a.ok) a.ok[my_cw] = (uint8_t)ok;
+                    const int n = atomicAdd(a.work_counter, 1);
+                    s_cw[slot] = n < batch ? n : -1;
+                }
+            }
+        }
+        __syncthreads();   // flags read, next codeword indices published, finished slots' APP arrays read out
+        if (tid < 2 * a.cwpc) s_flag[tid] = 0;
+        if (was_load) {    // requested during the previous pass: join with iteration 0
+            land();
+            st = ST_RUN; my_it = 0;
+            c.cur = make_uint4(0u, 0u, 0u, 0u);
+            c.cur2 = c.cur;
+            c.ext_lo = c.ext_hi = 0u;
+        }
+        if (fin) {
+            my_cw = s_cw[slot];
+            if (my_cw >= 0) { request(my_cw); st = ST_LOAD; }
+            else st = ST_IDLE;
+        }
+        if (__syncthreads_and(st == ST_IDLE)) break;   // also publishes the clamped values and the flag reset
     }
 }
 

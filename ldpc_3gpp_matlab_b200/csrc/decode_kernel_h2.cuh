@@ -40,6 +40,35 @@ __device__ __forceinline__ uint32_t ext_app_h2(const uint32_t *my_rec, int row, 
     const uint32_t sel = bitselect(rec.x, rec.y, is_p);
     return as_u32(__hadd2(as_h2(chan), as_h2(sel ^ (chan & kH2Sign))));
 }
+// Hard decisions of the degree-1 parity variables of all active extension rows, both codewords of the pair (bit r of ma / mb
+// = row r, codeword A / B), records fetched eight rows at a time: see ext_hard_mask in decode_kernel.cuh.
+__device__ __noinline__ ulonglong2 ext_hard_mask_h2(const uint32_t *my_rec, const uint64_t pol, const int n_rows, const uint32_t p_addr,
+                                                    const uint32_t col_bytes) {
+    unsigned long long a = 0ull, b = 0ull;
+    for (int r0 = 4; r0 < n_rows; r0 += 8) {
+        uint32_t x[8], y[8], meta[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = min(r0 + i, n_rows - 1);
+            x[i] = ld_word(my_rec + (r * 3 + 0) * kRecStride, pol);
+            y[i] = ld_word(my_rec + (r * 3 + 1) * kRecStride, pol);
+            meta[i] = ld_word(my_rec + (r * 3 + 2) * kRecStride, pol);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (r0 + i < n_rows) {
+                const uint32_t chan = lds_u32(p_addr + (uint32_t)(r0 + i - 4) * col_bytes);
+                const uint32_t is_p = __heq2_mask(as_h2(meta[i] & 0x000f000fu), as_h2(0x000f000fu));
+                const uint32_t sel = bitselect(x[i], y[i], is_p);
+                const uint32_t app = as_u32(__hadd2(as_h2(chan), as_h2(sel ^ (chan & kH2Sign))));
+                a |= (unsigned long long)((app >> 15) & 1u) << (r0 + i);
+                b |= (unsigned long long)(app >> 31) << (r0 + i);
+            }
+        }
+    }
+    return make_ulonglong2(a, b);
+}
+
 // last_row_parity of the pair kernel: the last active row's record is reloaded from the L2 scratch (holding it in registers
 // through the layer loop, as the float32 kernel does, made ptxas spill inside the BG1 loop: 25 spill instructions)
 struct ExtAppH2 {
@@ -59,25 +88,23 @@ struct ExtAppH2 {
 // syndrome with the base graph's shape known at compile time (see SyndromeRows in decode_kernel.cuh)
 template <int BG, int R, int REND, bool FULL>
 struct SyndromeRowsH2 {
-    static __device__ __forceinline__ uint32_t run(const DecArgs &a, const Lane &l, const uint32_t *my_rec, const uint64_t pol, uint32_t fail) {
+    static __device__ __forceinline__ uint32_t run(const DecArgs &a, const Lane &l, const unsigned long long ma, const unsigned long long mb, uint32_t fail) {
         if (R >= 4 && R >= a.n_rows) return fail;
         constexpr int DEG = BgShape<BG>::deg(R);
+        constexpr int NE = R >= 4 ? DEG - 1 : DEG;
         constexpr int E0 = BgShape<BG>::start(R);
-        uint32_t par = 0;
+        // degree-1 parity variable of an extension row: hard decisions of both codewords from ext_hard_mask_h2
+        uint32_t par = R >= 4 ? (((uint32_t)((ma >> R) & 1ull) << 15) | ((uint32_t)((mb >> R) & 1ull) << 31)) : 0u;
 #pragma unroll
-        for (int e = 0; e < DEG; ++e) {
-            uint32_t w = lds_u32(edge_addr<FULL>(l, a.ed[E0 + e], (R >= 4) && e == DEG - 1));
-            if (R >= 4 && e == DEG - 1) w = ext_app_h2(my_rec, R, pol, w);   // degree-1 parity variable
-            par ^= w;
-        }
+        for (int e = 0; e < NE; ++e) par ^= lds_u32(edge_addr<FULL>(l, a.ed[E0 + e]));
         fail |= par;
         asm volatile("" : "+r"(fail));   // one row's loads are consumed before the next row's are issued (register pressure)
-        return SyndromeRowsH2<BG, R + 1, REND, FULL>::run(a, l, my_rec, pol, fail);
+        return SyndromeRowsH2<BG, R + 1, REND, FULL>::run(a, l, ma, mb, fail);
     }
 };
 template <int BG, int REND, bool FULL>
 struct SyndromeRowsH2<BG, REND, REND, FULL> {
-    static __device__ __forceinline__ uint32_t run(const DecArgs &, const Lane &, const uint32_t *, const uint64_t, uint32_t fail) { return fail; }
+    static __device__ __forceinline__ uint32_t run(const DecArgs &, const Lane &, const unsigned long long, const unsigned long long, uint32_t fail) { return fail; }
 };
 
 // Bit-sliced, two-stage syndrome of a codeword pair (see syndrome_bitsliced in decode_kernel.cuh): the hard
@@ -85,16 +112,23 @@ struct SyndromeRowsH2<BG, REND, REND, FULL> {
 // All pointers are shared-window byte addresses (explicit LDS / STS: a generic pointer costs an address-space
 // resolution per access in an out-of-line routine).
 __device__ __forceinline__ void pack_hard_bits_h2(uint32_t app_s, uint32_t hb_s, int Z, int col0, int col1, int n_cols_all, int z,
-                                                  int ext_row0 = -1, const uint32_t *my_rec = nullptr, uint64_t pol = 0ull) {
+                                                  int ext_row0 = -1, const unsigned long long ma = 0ull, const unsigned long long mb = 0ull) {
     const uint32_t plane = (uint32_t)n_cols_all * (uint32_t)(Z >> 5) * 4u;
     uint32_t src = app_s + (uint32_t)(col0 * Z + z) * 4u;
     uint32_t dst = hb_s + (uint32_t)(col0 * (Z >> 5) + (z >> 5)) * 4u;
 #pragma unroll 1
     for (int col = col0; col < col1; ++col, src += (uint32_t)Z * 4u, dst += (uint32_t)(Z >> 5) * 4u) {
-        uint32_t x = lds_u32(src);
-        if (ext_row0 >= 0) x = ext_app_h2(my_rec, ext_row0 + (col - col0), pol, x);   // degree-1 parity column (see pack_hard_bits)
-        const uint32_t wa = __ballot_sync(0xffffffffu, (x >> 15) & 1u);
-        const uint32_t wb = __ballot_sync(0xffffffffu, x >> 31);
+        uint32_t ba, bb;
+        if (ext_row0 >= 0) {   // degree-1 parity column (see pack_hard_bits)
+            ba = (uint32_t)((ma >> (ext_row0 + (col - col0))) & 1ull);
+            bb = (uint32_t)((mb >> (ext_row0 + (col - col0))) & 1ull);
+        } else {
+            const uint32_t x = lds_u32(src);
+            ba = (x >> 15) & 1u;
+            bb = x >> 31;
+        }
+        const uint32_t wa = __ballot_sync(0xffffffffu, ba);
+        const uint32_t wb = __ballot_sync(0xffffffffu, bb);
         if ((z & 31) == 0) {
             sts_u32(dst, wa);
             sts_u32(dst + plane, wb);
@@ -132,7 +166,8 @@ __device__ __noinline__ uint32_t syndrome_bitsliced_h2(uint32_t app_s, uint32_t 
     if (__syncthreads_or(fb != 0u)) f |= 0x80000000u;
     const bool need_ext = (live_a && !(f & 0x00008000u)) || (live_b && !(f & 0x80000000u));
     if (!need_ext || n_rows <= 4) return f;
-    pack_hard_bits_h2(app_s, hb_s, Z, kCore, min(S::kCols, S::kKcols + n_rows), S::kCols, z, 4, my_rec, pol);
+    const ulonglong2 m = ext_hard_mask_h2(my_rec, pol, n_rows, app_s + (uint32_t)(kCore * Z + z) * 4u, (uint32_t)Z * 4u);
+    pack_hard_bits_h2(app_s, hb_s, Z, kCore, min(S::kCols, S::kKcols + n_rows), S::kCols, z, 4, m.x, m.y);
     __syncthreads();
     fa = 0; fb = 0;
     for (int r = 4 + lane; r < n_rows; r += 32) {
@@ -153,11 +188,12 @@ __device__ __noinline__ uint32_t syndrome_bitsliced_h2(uint32_t app_s, uint32_t 
 // out of line, two stages: see syndrome_unrolled_core / _ext in decode_kernel.cuh
 template <int BG, bool FULL>
 __device__ __noinline__ uint32_t syndrome_unrolled_core_h2(const DecArgs &a, const Lane l) {
-    return SyndromeRowsH2<BG, 0, 4, FULL>::run(a, l, nullptr, 0ull, 0u);
+    return SyndromeRowsH2<BG, 0, 4, FULL>::run(a, l, 0ull, 0ull, 0u);
 }
 template <int BG, bool FULL>
 __device__ __noinline__ uint32_t syndrome_unrolled_ext_h2(const DecArgs &a, const Lane l, const uint32_t *my_rec, const uint64_t pol) {
-    return SyndromeRowsH2<BG, 4, BgShape<BG>::kRows, FULL>::run(a, l, my_rec, pol, 0u);
+    const ulonglong2 m = ext_hard_mask_h2(my_rec, pol, a.n_rows, a.smem_base + l.slot_off + l.zoff + (uint32_t)((a.kcols + 4) * a.Z) * 4u, (uint32_t)a.Z * 4u);
+    return SyndromeRowsH2<BG, 4, BgShape<BG>::kRows, FULL>::run(a, l, m.x, m.y, 0u);
 }
 
 template <int DEG>
@@ -338,7 +374,7 @@ __device__ __forceinline__ uint32_t syndrome_fail_h2(const DecArgs &a, const Dec
         const int e1 = a.row_start[r + 1];
         for (int e = a.row_start[r]; e < e1; ++e) {
             uint32_t w = lds_u32(edge_addr<false>(c.l, a.ed[e]));
-            if (r >= 4 && e == e1 - 1) w = ext_app_h2(c.my_rec, r, c.pol, w);
+            if (r >= 4 && e == e1 - 1) w = ext_app_h2(c.my_rec, r, c.pol, w);   // (unbatched: this generic routine is not on any hot path)
             par ^= w;
         }
         fail |= par;

@@ -122,6 +122,7 @@ struct nrldpc_handle {
     nrldpc::HostPool *pool = nullptr;        // worker threads of the staged host path (created on first use)
     int host_threads = 0;
     long long l2_window = 0;                 // bytes of the persisting access-policy window over the c2v scratch (0: none; NRLDPC_L2_WINDOW=0/1)
+    int refill = 1;                          // NRLDPC_REFILL: 0 = never refill slots, 1 = where measured to pay (default), 2 = whenever possible
     int no_staging = 0;                      // NRLDPC_NO_STAGING=1: hand pageable buffers to cudaMemcpyAsync as they are (A/B)
     int bp_threads = 1024;           // CTA width of the sum-product kernel (NRLDPC_BP_THREADS=512 selects the 128-register build)
 };
@@ -307,10 +308,21 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
         kern = bg1 ? (masked ? (Kern)nrldpc::decode_nms_h2_kernel<1, true, true> : full ? (Kern)nrldpc::decode_nms_h2_kernel<1, true> : (Kern)nrldpc::decode_nms_h2_kernel<1, false>)
                    : (masked ? (Kern)nrldpc::decode_nms_h2_kernel<2, true, true> : full ? (Kern)nrldpc::decode_nms_h2_kernel<2, true> : (Kern)nrldpc::decode_nms_h2_kernel<2, false>);
     else if (h->dec_variant == 0)
-        kern = (Kern)nrldpc::decode_nms_kernel<0, false>;
-    else
-        kern = bg1 ? (masked ? (Kern)nrldpc::decode_nms_kernel<1, true, true> : full ? (Kern)nrldpc::decode_nms_kernel<1, true> : (Kern)nrldpc::decode_nms_kernel<1, false>)
-                   : (masked ? (Kern)nrldpc::decode_nms_kernel<2, true, true> : full ? (Kern)nrldpc::decode_nms_kernel<2, true> : (Kern)nrldpc::decode_nms_kernel<2, false>);
+        kern = (Kern)nrldpc::decode_nms_kernel<0, false, 0>;
+    else {
+        // multi-codeword CTAs under the parity-check stop track the parity variables' hard decisions in registers (mode 2)
+        const bool track = !full && h->cfg.early_term;
+        kern = bg1 ? (masked ? (Kern)nrldpc::decode_nms_kernel<1, true, 1> : full ? (Kern)nrldpc::decode_nms_kernel<1, true, 0>
+                      : track ? (Kern)nrldpc::decode_nms_kernel<1, false, 2> : (Kern)nrldpc::decode_nms_kernel<1, false, 0>)
+                   : (masked ? (Kern)nrldpc::decode_nms_kernel<2, true, 1> : full ? (Kern)nrldpc::decode_nms_kernel<2, true, 0>
+                      : track ? (Kern)nrldpc::decode_nms_kernel<2, false, 2> : (Kern)nrldpc::decode_nms_kernel<2, false, 0>);
+    }
+    // multi-codeword CTAs under the parity-check stop: every slot is refilled on its own (decode_nms_refill_kernel)
+    // (measured, profiles/r02_v4_refill_ab.txt: pays from about 24 codewords per CTA on -- Z <= 16 -- where a group waits long for
+    // its slowest member; with fewer slots the pass a refilled slot sits out costs more than the idling it removes)
+    const bool refill = !h2 && h->dec_variant != 0 && h->cfg.early_term && cwpc > 1 && batch < ((int64_t)1 << 31) - 65536 &&
+                        (h->refill == 1 ? cwpc >= 24 : h->refill == 2);
+    if (refill) kern = bg1 ? (Kern)nrldpc::decode_nms_refill_kernel<1> : (Kern)nrldpc::decode_nms_refill_kernel<2>;
     // persistent grid: every SM filled to its occupancy (2 CTAs of 384 threads at Z = 384, more for narrower CTAs);
     // attribute and occupancy are looked up once per (kernel, CTA width, shared-memory size)
     int occ = 1;
@@ -683,6 +695,7 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
     if (const char *v = getenv("NRLDPC_GRID_CAP")) h->grid_cap = std::max(0, atoi(v));
     if (getenv("NRLDPC_NO_TMA")) h->no_tma = 1;
     if (getenv("NRLDPC_NO_STAGING")) h->no_staging = 1;
+    if (const char *v = getenv("NRLDPC_REFILL")) h->refill = std::max(0, std::min(2, atoi(v)));
     if (const char *v = getenv("NRLDPC_CWPC")) h->cwpc_override = std::max(0, atoi(v));
     if (const char *v = getenv("NRLDPC_OCC_CAP")) { h->occ_cap = std::max(1, std::min(16, atoi(v))); h->occ_cap_forced = 1; }
     if (const char *v = getenv("NRLDPC_SHAPE_MODEL")) h->shape_model = atoi(v) ? 1 : 0;
@@ -1131,6 +1144,51 @@ NRLDPC_EXPORT int nrldpc_qpsk_awgn_llr(nrldpc_t *h, const uint8_t *f_bits, int64
     const long long quads = total / 4;
     nrldpc::qpsk_awgn_llr_kernel<<<grid_for(h, quads, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         f_bits, f_llr, quads, sqrtf(0.5f * variance), 2.8284271247461900976f / variance, seed, stream_id);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+NRLDPC_EXPORT int nrldpc_qpsk_awgn_rate_recover(nrldpc_t *h, const uint8_t *f_bits, int64_t batch, const nrldpc_rm *rm, float variance,
+                                                uint64_t seed, uint64_t stream_id, float *harq, float *llr_cw, void *stream) {
+    if (!h) return NRLDPC_ESHAPE;
+    nrldpc::RmGeom g{};
+    if (int rc = make_geom(h, rm, &g)) return rc;
+    if (batch < 0) return fail(h, NRLDPC_ESHAPE, "batch must be >= 0");
+    if (!(variance > 0.0f)) return fail(h, NRLDPC_EUNSUPPORTED, "variance must be positive");
+    if (g.Qm != 2) return fail(h, NRLDPC_EUNSUPPORTED, "the fused channel + rate-recovery kernel is QPSK only (Q_m = 2)");
+    if (g.E % 4) return fail(h, NRLDPC_EUNSUPPORTED, "E must be a multiple of 4 (two QPSK symbols per Philox draw)");
+    if ((size_t)g.E * sizeof(float) > kStageSmemMax) return fail(h, NRLDPC_EUNSUPPORTED, "E does not fit in shared memory; call the two stages");
+    if (batch == 0) return 0;
+    if (!f_bits || !llr_cw) return fail(h, NRLDPC_ESHAPE, "f_bits and llr_cw must not be NULL");
+    if ((reinterpret_cast<uintptr_t>(f_bits) & 3) || (reinterpret_cast<uintptr_t>(llr_cw) & 15))
+        return fail(h, NRLDPC_ESHAPE, "f_bits must be 4-byte and llr_cw 16-byte aligned");
+    ENTER_DEVICE(h);
+    const size_t smem = (size_t)g.E * sizeof(float);
+    int occ = 1;
+    if (int rc = cached_occupancy(h, reinterpret_cast<const void *>(nrldpc::qpsk_awgn_rate_recover_kernel), 512, smem, &occ)) return rc;
+    const int grid = (int)std::min<int64_t>(batch, (int64_t)h->num_sms * occ);
+    const uint32_t magic = g.EQ == 1 ? 0xffffffffu : (uint32_t)((1ull << 32) / (uint64_t)g.EQ);
+    nrldpc::qpsk_awgn_rate_recover_kernel<<<grid, 512, smem, static_cast<cudaStream_t>(stream)>>>(
+        f_bits, harq, llr_cw, batch, g, magic, sqrtf(0.5f * variance), 2.8284271247461900976f / variance, seed, stream_id);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
+NRLDPC_EXPORT int nrldpc_bler_count(nrldpc_t *h, const uint8_t *hard, const uint8_t *info, const uint8_t *tb_hat, int64_t tb_hat_stride,
+                                    const uint8_t *tb, int64_t tb_stride, const uint8_t *tb_ok, const uint8_t *cb_passed,
+                                    const int32_t *iters, int64_t n_tb, int32_t C, int32_t K_prime, int32_t A, uint8_t *latch,
+                                    uint64_t *counters, int32_t do_latch, int32_t finalize, void *stream) {
+    if (!h) return NRLDPC_ESHAPE;
+    if (n_tb < 0 || C < 1 || K_prime < 1 || K_prime > h->d.K || A < 0) return fail(h, NRLDPC_ESHAPE, "n_tb >= 0, C >= 1, 0 < K_prime <= K, A >= 0 required");
+    if (n_tb == 0) return 0;
+    if (!latch || !counters || (do_latch && (!tb_hat || !tb || !tb_ok || !iters)) || (finalize && (!hard || !info)))
+        return fail(h, NRLDPC_ESHAPE, "nrldpc_bler_count: NULL buffer");
+    ENTER_DEVICE(h);
+    nrldpc::bler_count_kernel<<<grid_for(h, n_tb * 32, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        hard, info, tb_hat, tb_hat_stride, tb, tb_stride, tb_ok, cb_passed, iters, n_tb, C, h->d.K, K_prime, A, latch,
+        reinterpret_cast<unsigned long long *>(counters), do_latch, finalize);
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
     return 0;

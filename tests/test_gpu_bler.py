@@ -180,3 +180,64 @@ def test_snr_vs_a_driver(tmp_path):
     for line, (a, v) in zip(lines, rows):
         x, y = line.split("\t")
         assert int(x) == a and abs(float(y) - v) < 1e-6
+
+
+def test_fused_channel_rate_recover_equals_two_stages():
+    """nrldpc_qpsk_awgn_rate_recover is bit-identical to nrldpc_qpsk_awgn_llr + nrldpc_rate_recover with the same
+    (seed, stream id): every rv_id, limited-buffer N_cb, wrap-around repetition (E > N_cb), filler, HARQ accumulation."""
+    import torch
+    from ldpc_3gpp_matlab_b200 import capi
+    st = torch.cuda.current_stream().cuda_stream
+    for bg, Z, Kp, E, k0, Ncb in ((1, 384, 8448, 25272, 0, 25344), (1, 384, 8000, 24000, 17 * 384, 25344), (2, 52, 416, 2000, 13 * 52, 2600),
+                                  (2, 52, 416, 6000, 25 * 52, 2000), (1, 96, 2000, 1200, 0, 6336)):
+        h = capi.Handle(bg, Z, 4, False)
+        B = 64
+        rm = capi.Rm(E, k0, Ncb, Kp, 2)
+        g = torch.Generator(device="cuda").manual_seed(Z + E)
+        f = torch.randint(0, 2, (B, E), dtype=torch.uint8, device="cuda", generator=g)
+        fl = torch.empty((B, E), dtype=torch.float32, device="cuda")
+        harq_a = torch.randn((B, h.N), dtype=torch.float32, device="cuda", generator=g)
+        harq_b = harq_a.clone()
+        out_a = torch.empty((B, h.n_cw), dtype=torch.float32, device="cuda")
+        out_b = torch.empty_like(out_a)
+        for rep, hq in enumerate(((None, None), (harq_a, harq_b), (harq_a, harq_b))):
+            h.qpsk_awgn_llr_raw(f, B, E, 0.7, 99, 5 + rep, fl, stream=st)
+            h.rate_recover_raw(fl, B, rm, hq[0], out_a, mem=capi.MEM_DEVICE, stream=st)
+            h.qpsk_awgn_rate_recover_raw(f, B, rm, 0.7, 99, 5 + rep, hq[1], out_b, stream=st)
+            torch.cuda.synchronize()
+            assert torch.equal(out_a.view(torch.int32), out_b.view(torch.int32)), (bg, Z, E, rep)
+            assert torch.equal(harq_a.view(torch.int32), harq_b.view(torch.int32))
+        h.close()
+
+
+def test_bler_counters_fused_path_equals_stagewise_path(monkeypatch):
+    """The batch loop with the fused channel + rate-recovery kernel and the device-side block-error bookkeeping returns the
+    counters of the stage-by-stage path (NRLDPC_BLER_UNFUSED) on the same seeds, and those equal a host recount from the
+    buffers: single block, segmented transport block (C = 2) with HARQ, and the no-CRC criterion."""
+    from ldpc_3gpp_matlab_b200.bler import BlerSimulator
+    for kw, esn0 in ((dict(A=8424, R=1 / 3, BG=1, batch=256), -0.35), (dict(A=3842, R=0.5, BG=2, batch=128, rv_id_sequence=(0, 2)), -3.0),
+                     (dict(A=400, R=0.2, BG=2, batch=512, crc=False), -2.2), (dict(A=1000, R=0.8, BG=1, batch=128, rv_id_sequence=(0, 1, 2)), -1.5)):
+        res = []
+        for unfused in ("", "1"):
+            if unfused:
+                monkeypatch.setenv("NRLDPC_BLER_UNFUSED", "1")
+            else:
+                monkeypatch.delenv("NRLDPC_BLER_UNFUSED", raising=False)
+            sim = BlerSimulator(iterations=8, seed=11, **kw)
+            tot = np.zeros(4, dtype=np.int64)
+            for _ in range(2):
+                c, any_ok = sim.run_batch(esn0)
+                tot += c
+            hard, info = sim.hard.cpu().numpy(), sim.info.cpu().numpy()
+            res.append((tot.copy(), hard, info))
+            if len(sim.rvs) == 1:                      # last batch, host recount of the bit errors of failed blocks
+                wrong = (hard[:, :sim.Kp] != info[:, :sim.Kp]).reshape(sim.B, sim.C, -1).sum(axis=(1, 2))
+                latch = sim.latch.cpu().numpy()
+                assert int(c[2]) == int((wrong * (latch == 0)).sum()) and int(c[1]) == int((latch == 0).sum())
+                assert int(c[3]) == int(sim.iters.sum())
+            sim.close()
+        assert (res[0][0] == res[1][0]).all(), (kw, res[0][0], res[1][0])
+        assert (res[0][1] == res[1][1]).all()
+        assert res[0][0][0] == 2 * kw["batch"]
+        if len(kw.get("rv_id_sequence", (0,))) == 1:
+            assert 0 < res[0][0][1] < res[0][0][0]      # the point sits in the waterfall: both outcomes occur

@@ -741,3 +741,37 @@ def test_forced_cta_shapes_are_bit_identical(capi, O, f16, monkeypatch):
                 h.close()
                 assert (out["hard"] == ref["hard"]).all() and _same_bits(out["app"], ref["app"]), (bg, Z, et, cw, cap)
                 assert (out["iters"] == ref["iters"]).all() and (out["parity_ok"] == ref["parity_ok"]).all(), (bg, Z, et, cw, cap)
+
+
+@pytest.mark.parametrize("bg,Z,rows,B", [(2, 52, 33, 3001), (1, 8, 46, 4000), (2, 6, 13, 5000), (1, 96, 20, 700), (2, 176, 42, 500), (1, 30, 46, 1500)])
+def test_slot_refill_under_the_stop(capi, O, bg, Z, rows, B, monkeypatch):
+    """Multi-codeword CTAs with 'Parity check satisfied' (NRLDPCDecoder.m:120): slots are refilled one by one as their
+    codewords converge (decode_nms_refill_kernel).  Batches of many CTA loads with a mix of operating points (codewords
+    needing 1 ... max iterations side by side, some never converging), ragged tail, soft output: decisions, iteration
+    counts, parity flags and APP bit patterns equal the oracle and the group kernel (NRLDPC_REFILL=0)."""
+    rng = np.random.default_rng(Z + B)
+    d = O.dims(bg, Z)
+    E = (d["kcols"] - 2 + rows) * Z
+    parts = [make_llr(O, bg, Z, B // 3 + (i < B % 3), E, esn0, rng, filler=(Z if Z > 7 else 0)) for i, esn0 in enumerate((6.0, 1.0, -2.5))]
+    info = np.concatenate([p[0] for p in parts]); llr = np.concatenate([p[1] for p in parts])
+    perm = rng.permutation(B)
+    info, llr = info[perm], np.ascontiguousarray(llr[perm])
+    ref = O.decode_nms(bg, Z, llr, 7, early_term=True, n_rows=rows)
+    assert ref["iters"].min() < 3 and ref["iters"].max() == 7
+    monkeypatch.setenv("NRLDPC_REFILL", "2")              # refill whenever possible (the default enables it for wide groups only)
+    h = capi.Handle(bg, Z, 7, True)
+    out = h.decode(llr, n_rows=rows, want_soft=True)
+    out2 = h.decode(llr, n_rows=rows)                     # no soft output: other code path for the final records
+    h.close()
+    monkeypatch.setenv("NRLDPC_REFILL", "0")              # whole groups, parity bits tracked in registers
+    h = capi.Handle(bg, Z, 7, True)
+    grp = h.decode(llr, n_rows=rows, want_soft=True)
+    h.close()
+    monkeypatch.delenv("NRLDPC_REFILL")
+    h = capi.Handle(bg, Z, 7, True)
+    dflt = h.decode(llr, n_rows=rows, want_soft=True)
+    h.close()
+    for r in (out, grp, dflt):
+        assert (r["hard"] == ref["hard"]).all() and _same_bits(r["app"], ref["app"])
+        assert (r["iters"] == ref["iters"]).all() and (r["parity_ok"] == ref["parity_ok"]).all()
+    assert (out2["hard"] == ref["hard"]).all() and (out2["iters"] == ref["iters"]).all() and (out2["parity_ok"] == ref["parity_ok"]).all()
