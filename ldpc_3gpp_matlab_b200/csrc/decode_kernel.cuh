@@ -80,7 +80,8 @@ struct DecArgs {
     uint32_t alpha_h2;       // {fp16(alpha), fp16(alpha)} for the packed-half kernel
     int rec_group;           // CTAs that share one [kRecWords][kRecStride] scratch block (CTA b uses thread columns (b % rec_group) * blockDim.x ...)
     uint32_t *c2v;           // [ceil(grid / rec_group)][kRecWords][kRecStride]; float32 record = {alpha*min1|sgn, alpha*min2|sgn, argmin | signbits << 5}
-    int *work_counter;
+    int *work_counter;       // device ticket counter: never reset between launches, the host passes the value it has reached ...
+    unsigned int work_base;  // ... so ticket - work_base is this launch's group (codeword) index: no memset node per launch
     unsigned short row_start[kMaxRows + 2];
     uint2 ed[kMaxEdges];
 };
@@ -815,7 +816,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
 
     while (true) {
         __syncthreads();  // previous group's outputs are out of smem
-        if (tid == 0) s_group = atomicAdd(a.work_counter, 1);
+        if (tid == 0) s_group = (int)((unsigned int)atomicAdd(a.work_counter, 1) - a.work_base);
         __syncthreads();
         const long long group = s_group;
         if (group >= n_groups) break;
@@ -978,7 +979,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_refill_
 
     int st = ST_IDLE, my_cw = -1, my_it = 0;
     if (lane_ok && z == 0) {
-        const int n = atomicAdd(a.work_counter, 1);
+        const int n = (int)((unsigned int)atomicAdd(a.work_counter, 1) - a.work_base);
         s_cw[slot] = n < batch ? n : -1;
     }
     if (tid < 2 * a.cwpc) s_flag[tid] = 0;
@@ -1048,7 +1049,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_refill_
                 if (z == 0) {
                     if (a.iters) a.iters[my_cw] = my_it;
                     if (a.ok) a.ok[my_cw] = (uint8_t)ok;
-                    const int n = atomicAdd(a.work_counter, 1);
+                    const int n = (int)((unsigned int)atomicAdd(a.work_counter, 1) - a.work_base);
                     s_cw[slot] = n < batch ? n : -1;
                 }
             }

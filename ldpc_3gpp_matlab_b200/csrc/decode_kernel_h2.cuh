@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
 
     while (true) {
         __syncthreads();  // previous group's outputs are out of smem
-        if (tid == 0) s_group = atomicAdd(a.work_counter, 1);
+        if (tid == 0) s_group = (int)((unsigned int)atomicAdd(a.work_counter, 1) - a.work_base);
         __syncthreads();
         const long long group = s_group;
         if (group >= n_groups) break;

@@ -67,7 +67,9 @@ struct PipeSlot {
     size_t cap_cw = 0;          // capacity in codewords of the decode staging
     size_t cap_bytes = 0;       // capacity of the generic staging buffers
     uint32_t *c2v = nullptr;    // decode scratch (one set per slot: kernels of different slots may overlap)
-    int *counter = nullptr;
+    int *counter = nullptr;     // ticket counter of the decode kernels (zeroed once; see DecArgs::work_base)
+    unsigned int tickets = 0;   // value the min-sum launches enqueued so far will leave in `counter`
+    bool counter_dirty = false; // a sum-product launch or a failed launch used the counter: zero it before the next min-sum launch
     size_t scratch_recs = 0;
     // pinned host ring of the staged host path (pageable and / or float64 caller buffers, see host_staging.h)
     unsigned char *h_in = nullptr;
@@ -122,6 +124,7 @@ struct nrldpc_handle {
     nrldpc::HostPool *pool = nullptr;        // worker threads of the staged host path (created on first use)
     int host_threads = 0;
     long long l2_window = 0;                 // bytes of the persisting access-policy window over the c2v scratch (0: none; NRLDPC_L2_WINDOW=0/1)
+    int zero_copy_max = 2;                   // host-memory decodes of up to this many codewords read / write pinned host memory directly (NRLDPC_ZERO_COPY_MAX, 0 = off)
     int refill = 1;                          // NRLDPC_REFILL: 0 = never refill slots, 1 = where measured to pay (default), 2 = whenever possible
     int no_staging = 0;                      // NRLDPC_NO_STAGING=1: hand pageable buffers to cudaMemcpyAsync as they are (A/B)
     int bp_threads = 1024;           // CTA width of the sum-product kernel (NRLDPC_BP_THREADS=512 selects the 128-register build)
@@ -239,8 +242,8 @@ size_t decode_smem_for(const nrldpc_dims &d, int cwpc) {
 
 // CTA shape of the decode kernels: codewords (float32) or codeword pairs (packed half) per CTA and the cap on resident
 // CTAs per SM.  Default rule: as many codewords as fit in 384 threads (and in the shared memory of two CTAs per SM), at
-// most 4 CTAs per SM.  Where the B200 scan (tools/gpu_shape_scan.py -> decode_shapes.inc) measured another shape at least
-// 2 % faster, that shape is used.  What the scan showed (profiles/r02_shape_scan_*.jsonl):
+// most 4 CTAs per SM.  Where the B200 scans (tools/gpu_shape_scan.py -> decode_shapes.inc; one with fixed iterations, one with
+// the parity-check stop, whose best shapes differ) measured another shape at least 2-3 % faster, that shape is used.  What the scan showed (profiles/r02_shape_scan_*.jsonl):
 //   * warps are bound to the SM's four schedulers by (warp index in the CTA) mod 4: Z = 224 (three 7-warp CTAs per SM)
 //     runs at exactly 7/8 of the Z = 384 rate per lane, so CTAs of 4k warps are preferred when lanes are not wasted;
 //   * many narrow one-codeword CTAs per SM lose on base graph 1 (BG1 Z = 128: 6 x 4 warps 8.4 Gb/s against 2 x 12 warps
@@ -267,7 +270,7 @@ void choose_decode_shape(nrldpc_handle *h) {
     h->cwpc = legacy;
     if (h->shape_model) {
         const int zi = lifting_index(d.Z);
-        const unsigned char *e = nrldpc_decode_shape[h->cfg.llr_dtype == NRLDPC_F16X2 ? 1 : 0][d.bg - 1][zi < 0 ? 0 : zi];
+        const unsigned char *e = nrldpc_decode_shape[h->cfg.early_term ? 1 : 0][h->cfg.llr_dtype == NRLDPC_F16X2 ? 1 : 0][d.bg - 1][zi < 0 ? 0 : zi];
         if (zi >= 0 && e[0] > 0 && e[0] <= cmax && decode_smem_for(d, e[0]) <= 227 * 1024) {
             h->cwpc = e[0];
             if (!h->occ_cap_forced) h->occ_cap = e[1];
@@ -277,7 +280,11 @@ void choose_decode_shape(nrldpc_handle *h) {
 }
 
 int ensure_scratch(nrldpc_handle *h, PipeSlot &s, size_t recs) {
-    if (!s.counter) CUDA_TRY(h, cudaMalloc(&s.counter, sizeof(int)));
+    if (!s.counter) {
+        CUDA_TRY(h, cudaMalloc(&s.counter, sizeof(int)));
+        CUDA_TRY(h, cudaMemset(s.counter, 0, sizeof(int)));
+        s.tickets = 0; s.counter_dirty = false;
+    }
     if (recs <= s.scratch_recs) return 0;
     if (s.c2v) cudaFree(s.c2v);
     s.c2v = nullptr; s.scratch_recs = 0;
@@ -334,7 +341,15 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
     // scratch stays about (threads resident on the device) x 145 words whatever the CTA width (it has to fit the L2)
     const int rec_group = std::max(1, nrldpc::kRecStride / threads);
     if (int rc = ensure_scratch(h, s, (size_t)((grid + rec_group - 1) / rec_group) * nrldpc::kRecWords * nrldpc::kRecStride)) return rc;
-    CUDA_TRY(h, cudaMemsetAsync(s.counter, 0, sizeof(int), stream));
+    // a launch that is being captured into a CUDA graph must be replayable: it zeroes the counter itself (memset node) and
+    // counts from zero; the host's running ticket count is then void and the next ordinary launch starts afresh
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+    const bool capturing = cap != cudaStreamCaptureStatusNone;
+    if (s.counter_dirty || capturing) {
+        CUDA_TRY(h, cudaMemsetAsync(s.counter, 0, sizeof(int), stream));
+        s.tickets = 0; s.counter_dirty = capturing;
+    }
     nrldpc::DecArgs &a = h->dec_args;  // tables were filled at create()
     a.llr = llr; a.hard = hard; a.soft = soft; a.iters = iters; a.ok = ok;
     a.batch = batch; a.Z = Z; a.ncols = h->d.cols; a.kcols = h->d.kcols; a.n_rows = n_rows;
@@ -342,7 +357,10 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
     a.slot_stride = decode_slot_stride(h->d.cols, Z, cwpc);
     a.cwpc = cwpc; a.rec_group = rec_group; a.alpha = h->cfg.alpha; a.l2_pin = h->l2_pin; a.one = 1;
     a.bitsliced_min_rows = h->bitsliced_min_rows; a.staged_min_rows = h->staged_min_rows;
-    a.c2v = s.c2v; a.work_counter = s.counter;
+    a.c2v = s.c2v; a.work_counter = s.counter; a.work_base = s.tickets;
+    // tickets this launch draws: one per group (refill kernel: per codeword) plus the failing fetch that ends every CTA (slot)
+    if (!capturing)
+        s.tickets += refill ? (unsigned int)batch + (unsigned int)grid * (unsigned int)cwpc : (unsigned int)n_groups + (unsigned int)grid;
     const uint32_t ah = __half_as_ushort(__float2half_rn(h->cfg.alpha));
     a.alpha_h2 = ah | (ah << 16);
     if (a.smem_base != h->smem_base) {
@@ -367,7 +385,7 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
     } else {
         kern<<<grid, threads, smem, stream>>>(a);
     }
-    CUDA_TRY(h, cudaGetLastError());
+    if (cudaError_t e_ = cudaGetLastError()) { s.counter_dirty = true; return fail(h, NRLDPC_ECUDA, "decode launch: %s", cudaGetErrorString(e_)); }
     h->launches += 1;
     return 0;
 }
@@ -387,6 +405,7 @@ int launch_decode_bp(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const T
     const int grid = (int)std::min<int64_t>(batch, (int64_t)h->num_sms * occ);
     const size_t stride = (size_t)h->d.edges * Z;
     if (!s.counter) CUDA_TRY(h, cudaMalloc(&s.counter, sizeof(int)));
+    s.counter_dirty = true;   // this kernel counts from zero (memset below)
     if ((size_t)grid * stride > s.rmsg_cap) {
         cudaFree(s.rmsg);
         s.rmsg = nullptr; s.rmsg_cap = 0;
@@ -695,6 +714,7 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
     if (const char *v = getenv("NRLDPC_GRID_CAP")) h->grid_cap = std::max(0, atoi(v));
     if (getenv("NRLDPC_NO_TMA")) h->no_tma = 1;
     if (getenv("NRLDPC_NO_STAGING")) h->no_staging = 1;
+    if (const char *v = getenv("NRLDPC_ZERO_COPY_MAX")) h->zero_copy_max = std::max(0, std::min(64, atoi(v)));
     if (const char *v = getenv("NRLDPC_REFILL")) h->refill = std::max(0, std::min(2, atoi(v)));
     if (const char *v = getenv("NRLDPC_CWPC")) h->cwpc_override = std::max(0, atoi(v));
     if (const char *v = getenv("NRLDPC_OCC_CAP")) { h->occ_cap = std::max(1, std::min(16, atoi(v))); h->occ_cap_forced = 1; }
@@ -915,6 +935,38 @@ int decode_impl(nrldpc_t *h, const void *llr, int in_kind, int64_t batch, int32_
     // persistent-grid wave of codewords (doubled while small) so the un-overlapped tail stays short.
     if (int rc = ensure_pipe(h)) return rc;
     if (h->dev_used) CUDA_TRY(h, cudaStreamWaitEvent(h->pipe[0].stream, h->dev_done, 0));
+
+    // A few codewords (the reference calls step() with ONE code block, NRLDPCDecoder.m:257-266): no copy engine at all.
+    // The kernel reads the LLRs straight from pinned host memory (its bulk copy crosses PCIe itself) and writes the
+    // decisions straight back -- one launch and one synchronisation instead of H2D + launch + D2H + synchronisation.
+    // Caller buffers that are pageable, float64 or misaligned pass through the pinned ring on the caller's thread.
+    if (batch <= h->zero_copy_max && !bp && in_kind != kInF16 && !app_soft) {
+        PipeSlot &s = h->pipe[0];
+        if (int rc = ensure_host_ring(h, s, (size_t)batch * h->d.n_cw * sizeof(float), (size_t)batch, true, true)) return rc;
+        const float *src = static_cast<const float *>(llr);
+        const size_t total = (size_t)batch * h->d.n_cw;
+        if (in_kind == kInF64) {
+            nrldpc::narrow_f64_to_f32(static_cast<const double *>(llr), reinterpret_cast<float *>(s.h_in), total);
+            src = reinterpret_cast<const float *>(s.h_in);
+        } else if (is_pageable(llr) || (reinterpret_cast<uintptr_t>(llr) & 15)) {
+            memcpy(s.h_in, llr, total * sizeof(float));
+            src = reinterpret_cast<const float *>(s.h_in);
+        }
+        const bool out_direct = !is_pageable(info_hard) && !(reinterpret_cast<uintptr_t>(info_hard) & 3) &&
+                                (!iters || !is_pageable(iters)) && (!parity_ok || !is_pageable(parity_ok));
+        uint8_t *d_hard = out_direct ? info_hard : s.h_hard;
+        int32_t *d_iters = !iters ? nullptr : out_direct ? iters : s.h_iters;
+        uint8_t *d_ok = !parity_ok ? nullptr : out_direct ? parity_ok : s.h_ok;
+        if (int rc = launch_decode(h, s, s.stream, src, batch, n_rows, d_hard, nullptr, d_iters, d_ok)) return rc;
+        CUDA_TRY(h, cudaStreamSynchronize(s.stream));
+        if (!out_direct) {
+            memcpy(info_hard, s.h_hard, (size_t)batch * h->d.K);
+            if (iters) memcpy(iters, s.h_iters, (size_t)batch * sizeof(int32_t));
+            if (parity_ok) memcpy(parity_ok, s.h_ok, (size_t)batch);
+        }
+        return 0;
+    }
+
     const int cwpc = h->cwpc;
     const int64_t wave = bp ? (int64_t)h->num_sms
                             : (int64_t)h->num_sms * nrldpc::kDecCtasPerSm * cwpc *

@@ -27,6 +27,28 @@ for name, kw in (("nms_f32", {}), ("nms_f16x2", dict(llr_dtype=capi.F16X2)), ("b
         print(rows[-1], flush=True)
     h.close()
 
+# the call the MEX gateway makes for one code block: nrldpc_decode64 on ordinary (pageable) float64 memory, decisions into
+# pageable memory; and the same pinned-float32 call with the direct host-memory path switched off (A/B)
+import os
+llr64 = llr[:1].cpu().numpy().astype(np.float64)
+hard_np = np.empty((1, h0.K), dtype=np.uint8)
+for label, env in (("nms_f32 decode64 pageable float64 (gateway call)", None), ("nms_f32 pinned, NRLDPC_ZERO_COPY_MAX=0", "0")):
+    if env is not None:
+        os.environ["NRLDPC_ZERO_COPY_MAX"] = env
+    hh = capi.Handle(w["bg"], w["Z"], 8, False)
+    lh = torch.empty((1, hh.n_cw), dtype=torch.float32, pin_memory=True); lh.copy_(llr[:1])
+    ph = torch.empty((1, hh.K), dtype=torch.uint8, pin_memory=True)
+    call = (lambda: hh.decode64_raw(llr64, 1, hard_np, mem=capi.MEM_HOST)) if env is None else (lambda: hh.decode_raw(lh, 1, ph, mem=capi.MEM_HOST))
+    for _ in range(5):
+        call()
+    ts = []
+    for _ in range(100):
+        t0 = time.perf_counter(); call(); ts.append(time.perf_counter() - t0)
+    rows.append({"mode": label, "batch": 1, "median_us": round(1e6 * float(np.median(ts)), 1), "min_us": round(1e6 * min(ts), 1)})
+    print(rows[-1], flush=True)
+    hh.close()
+    os.environ.pop("NRLDPC_ZERO_COPY_MAX", None)
+
 # where the time of a one-codeword call goes: the kernel alone on device buffers (CUDA events over back-to-back launches),
 # and the reference's whole per-block RX chain (NRLDPCDecoder.m:133-140: rate recovery -> decode -> CRC) on device buffers
 h = capi.Handle(w["bg"], w["Z"], 8, False)

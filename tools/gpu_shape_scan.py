@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--early-term", action="store_true")
     ap.add_argument("--caps", default="4,8")
+    ap.add_argument("--esn0", type=float, default=None)
     args = ap.parse_args()
     import torch
     from ldpc_3gpp_matlab_b200 import capi
@@ -45,7 +46,7 @@ def main():
         fl = torch.empty((B, E), dtype=torch.float32, device="cuda")
         llr = torch.empty((B, ncw), dtype=torch.float32, device="cuda")
         h0.rate_match_raw(cw[:B], B, rm, f, mem=capi.MEM_DEVICE, stream=st)
-        h0.qpsk_awgn_llr_raw(f, B, E, 10 ** (-(0.0 if bg == 1 else 0.5) / 10), 1234, Z, fl, stream=st)
+        h0.qpsk_awgn_llr_raw(f, B, E, 10 ** (-((0.0 if bg == 1 else 0.5) if args.esn0 is None else args.esn0) / 10), 1234, Z, fl, stream=st)
         h0.rate_recover_raw(fl, B, rm, None, llr, mem=capi.MEM_DEVICE, stream=st)
         h0.close()
         ref = None
