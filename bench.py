@@ -373,7 +373,7 @@ def main():
     numa_bound = D.bind_to_gpu_numa_node(phys_gpu) if world > 1 else False
     stream = torch.cuda.current_stream().cuda_stream
     # host staging threads of the host-memory path (nrldpc_decode64 on pageable doubles): share the cores between the ranks
-    os.environ.setdefault("NRLDPC_HOST_THREADS", str(max(1, min(16, (os.cpu_count() or 1) // world))))
+    os.environ.setdefault("NRLDPC_HOST_THREADS", str(max(1, min(32, (os.cpu_count() or 1) // world))))
 
     f16 = args.llr_dtype == "f16x2"
     h = capi.Handle(w["bg"], w["Z"], w["iters"], bool(w["early_term"]), device=local_rank,

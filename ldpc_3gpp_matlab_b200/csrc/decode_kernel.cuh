@@ -282,7 +282,7 @@ __device__ __forceinline__ void row_gather(const Lane &l, const uint2 *__restric
                                            const uint32_t om2, const uint32_t ometa, RowState<DEG> &s) {
     constexpr int NE = IDENT_LAST ? DEG - 1 : DEG;   // edges whose variable has other checks too
     float m1 = 0.f, m2 = 0.f;
-    uint32_t sx = 0, ts = 0;
+    uint32_t ts = 0, tp = 0;
     const uint32_t oarg = ometa & 31u;
 #pragma unroll
     for (int e = 0; e < DEG; ++e) {
@@ -308,10 +308,13 @@ __device__ __forceinline__ void row_gather(const Lane &l, const uint2 *__restric
             m2 = fminf(m2, fmaxf(ab, m1));
             m1 = fminf(m1, ab);
         }
-        sx ^= __float_as_uint(tt);
         if (e < NE) ts = __funnelshift_l(__float_as_uint(tt), ts, 1);  // ts = ts << 1 | signbit(tt)
+        else tp = __float_as_uint(tt);
     }
-    s.m1 = m1; s.m2 = m2; s.sx = sx; s.ts = ts;
+    // the row's sign product = parity of the number of negative t's: one POPC over the collected sign bits per ROW instead of
+    // one XOR per EDGE (the degree-1 edge's sign is not recorded in ts: it is folded in before the count)
+    const uint32_t all = IDENT_LAST ? __funnelshift_l(tp, ts, 1) : ts;
+    s.m1 = m1; s.m2 = m2; s.sx = (uint32_t)__popc(all) << 31; s.ts = ts;
 }
 
 // second half: new messages, APP write-back, the row's new record.  PAR: also XOR the new APP values into `par` -- its sign

@@ -88,7 +88,7 @@ int default_host_threads() {
     int n = (int)std::thread::hardware_concurrency();
     cpu_set_t set;
     if (sched_getaffinity(0, sizeof(set), &set) == 0) n = CPU_COUNT(&set);
-    return std::max(1, std::min(16, n));
+    return std::max(1, std::min(32, n));
 }
 
 #if defined(__x86_64__)

@@ -26,7 +26,7 @@ private:
     Impl *p_;
 };
 
-// NRLDPC_HOST_THREADS, else min(16, CPUs this process may run on)
+// NRLDPC_HOST_THREADS, else min(32, CPUs this process may run on)
 int default_host_threads();
 
 // out[i] = (float)in[i], round to nearest even (+inf stays +inf, NaN stays NaN): the same rounding as the device's

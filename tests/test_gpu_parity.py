@@ -775,3 +775,48 @@ def test_slot_refill_under_the_stop(capi, O, bg, Z, rows, B, monkeypatch):
         assert (r["hard"] == ref["hard"]).all() and _same_bits(r["app"], ref["app"])
         assert (r["iters"] == ref["iters"]).all() and (r["parity_ok"] == ref["parity_ok"]).all()
     assert (out2["hard"] == ref["hard"]).all() and (out2["iters"] == ref["iters"]).all() and (out2["parity_ok"] == ref["parity_ok"]).all()
+
+
+def test_device_mode_streams_and_graph_capture(capi, O):
+    """NRLDPC_MEM_DEVICE decodes of one handle from two streams (the handle's scratch is shared: the library orders the
+    launches) and a decode captured into a CUDA graph and replayed (the work counter must not depend on host-side state
+    baked in at capture time): every result equals the oracle."""
+    import torch
+    rng = np.random.default_rng(41)
+    bg, Z = 1, 96
+    d = O.dims(bg, Z)
+    info, llr_np = make_llr(O, bg, Z, 300, d["N"], 0.8, rng)
+    ref = O.decode_nms(bg, Z, llr_np, 6, early_term=True)
+    llr = torch.from_numpy(llr_np).cuda()
+    h = capi.Handle(bg, Z, 6, True)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    outs = []
+    for i in range(6):
+        st = (s1, s2)[i % 2]
+        hard = torch.zeros((300, d["K"]), dtype=torch.uint8, device="cuda")
+        it = torch.zeros(300, dtype=torch.int32, device="cuda")
+        with torch.cuda.stream(st):
+            h.decode_raw(llr, 300, hard, iters=it, mem=capi.MEM_DEVICE, stream=st.cuda_stream)
+        outs.append((hard, it))
+    torch.cuda.synchronize()
+    for hard, it in outs:
+        assert (hard.cpu().numpy() == ref["hard"]).all() and (it.cpu().numpy() == ref["iters"]).all()
+    # graph capture + replay
+    hard = torch.zeros((300, d["K"]), dtype=torch.uint8, device="cuda")
+    it = torch.zeros(300, dtype=torch.int32, device="cuda")
+    g = torch.cuda.CUDAGraph()
+    cap_stream = torch.cuda.Stream()
+    with torch.cuda.stream(cap_stream):
+        h.decode_raw(llr, 300, hard, iters=it, mem=capi.MEM_DEVICE, stream=cap_stream.cuda_stream)   # warm-up outside capture
+    torch.cuda.synchronize()
+    with torch.cuda.graph(g, stream=cap_stream):
+        h.decode_raw(llr, 300, hard, iters=it, mem=capi.MEM_DEVICE, stream=torch.cuda.current_stream().cuda_stream)
+    for _ in range(3):
+        hard.zero_(); it.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert (hard.cpu().numpy() == ref["hard"]).all() and (it.cpu().numpy() == ref["iters"]).all()
+    # an ordinary launch after the captured one starts from a clean counter again
+    out = h.decode(llr_np)
+    assert (out["hard"] == ref["hard"]).all() and (out["iters"] == ref["iters"]).all()
+    h.close()
