@@ -23,6 +23,8 @@
  *     process-wide, so live handles of different (BG, Z) never invalidate each other's launches).
  *   - NRLDPC_MEM_DEVICE decodes of ONE handle share its scratch: launches on different streams are ordered
  *     behind each other by the library (an event wait), they do not overlap; use one handle per stream for overlap.
+ *     A decode captured into a CUDA graph is replayable (it resets its own work counter) but takes no part in that
+ *     ordering: do not replay the graph concurrently with other work on the same handle.
  *   - every entry point restores the caller's current CUDA device before it returns.
  */
 #ifndef NRLDPC_B200_H

@@ -377,7 +377,6 @@ struct DecCtx {
     uint64_t pol;
     uint4 cur, cur2; // prefetched records of the next layer (and of its partner when the next layer is a pair)
     bool done;       // this thread does no row work (inactive lane, or its codeword has converged)
-    bool live;       // MASKED kernels: this lane owns a check (tid < Z); the lanes that pad the last warp shadow lanes 0.. and never store
     int last_fail;   // FULL kernels, every base row active: some check of the iteration's last layer is unsatisfied (CTA-uniform)
     uint32_t ext_lo, ext_hi;   // TRACK kernels: hard decisions of the degree-1 parity variables, bit (r - 4) of the pair = extension row r
     uint4 last_rec;  // FULL kernels, trimmed row count: the record the last ACTIVE row wrote in this iteration (kept in registers
@@ -685,8 +684,9 @@ __device__ __forceinline__ void iteration_looped(const DecArgs &a, DecCtx &c, co
 // across).  (Prefetching unconditionally over zeroed records was measured 0.5-1 % slower in this kernel and
 // 7 % slower in the packed-half kernel.)
 // FULL: every thread of the CTA runs the row code for the whole decode (one codeword per CTA): no per-thread activity
-// test.  MASKED (FULL only): Z is not a multiple of 32, the lanes that pad the last warp shadow lanes 0.. (same loads,
-// same arithmetic) and only their stores are predicated off -- the CTA-uniform code serves every one-codeword CTA.
+// test.  MASKED (FULL only): Z is not a multiple of 32.  The CTA is launched with exactly Z threads (its last warp is partly
+// filled -- barriers and the barrier reductions count warps, so nothing else changes); the flavour only rules out the
+// warp-ballot (bit-sliced) syndrome.  The CTA-uniform code thus serves every one-codeword CTA.
 // MODE: 0 plain, 1 MASKED (FULL only), 2 TRACK (multi-codeword kernels under the stop: see row_scatter_par)
 template <int BG, int R, bool FULL, int MODE = 0>
 struct UnrolledRows {
@@ -719,9 +719,9 @@ struct UnrolledRows {
                 RowState<DEG2> s1;
                 row_gather<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur.x, c.cur.y, c.cur.z, s0);
                 row_gather<DEG2, (R >= 4), FULL>(c.l, a.ed + E1, c.cur2.x, c.cur2.y, c.cur2.z, s1);
-                const uint4 rec0 = row_scatter_par<DEG, (R >= 4), kLastPair, kPos0>(s0, a.alpha, par, !MASKED || c.live, (R - 4) < 32 ? &c.ext_lo : &c.ext_hi);
-                const uint4 rec1 = row_scatter_par<DEG2, (R >= 4), kLastPair, kPos1>(s1, a.alpha, par, !MASKED || c.live, (R + 1 - 4) < 32 ? &c.ext_lo : &c.ext_hi);
-                if (store_rec && (!MASKED || c.live)) {
+                const uint4 rec0 = row_scatter_par<DEG, (R >= 4), kLastPair, kPos0>(s0, a.alpha, par, true, (R - 4) < 32 ? &c.ext_lo : &c.ext_hi);
+                const uint4 rec1 = row_scatter_par<DEG2, (R >= 4), kLastPair, kPos1>(s1, a.alpha, par, true, (R + 1 - 4) < 32 ? &c.ext_lo : &c.ext_hi);
+                if (store_rec) {
                     st_rec(c.my_rec, R == 0 ? a.n_rows : R, rec0, c.pol);
                     st_rec(c.my_rec, R + 1, rec1, c.pol);
                 }
@@ -732,7 +732,7 @@ struct UnrolledRows {
             // The hard decisions written by the LAST layer of an iteration are final, so an unsatisfied check there
             // proves that the codeword has not converged: with every base row active the layer's barrier doubles as the
             // CTA-wide OR of those parities and the kernel skips the syndrome after most iterations (exact either way).
-            if (kLastPair) c.last_fail = __syncthreads_or((int)(par >> 31) & (int)(!MASKED || c.live));
+            if (kLastPair) c.last_fail = __syncthreads_or((int)(par >> 31));
             else __syncthreads();
             UnrolledRows<BG, (PAIR ? R + 2 : BgShape<BG>::kRows), FULL, MODE>::run(a, c, ld_from, ld_to, store_rec, rec_last);
         } else {
@@ -743,9 +743,9 @@ struct UnrolledRows {
                     nxt = ld_rec(c.my_rec, R + 1, c.pol);   // slot R+1; slot n_rows holds layer 0
                     if (!PAIR && pair_first<BG>(R + 1)) nxt2 = ld_rec(c.my_rec, R + 2, c.pol);
                 }
-                const uint4 rec = process_row<DEG, (R >= 4), FULL, kPos0>(c.l, a.ed + E0, c.cur.x, c.cur.y, c.cur.z, a.alpha, !MASKED || c.live,
+                const uint4 rec = process_row<DEG, (R >= 4), FULL, kPos0>(c.l, a.ed + E0, c.cur.x, c.cur.y, c.cur.z, a.alpha, true,
                                                                              (R - 4) < 32 ? &c.ext_lo : &c.ext_hi);
-                if (store_rec && (!MASKED || c.live)) st_rec(c.my_rec, R == 0 ? a.n_rows : R, rec, c.pol);
+                if (store_rec) st_rec(c.my_rec, R == 0 ? a.n_rows : R, rec, c.pol);
                 c.cur = nxt;
                 c.cur2 = nxt2;
                 if (FULL && R >= 4) rec_last = rec;
@@ -801,7 +801,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
 
     const int tid = threadIdx.x;
     const int slot = tid / Z;
-    const int z = tid - slot * Z;   // MASKED: the padding lanes (slot 1) shadow lanes 0.. of the codeword
+    const int z = tid - slot * Z;
     const bool lane_ok = tid < a.cwpc * Z;
     const long long n_groups = (a.batch + a.cwpc - 1) / a.cwpc;
     const bool want_ok = a.ok != nullptr;
@@ -815,7 +815,6 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
     c.l.one = (uint32_t)a.one;
     c.my_rec = a.c2v + (size_t)(blockIdx.x / a.rec_group) * (kRecWords * kRecStride) + (blockIdx.x % a.rec_group) * blockDim.x + tid;
     c.pol = make_l2_policy(a.l2_pin);
-    c.live = tid < Z;
 
     while (true) {
         __syncthreads();  // previous group's outputs are out of smem
@@ -861,16 +860,20 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
                     const bool staged = a.n_rows >= a.staged_min_rows;
                     // bit r = hard decision of extension row r's parity variable (TRACK: kept up to date by the row updates)
                     const unsigned long long ext_bits = TRACK ? ((((unsigned long long)c.ext_hi << 32) | c.ext_lo) << 4) : 0ull;
+                    bool filtered = false;
                     if (TRACK) {
                         // per-slot last-layer filter: the decisions written by the last active row are final, so an unsatisfied
-                        // check there proves the codeword has not converged and the syndrome is skipped for this slot
+                        // check there proves the codeword has not converged and the syndrome is skipped for this slot.  The
+                        // verdict goes to the SECOND flag (a failure like any other) and is read back before anybody writes
+                        // that flag again (behind the next barrier): no thread reads a flag that a neighbour may be writing.
                         if (!c.done) {
                             const uint32_t pbit = (uint32_t)((ext_bits >> (a.n_rows - 1)) & 1ull) << 31;
-                            if (last_row_parity(a, c.l, make_uint4(0u, 0u, 0u, 0u), ExtFromBit{pbit}) >> 31) s_flag[slot] = 1;
+                            if (last_row_parity(a, c.l, make_uint4(0u, 0u, 0u, 0u), ExtFromBit{pbit}) >> 31) s_flag2[slot] = 1;
                         }
                         __syncthreads();
+                        filtered = s_flag2[slot] != 0;
                     }
-                    if (!c.done && !(TRACK && s_flag[slot])) {
+                    if (!c.done && !filtered) {
                         uint32_t f = BG == 0 ? syndrome_fail(a, c, 0, 4) : syndrome_unrolled_core<B, FULL>(a, c.l);
                         if (!staged) f |= BG == 0 ? syndrome_fail(a, c, 4, a.n_rows)
                                         : TRACK ? syndrome_unrolled_ext_bits<B, FULL>(a, c.l, ext_bits) : syndrome_unrolled_ext<B, FULL>(a, c.l, c.my_rec, c.pol);
@@ -879,7 +882,7 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
                     if (staged) {
                         // extension rows only for codewords whose core checks all hold
                         __syncthreads();
-                        if (!c.done && !s_flag[slot]) {
+                        if (!c.done && !filtered && !s_flag[slot]) {
                             const uint32_t f = BG == 0 ? syndrome_fail(a, c, 4, a.n_rows)
                                              : TRACK ? syndrome_unrolled_ext_bits<B, FULL>(a, c.l, ext_bits) : syndrome_unrolled_ext<B, FULL>(a, c.l, c.my_rec, c.pol);
                             if (f >> 31) s_flag2[slot] = 1;
@@ -963,7 +966,6 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_refill_
     c.l.one = (uint32_t)a.one;
     c.my_rec = a.c2v + (size_t)(blockIdx.x / a.rec_group) * (kRecWords * kRecStride) + (blockIdx.x % a.rec_group) * blockDim.x + tid;
     c.pol = make_l2_policy(a.l2_pin);
-    c.live = true;
     c.last_fail = 0;
     const uint32_t my_app_s = a.smem_base + c.l.slot_off + c.l.zoff;   // element z of block column 0 of this slot's APP array
     const uint32_t col_bytes = (uint32_t)Z * 4u;
@@ -1004,19 +1006,20 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_refill_
 
         const bool was_run = st == ST_RUN, was_load = st == ST_LOAD;
         const unsigned long long ext_bits = (((unsigned long long)c.ext_hi << 32) | c.ext_lo) << 4;   // see decode_nms_kernel (TRACK)
-        if (was_run) {
+        if (was_run) {   // last-layer filter: verdict in the second flag, read back before that flag is written again (see decode_nms_kernel)
             const uint32_t pbit = (uint32_t)((ext_bits >> (a.n_rows - 1)) & 1ull) << 31;
-            if (last_row_parity(a, c.l, make_uint4(0u, 0u, 0u, 0u), ExtFromBit{pbit}) >> 31) s_flag[slot] = 1;
+            if (last_row_parity(a, c.l, make_uint4(0u, 0u, 0u, 0u), ExtFromBit{pbit}) >> 31) s_flag2[slot] = 1;
         }
         __syncthreads();
-        if (was_run && !s_flag[slot]) {
+        const bool filtered = lane_ok && s_flag2[slot] != 0;
+        if (was_run && !filtered) {
             uint32_t f = syndrome_unrolled_core<BG, false>(a, c.l);
             if (!staged) f |= syndrome_unrolled_ext_bits<BG, false>(a, c.l, ext_bits);
             if (f >> 31) s_flag[slot] = 1;
         }
         if (staged) {
             __syncthreads();
-            if (was_run && !s_flag[slot]) {
+            if (was_run && !filtered && !s_flag[slot]) {
                 const uint32_t f = syndrome_unrolled_ext_bits<BG, false>(a, c.l, ext_bits);
                 if (f >> 31) s_flag2[slot] = 1;
             }

@@ -309,7 +309,6 @@ struct DecCtxH2 {
     uint64_t pol;
     uint4 cur, cur2;   // prefetched records of the next layer (and of its partner when the next layer is a row pair)
     bool done;   // this thread does no row work (inactive lane, or both codewords of its pair are finished)
-    bool live;   // MASKED kernels: this lane owns a check (tid < Z), see decode_kernel.cuh
     uint32_t last_fail;   // FULL, every base row active: bit 15 / 31 = codeword A / B has an unsatisfied check in the last layer
 };
 
@@ -409,9 +408,9 @@ struct UnrolledRowsH2 {
                 RowStateH2<DEG2> s1;
                 row_gather_h2<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur, s0);
                 row_gather_h2<DEG2, (R >= 4), FULL>(c.l, a.ed + E1, c.cur2, s1);
-                const uint4 rec0 = row_scatter_h2_par<DEG, (R >= 4), kLastPair>(s0, a.alpha_h2, par, !MASKED || c.live);
-                const uint4 rec1 = row_scatter_h2_par<DEG2, (R >= 4), kLastPair>(s1, a.alpha_h2, par, !MASKED || c.live);
-                if (store_rec && (!MASKED || c.live)) {
+                const uint4 rec0 = row_scatter_h2_par<DEG, (R >= 4), kLastPair>(s0, a.alpha_h2, par);
+                const uint4 rec1 = row_scatter_h2_par<DEG2, (R >= 4), kLastPair>(s1, a.alpha_h2, par);
+                if (store_rec) {
                     st_rec(c.my_rec, R, rec0, c.pol);
                     st_rec(c.my_rec, R + 1, rec1, c.pol);
                 }
@@ -421,7 +420,6 @@ struct UnrolledRowsH2 {
             // last layer of an iteration with every base row active: its hard decisions are final, the barrier doubles as
             // the CTA-wide OR of its parities (see decode_kernel.cuh); one reduction per codeword of the pair
             if (kLastPair) {
-                if (MASKED && !c.live) par = 0u;
                 const int fa = __syncthreads_or((int)((par >> 15) & 1u));
                 const int fb = __syncthreads_or((int)(par >> 31));
                 c.last_fail = (fa ? 0x00008000u : 0u) | (fb ? 0x80000000u : 0u);
@@ -440,8 +438,8 @@ struct UnrolledRowsH2 {
                 }
                 // layer 0's 4th word is not prefetched across the iteration boundary: fetch it on entry
                 if (R == 0 && kW4 && (ld_from == 0)) c.cur.w = ld_word(w4, c.pol);
-                const uint4 rec = process_row_h2<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur, a.alpha_h2, !MASKED || c.live);
-                if (store_rec && (!MASKED || c.live)) {
+                const uint4 rec = process_row_h2<DEG, (R >= 4), FULL>(c.l, a.ed + E0, c.cur, a.alpha_h2);
+                if (store_rec) {
                     st_rec(c.my_rec, R == 0 ? a.n_rows : R, rec, c.pol);
                     if (kW4) st_word(w4 + R * kRecStride, rec.w, c.pol);
                 }
@@ -498,7 +496,6 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
     c.l.one = (uint32_t)a.one;
     c.my_rec = a.c2v + (size_t)(blockIdx.x / a.rec_group) * (kRecWords * kRecStride) + (blockIdx.x % a.rec_group) * blockDim.x + tid;
     c.pol = make_l2_policy(a.l2_pin);
-    c.live = tid < Z;
     uint32_t *my_app = app + (size_t)(lane_ok ? slot : 0) * a.slot_stride;
 
     while (true) {

@@ -299,16 +299,17 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
     const int Z = h->d.Z;
     const bool h2 = h->cfg.llr_dtype == NRLDPC_F16X2;
     // cwpc: codewords (float32) or codeword pairs (packed half) resident per CTA
-    const int cwpc = h->cwpc, threads = decode_threads_for(cwpc, Z);
+    // one codeword (pair) per CTA: exactly Z threads, also when that leaves the last warp partly filled
+    const int cwpc = h->cwpc, threads = cwpc == 1 ? Z : decode_threads_for(cwpc, Z);
     const int per_group = h2 ? 2 * cwpc : cwpc;
     const int64_t n_groups = (batch + per_group - 1) / per_group;
     const size_t smem = decode_smem_for(h->d, cwpc);
     (void)n_rows;
     // variant 0: generic looped layers (float32 only); otherwise the layer loop is unrolled for the base graph.
     // FULL: one codeword (pair) per CTA, CTA-uniform code; MASKED: the same with a partially filled last warp (Z not a
-    // multiple of 32), stores predicated on the lane
+    // multiple of 32: no warp-ballot syndrome)
     using Kern = void (*)(const nrldpc::DecArgs);
-    const bool full = cwpc == 1, masked = full && threads != Z;
+    const bool full = cwpc == 1, masked = full && (Z % 32) != 0;
     const bool bg1 = h->d.bg == 1;
     Kern kern;
     if (h2)
@@ -921,9 +922,16 @@ int decode_impl(nrldpc_t *h, const void *llr, int in_kind, int64_t batch, int32_
         }
         // device-mode launches share one scratch (c2v records, work counter, conversion buffer): a launch on another
         // stream than the previous one is ordered behind it
-        if (h->dev_used && st != h->last_dev_stream) CUDA_TRY(h, cudaStreamWaitEvent(st, h->dev_done, 0));
+        // (a launch being captured into a CUDA graph takes no part in this: an event recorded during capture belongs to
+        // the graph and cannot be waited on by ordinary work afterwards; whoever replays the graph orders the replays
+        // against other use of the handle, nrldpc_b200.h)
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) { cudaGetLastError(); cap = cudaStreamCaptureStatusNone; }
+        const bool capturing = cap != cudaStreamCaptureStatusNone;
+        if (!capturing && h->dev_used && st != h->last_dev_stream) CUDA_TRY(h, cudaStreamWaitEvent(st, h->dev_done, 0));
         if (int rc = launch_any(h, h->pipe[0], st, llr, in_kind, h->dev_widen, batch, n_rows, info_hard, app_soft, iters, parity_ok))
             return rc;
+        if (capturing) return 0;
         CUDA_TRY(h, cudaEventRecord(h->dev_done, st));
         h->last_dev_stream = st;
         h->dev_used = true;
