@@ -78,6 +78,7 @@ struct DecArgs {
     int one;                 // = 1 (see mad_u32)
     uint32_t smem_base;      // shared-window address of the kernel's dynamic shared memory
     uint32_t alpha_h2;       // {fp16(alpha), fp16(alpha)} for the packed-half kernel
+    int spares;              // decode_nms_refill2_kernel: surplus codeword buffers (mailboxes) per CTA
     int rec_group;           // CTAs that share one [kRecWords][kRecStride] scratch block (CTA b uses thread columns (b % rec_group) * blockDim.x ...)
     uint32_t *c2v;           // [ceil(grid / rec_group)][kRecWords][kRecStride]; float32 record = {alpha*min1|sgn, alpha*min2|sgn, argmin | signbits << 5}
     int *work_counter;       // device ticket counter: never reset between launches, the host passes the value it has reached ...

@@ -19,6 +19,7 @@
 #include "chain_kernels.cuh"
 #include "decode_kernel.cuh"
 #include "decode_kernel_h2.cuh"
+#include "decode_kernel_refill.cuh"
 #include "decode_kernel_bp.cuh"
 #include "host_staging.h"
 
@@ -125,7 +126,9 @@ struct nrldpc_handle {
     int host_threads = 0;
     long long l2_window = 0;                 // bytes of the persisting access-policy window over the c2v scratch (0: none; NRLDPC_L2_WINDOW=0/1)
     int zero_copy_max = 2;                   // host-memory decodes of up to this many codewords read / write pinned host memory directly (NRLDPC_ZERO_COPY_MAX, 0 = off)
-    int refill = 1;                          // NRLDPC_REFILL: 0 = never refill slots, 1 = where measured to pay (default), 2 = whenever possible
+    int refill = 1;                          // NRLDPC_REFILL: 0 = never refill slots, 1 = where measured to pay (default), 2 = refill kernel whenever possible,
+                                             // 3 = prefetched refill (decode_kernel_refill.cuh) whenever possible
+    int refill_spares = 2;                   // NRLDPC_REFILL_SPARES: mailboxes per CTA of the prefetched-refill kernel
     int no_staging = 0;                      // NRLDPC_NO_STAGING=1: hand pageable buffers to cudaMemcpyAsync as they are (A/B)
     int bp_threads = 1024;           // CTA width of the sum-product kernel (NRLDPC_BP_THREADS=512 selects the 128-register build)
 };
@@ -303,7 +306,7 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
     const int cwpc = h->cwpc, threads = cwpc == 1 ? Z : decode_threads_for(cwpc, Z);
     const int per_group = h2 ? 2 * cwpc : cwpc;
     const int64_t n_groups = (batch + per_group - 1) / per_group;
-    const size_t smem = decode_smem_for(h->d, cwpc);
+    size_t smem = decode_smem_for(h->d, cwpc);
     (void)n_rows;
     // variant 0: generic looped layers (float32 only); otherwise the layer loop is unrolled for the base graph.
     // FULL: one codeword (pair) per CTA, CTA-uniform code; MASKED: the same with a partially filled last warp (Z not a
@@ -331,6 +334,17 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
     const bool refill = !h2 && h->dec_variant != 0 && h->cfg.early_term && cwpc > 1 && batch < ((int64_t)1 << 31) - 65536 &&
                         (h->refill == 1 ? cwpc >= 24 : h->refill == 2);
     if (refill) kern = bg1 ? (Kern)nrldpc::decode_nms_refill_kernel<1> : (Kern)nrldpc::decode_nms_refill_kernel<2>;
+    // prefetched refill: S slots + P mailboxes per CTA (bulk copies need 16-byte aligned buffers: Z a multiple of 4)
+    const int stride_w = decode_slot_stride(h->d.cols, Z, cwpc);
+    const int spares = h->refill_spares;
+    const size_t smem2 = (size_t)(cwpc + spares) * stride_w * 4 + (size_t)(4 * cwpc + 3 * spares + 4) * 4 + 8 + (size_t)(1 + spares) * 8;
+    const bool refill2 = !h2 && h->dec_variant != 0 && h->cfg.early_term && cwpc > 1 && batch < ((int64_t)1 << 31) - 65536 &&
+                         (stride_w & 3) == 0 && smem2 <= 227 * 1024 && h->refill == 3;
+    if (refill2) {
+        kern = bg1 ? (Kern)nrldpc::decode_nms_refill2_kernel<1> : (Kern)nrldpc::decode_nms_refill2_kernel<2>;
+        smem = smem2;
+        s.counter_dirty = true;   // this kernel counts from zero (it draws an unpredictable number of tickets)
+    }
     // persistent grid: every SM filled to its occupancy (2 CTAs of 384 threads at Z = 384, more for narrower CTAs);
     // attribute and occupancy are looked up once per (kernel, CTA width, shared-memory size)
     int occ = 1;
@@ -351,12 +365,13 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
         CUDA_TRY(h, cudaMemsetAsync(s.counter, 0, sizeof(int), stream));
         s.tickets = 0; s.counter_dirty = capturing;
     }
+    if (refill2) s.counter_dirty = true;   // the next launch zeroes the counter again
     nrldpc::DecArgs &a = h->dec_args;  // tables were filled at create()
     a.llr = llr; a.hard = hard; a.soft = soft; a.iters = iters; a.ok = ok;
     a.batch = batch; a.Z = Z; a.ncols = h->d.cols; a.kcols = h->d.kcols; a.n_rows = n_rows;
     a.n_edges = h->h_row_start[n_rows]; a.max_iters = h->cfg.max_iters; a.early_term = h->cfg.early_term;
     a.slot_stride = decode_slot_stride(h->d.cols, Z, cwpc);
-    a.cwpc = cwpc; a.rec_group = rec_group; a.alpha = h->cfg.alpha; a.l2_pin = h->l2_pin; a.one = 1;
+    a.cwpc = cwpc; a.spares = spares; a.rec_group = rec_group; a.alpha = h->cfg.alpha; a.l2_pin = h->l2_pin; a.one = 1;
     a.bitsliced_min_rows = h->bitsliced_min_rows; a.staged_min_rows = h->staged_min_rows;
     a.c2v = s.c2v; a.work_counter = s.counter; a.work_base = s.tickets;
     // tickets this launch draws: one per group (refill kernel: per codeword) plus the failing fetch that ends every CTA (slot)
@@ -716,7 +731,8 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
     if (getenv("NRLDPC_NO_TMA")) h->no_tma = 1;
     if (getenv("NRLDPC_NO_STAGING")) h->no_staging = 1;
     if (const char *v = getenv("NRLDPC_ZERO_COPY_MAX")) h->zero_copy_max = std::max(0, std::min(64, atoi(v)));
-    if (const char *v = getenv("NRLDPC_REFILL")) h->refill = std::max(0, std::min(2, atoi(v)));
+    if (const char *v = getenv("NRLDPC_REFILL")) h->refill = std::max(0, std::min(3, atoi(v)));
+    if (const char *v = getenv("NRLDPC_REFILL_SPARES")) h->refill_spares = std::max(1, std::min(8, atoi(v)));
     if (const char *v = getenv("NRLDPC_CWPC")) h->cwpc_override = std::max(0, atoi(v));
     if (const char *v = getenv("NRLDPC_OCC_CAP")) { h->occ_cap = std::max(1, std::min(16, atoi(v))); h->occ_cap_forced = 1; }
     if (const char *v = getenv("NRLDPC_SHAPE_MODEL")) h->shape_model = atoi(v) ? 1 : 0;
