@@ -734,7 +734,7 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
     if (const char *v = getenv("NRLDPC_REFILL")) h->refill = std::max(0, std::min(3, atoi(v)));
     if (const char *v = getenv("NRLDPC_REFILL_SPARES")) h->refill_spares = std::max(1, std::min(8, atoi(v)));
     if (const char *v = getenv("NRLDPC_CWPC")) h->cwpc_override = std::max(0, atoi(v));
-    if (const char *v = getenv("NRLDPC_OCC_CAP")) { h->occ_cap = std::max(1, std::min(16, atoi(v))); h->occ_cap_forced = 1; }
+    if (const char *v = getenv("NRLDPC_OCC_CAP")) { h->occ_cap = std::max(1, std::min(32, atoi(v))); h->occ_cap_forced = 1; }
     if (const char *v = getenv("NRLDPC_SHAPE_MODEL")) h->shape_model = atoi(v) ? 1 : 0;
     h->host_threads = nrldpc::default_host_threads();
 

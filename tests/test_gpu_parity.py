@@ -743,7 +743,7 @@ def test_forced_cta_shapes_are_bit_identical(capi, O, f16, monkeypatch):
                 assert (out["iters"] == ref["iters"]).all() and (out["parity_ok"] == ref["parity_ok"]).all(), (bg, Z, et, cw, cap)
 
 
-@pytest.mark.parametrize("bg,Z,rows,B", [(2, 52, 33, 3001), (1, 8, 46, 4000), (2, 6, 13, 5000), (1, 96, 20, 700), (2, 176, 42, 500), (1, 30, 46, 1500)])
+@pytest.mark.parametrize("bg,Z,rows,B", [(2, 52, 33, 3001), (1, 8, 46, 4000), (2, 6, 13, 5000), (1, 96, 20, 700), (2, 176, 42, 500), (1, 30, 46, 1500), (2, 4, 42, 6000)])
 def test_slot_refill_under_the_stop(capi, O, bg, Z, rows, B, monkeypatch):
     """Multi-codeword CTAs with 'Parity check satisfied' (NRLDPCDecoder.m:120): slots are refilled one by one as their
     codewords converge (decode_nms_refill_kernel).  Batches of many CTA loads with a mix of operating points (codewords
@@ -763,6 +763,20 @@ def test_slot_refill_under_the_stop(capi, O, bg, Z, rows, B, monkeypatch):
     out = h.decode(llr, n_rows=rows, want_soft=True)
     out2 = h.decode(llr, n_rows=rows)                     # no soft output: other code path for the final records
     h.close()
+    # prefetched refill (decode_kernel_refill.cuh; Z a multiple of 4, other sizes fall back) with 1, 2 and 5 mailboxes per CTA
+    monkeypatch.setenv("NRLDPC_REFILL", "3")
+    pre = []
+    for spares in ("1", "2", "5"):
+        monkeypatch.setenv("NRLDPC_REFILL_SPARES", spares)
+        h = capi.Handle(bg, Z, 7, True)
+        pre.append(h.decode(llr, n_rows=rows, want_soft=True))
+        pre.append(h.decode(llr[:B // 7], n_rows=rows, want_soft=True))   # the same handle again, a batch that ends inside a CTA load
+        h.close()
+    monkeypatch.delenv("NRLDPC_REFILL_SPARES")
+    for i, r in enumerate(pre):
+        n = B if i % 2 == 0 else B // 7
+        assert (r["hard"] == ref["hard"][:n]).all() and _same_bits(r["app"], ref["app"][:n]), (i, "prefetched refill")
+        assert (r["iters"] == ref["iters"][:n]).all() and (r["parity_ok"] == ref["parity_ok"][:n]).all(), (i, "prefetched refill")
     monkeypatch.setenv("NRLDPC_REFILL", "0")              # whole groups, parity bits tracked in registers
     h = capi.Handle(bg, Z, 7, True)
     grp = h.decode(llr, n_rows=rows, want_soft=True)

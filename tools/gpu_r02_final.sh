@@ -36,12 +36,12 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 python tools/gpu_latency.py > $O/latency.log 2>&1; cp gpurun_out/latency.json $O/latency.json
 python tools/gpu_bler_rate.py > $O/bler_rate.log 2>&1; cp gpurun_out/bler_rate.json $O/bler_rate.json
 : > $O/sanitizer.txt
-for tool in memcheck racecheck; do
-  for args in "0 1 384 3 1" "1 1 384 3 1" "0 2 52 15 1" "0 1 208 3 1" "0 1 8 200 1"; do
+for tool in memcheck racecheck synccheck; do
+  for args in "0 1 384 3 1" "1 1 384 3 1" "0 2 52 15 1" "0 1 208 3 1" "1 1 208 3 1" "0 1 8 200 1" "0 2 8 300 1"; do
     echo "== compute-sanitizer --tool $tool tools/gpu_repro.py $args" >> $O/sanitizer.txt
     timeout 400 compute-sanitizer --tool $tool python tools/gpu_repro.py $args 2>&1 | grep -E "hard equal|ERROR SUMMARY|RACECHECK SUMMARY|Error|error" | head -6 >> $O/sanitizer.txt
   done
 done
 tail -30 $O/sanitizer.txt
-python tools/sweep.py --out $O/sweep_1gpu > $O/sweep.log 2>&1; tail -3 $O/sweep.log
+python tools/sweep.py --mb 400 --out $O/sweep_1gpu > $O/sweep.log 2>&1; tail -3 $O/sweep.log
 du -sh $O

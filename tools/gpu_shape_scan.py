@@ -19,6 +19,8 @@ def main():
     ap.add_argument("--early-term", action="store_true")
     ap.add_argument("--caps", default="4,8")
     ap.add_argument("--esn0", type=float, default=None)
+    ap.add_argument("--extra-caps", default="", help="occupancy caps above 8, tried for CTAs of at most 96 threads (plus CTA widths 32 / 64 / 96)")
+    ap.add_argument("--only-extra", action="store_true", help="time only the default shape and the --extra-caps candidates")
     args = ap.parse_args()
     import torch
     from ldpc_3gpp_matlab_b200 import capi
@@ -61,6 +63,15 @@ def main():
                 if cap > 4 and T > 192:      # a cap above 4 only matters for narrow CTAs
                     continue
                 cands.append((f"cw{c}_cap{cap}", c, cap))
+        if args.only_extra:
+            cands = cands[:1]
+        if args.extra_caps:
+            for c in sorted({T // Z for T in (32, 64, 96) if 1 <= T // Z <= cmax} | {1}):
+                T = max(32, (c * Z + 31) // 32 * 32) if c > 1 else Z
+                if T > 96:
+                    continue
+                for cap in (int(x) for x in args.extra_caps.split(",")):
+                    cands.append((f"cw{c}_cap{cap}", c, cap))
         for name, c, cap in cands:
             for k in ("NRLDPC_CWPC", "NRLDPC_OCC_CAP"):
                 os.environ.pop(k, None)
