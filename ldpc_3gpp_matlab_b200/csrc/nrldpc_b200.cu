@@ -20,6 +20,7 @@
 #include "decode_kernel.cuh"
 #include "decode_kernel_h2.cuh"
 #include "decode_kernel_refill.cuh"
+#include "decode_kernel_shfl.cuh"
 #include "decode_kernel_bp.cuh"
 #include "host_staging.h"
 
@@ -98,7 +99,8 @@ struct nrldpc_handle {
     int enc_s0[4];
     int enc_delta = 0;
     PipeSlot pipe[kNumPipe];
-    int dec_variant = 1;             // NRLDPC_DECODE_VARIANT=loop selects the generic looped kernel
+    int dec_variant = 1;             // NRLDPC_DECODE_VARIANT=loop selects the generic looped kernel, =shfl the lane-per-edge warp-shuffle kernel (Z <= 32)
+    int shfl_cwpc = 0, shfl_threads = 256;   // NRLDPC_SHFL_CWPC / NRLDPC_SHFL_THREADS (0: 32 / Z codewords per CTA)
     int bitsliced_min_rows = 4;      // syndrome variants, see DecArgs (NRLDPC_BITSLICED_MIN_ROWS / NRLDPC_STAGED_MIN_ROWS: experiments)
     int staged_min_rows = 8;
     int l2_pin = 1;                  // NRLDPC_L2_PIN=0 drops the evict_last policy on the c2v scratch
@@ -296,11 +298,15 @@ int ensure_scratch(nrldpc_handle *h, PipeSlot &s, size_t recs) {
     return 0;
 }
 
+int launch_decode_shfl(nrldpc_handle *h, cudaStream_t stream, const float *llr, int64_t batch, int n_rows, uint8_t *hard, float *soft,
+                       int32_t *iters, uint8_t *ok);
+
 // Enqueue one decode launch on `stream` using slot `s`'s scratch.
 int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const float *llr, int64_t batch,
                   int n_rows, uint8_t *hard, float *soft, int32_t *iters, uint8_t *ok) {
     const int Z = h->d.Z;
     const bool h2 = h->cfg.llr_dtype == NRLDPC_F16X2;
+    if (h->dec_variant == 2 && Z <= 32 && !h2) return launch_decode_shfl(h, stream, llr, batch, n_rows, hard, soft, iters, ok);
     // cwpc: codewords (float32) or codeword pairs (packed half) resident per CTA
     // one codeword (pair) per CTA: exactly Z threads, also when that leaves the last warp partly filled
     const int cwpc = h->cwpc, threads = cwpc == 1 ? Z : decode_threads_for(cwpc, Z);
@@ -402,6 +408,37 @@ int launch_decode(nrldpc_handle *h, PipeSlot &s, cudaStream_t stream, const floa
         kern<<<grid, threads, smem, stream>>>(a);
     }
     if (cudaError_t e_ = cudaGetLastError()) { s.counter_dirty = true; return fail(h, NRLDPC_ECUDA, "decode launch: %s", cudaGetErrorString(e_)); }
+    h->launches += 1;
+    return 0;
+}
+
+// Lane-per-edge warp-shuffle kernel (decode_kernel_shfl.cuh): experiment / small-Z latency path, float32, Z <= 32.
+int launch_decode_shfl(nrldpc_handle *h, cudaStream_t stream, const float *llr, int64_t batch, int n_rows, uint8_t *hard, float *soft,
+                       int32_t *iters, uint8_t *ok) {
+    const int Z = h->d.Z, rows_all = h->d.cols - h->d.kcols;
+    auto smem_for = [&](int c) {
+        return (size_t)c * h->d.n_cw * 4 + (size_t)rows_all * c * Z * 12 + (size_t)(rows_all - 4) * c * Z * 4 + (size_t)h->d.edges * 4 + (size_t)c * 8 + 16;
+    };
+    int cwpc = h->shfl_cwpc > 0 ? h->shfl_cwpc : std::max(1, 32 / Z);
+    cwpc = (int)std::max<int64_t>(1, std::min<int64_t>(cwpc, batch));
+    while (cwpc > 1 && smem_for(cwpc) > 200 * 1024) --cwpc;
+    const size_t smem = smem_for(cwpc);
+    const int threads = h->shfl_threads;
+    int occ = 1;
+    if (int rc = cached_occupancy(h, reinterpret_cast<const void *>(nrldpc::decode_nms_shfl_kernel), threads, smem, &occ)) return rc;
+    const int64_t n_groups = (batch + cwpc - 1) / cwpc;
+    const int grid = (int)std::min<int64_t>(n_groups, (int64_t)h->num_sms * occ);
+    nrldpc::DecArgs &a = h->dec_args;
+    a.llr = llr; a.hard = hard; a.soft = soft; a.iters = iters; a.ok = ok;
+    a.batch = batch; a.Z = Z; a.ncols = h->d.cols; a.kcols = h->d.kcols; a.n_rows = n_rows;
+    a.n_edges = h->h_row_start[n_rows]; a.max_iters = h->cfg.max_iters; a.early_term = h->cfg.early_term;
+    a.slot_stride = h->d.n_cw; a.cwpc = cwpc; a.alpha = h->cfg.alpha; a.one = 1;
+    if (a.smem_base != h->smem_base) {
+        for (int e = 0; e < h->d.edges; ++e) a.ed[e].y += h->smem_base - a.smem_base;
+        a.smem_base = h->smem_base;
+    }
+    nrldpc::decode_nms_shfl_kernel<<<grid, threads, smem, stream>>>(a);
+    CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
     return 0;
 }
@@ -722,7 +759,9 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
             h->l2_window = std::min<long long>(prop.persistingL2CacheMaxSize, prop.accessPolicyMaxWindowSize);
         }
     }
-    if (const char *v = getenv("NRLDPC_DECODE_VARIANT")) h->dec_variant = strcmp(v, "loop") == 0 ? 0 : 1;
+    if (const char *v = getenv("NRLDPC_DECODE_VARIANT")) h->dec_variant = strcmp(v, "loop") == 0 ? 0 : strcmp(v, "shfl") == 0 ? 2 : 1;
+    if (const char *v = getenv("NRLDPC_SHFL_CWPC")) h->shfl_cwpc = std::max(0, atoi(v));
+    if (const char *v = getenv("NRLDPC_SHFL_THREADS")) h->shfl_threads = std::max(32, std::min(256, atoi(v) / 32 * 32));
     if (const char *v = getenv("NRLDPC_L2_PIN")) h->l2_pin = atoi(v) ? 1 : 0;
     if (const char *v = getenv("NRLDPC_BITSLICED_MIN_ROWS")) h->bitsliced_min_rows = std::max(4, atoi(v));
     if (const char *v = getenv("NRLDPC_STAGED_MIN_ROWS")) h->staged_min_rows = std::max(5, atoi(v));

@@ -834,3 +834,44 @@ def test_device_mode_streams_and_graph_capture(capi, O):
     out = h.decode(llr_np)
     assert (out["hard"] == ref["hard"]).all() and (out["iters"] == ref["iters"]).all()
     h.close()
+
+
+@pytest.mark.parametrize("bg", [1, 2])
+def test_warp_shuffle_mapping_bit_exact_small_Z(capi, O, bg, monkeypatch):
+    """The lane-per-edge kernel with the check-node reduction done by warp shuffles (decode_kernel_shfl.cuh,
+    NRLDPC_DECODE_VARIANT=shfl, every Z <= 32): butterfly minima / ballot signs give the same bits as the register scan of
+    the default kernel and as the oracle -- fixed iterations and the stop, trimmed rows, filler, soft output, ragged batches,
+    one and several codewords per CTA, CTAs of 64 and 256 threads, a core-pass / extension-fail mix."""
+    monkeypatch.setenv("NRLDPC_DECODE_VARIANT", "shfl")
+    rng = np.random.default_rng(700 + bg)
+    rows_all = 46 if bg == 1 else 42
+    for Z in [z for z in ALL_Z if z <= 32]:
+        d = O.dims(bg, Z)
+        B = 37 if Z > 8 else 75
+        rows = int(rng.integers(4, rows_all + 1)) if Z % 3 else rows_all
+        E = (d["K"] // Z - 2 + rows) * Z
+        info, llr = make_llr(O, bg, Z, B, E, rng.uniform(-1.0, 3.0), rng, filler=(Z if Z % 2 == 0 and Z > 4 else 0))
+        for et in (False, True):
+            ref = O.decode_nms(bg, Z, llr, 6, early_term=et, n_rows=rows)
+            for cwpc, threads in (("0", "256"), ("1", "64"), ("5", "128")):
+                monkeypatch.setenv("NRLDPC_SHFL_CWPC", cwpc)
+                monkeypatch.setenv("NRLDPC_SHFL_THREADS", threads)
+                h = capi.Handle(bg, Z, 6, et)
+                out = h.decode(llr, n_rows=rows, want_soft=True)
+                one = h.decode(llr[:1], n_rows=rows)
+                h.close()
+                assert (out["hard"] == ref["hard"]).all(), (bg, Z, et, cwpc)
+                assert _same_bits(out["app"], ref["app"]), (bg, Z, et, cwpc)
+                assert (out["iters"] == ref["iters"]).all() and (out["parity_ok"] == ref["parity_ok"]).all(), (bg, Z, et, cwpc)
+                assert (one["hard"] == ref["hard"][:1]).all() and (one["iters"] == ref["iters"][:1]).all(), (bg, Z, et, cwpc)
+    # codewords whose core checks hold while an extension check fails for ever
+    Z, rows = 16, rows_all
+    info, llr, kind = make_core_pass_llr(O, bg, Z, 48, rows, rng)
+    ref = O.decode_nms(bg, Z, llr, 5, early_term=True, n_rows=rows)
+    monkeypatch.setenv("NRLDPC_SHFL_CWPC", "0")
+    monkeypatch.setenv("NRLDPC_SHFL_THREADS", "256")
+    h = capi.Handle(bg, Z, 5, True)
+    out = h.decode(llr, n_rows=rows, want_soft=True)
+    h.close()
+    assert (out["hard"] == ref["hard"]).all() and _same_bits(out["app"], ref["app"])
+    assert (out["iters"] == ref["iters"]).all() and (out["parity_ok"] == ref["parity_ok"]).all()
