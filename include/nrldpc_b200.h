@@ -210,6 +210,13 @@ int nrldpc_mod_awgn_llr(nrldpc_t *h, const uint8_t *bits, int64_t n_bits, int32_
 int nrldpc_crc(nrldpc_t *h, const uint8_t *bits, int64_t batch, int32_t n_bits, int64_t stride, int32_t kind,
                uint8_t *parity, int64_t parity_stride, uint8_t *ok, void *stream);
 
+/* ---- random information blocks of the Monte-Carlo loop on device: a = round(rand(A,1)) (plot_BLER_vs_SNR.m:112).
+ * bits[r*stride + k] for r < rows, k < n_bits (one bit per byte, device memory; nothing beyond n_bits of a row is written)
+ * from the counter-based generator keyed (seed, stream_id, index of the row's 128-bit group): the same bits whatever the launch
+ * geometry, independent streams per (seed, stream_id) as the script asks of parallel runs (:23-27). */
+int nrldpc_random_bits(nrldpc_t *h, uint8_t *bits, int64_t rows, int32_t n_bits, int64_t stride, uint64_t seed, uint64_t stream_id,
+                       void *stream);
+
 /* ---- block-error bookkeeping of the Monte-Carlo loop on device (plot_BLER_vs_SNR.m:139-155; a_hat = [] unless the CRCs
  * pass, NRLDPCDecoder.m:296-309,336-339; a block error is ~isequal(a, a_hat)), one decoding attempt of n_tb transport
  * blocks of C code blocks each.  All buffers are device memory.

@@ -68,8 +68,8 @@ class BlerSimulator:
                              algorithm=algorithm)
         self.B = int(batch)
         self.rank, self.world, self.seed = rank, world, seed
-        self.gen = torch.Generator(device="cuda").manual_seed(D.rank_seed(seed, rank) & 0x7FFFFFFFFFFF)
-        self.stream_id = 0
+        self.stream_id = 0       # channel uses of this simulator: key of the AWGN generator
+        self.n_batches = 0       # batches drawn: key of the information-bit generator (its own key space, bit 62 set)
         dev = "cuda"
         n = self.B * self.C
         self.info = torch.zeros((n, self.K), dtype=torch.uint8, device=dev)
@@ -122,19 +122,20 @@ class BlerSimulator:
         torch, h, B, C = self.torch, self.h, self.B, self.C
         st = torch.cuda.current_stream().cuda_stream
         var = 10 ** (-esn0_db / 10)                      # plot_BLER_vs_SNR.m:105-106
+        self.n_batches += 1
         A, Kp, Lcb, K = self.A, self.Kp, self.L_cb, self.K
         if self.use_crc:
             # a -> b = [a ; TB CRC] (NRLDPCEncoder.m:70-89) -> C blocks of K'-L_cb bits + CB CRC24B (:92-124), on device.
             # One code block: the transport block IS the head of the code block row, so it is drawn and CRC'd in place.
             tb, tb_stride = (self.info, K) if C == 1 else (self.tb, self.Bsz)
-            tb[:, :A] = torch.randint(0, 2, (B, A), dtype=torch.uint8, device="cuda", generator=self.gen)
+            h.random_bits_raw(tb, B, A, tb_stride, D.rank_seed(self.seed, self.rank), (1 << 62) | self.n_batches, stream=st)   # a = round(rand(A,1)), :112
             h.crc_raw(tb, B, A, tb_stride, self.tb_kind, parity=tb.data_ptr() + A, parity_stride=tb_stride, stream=st)
             if C > 1:
                 self.info.view(B, C, -1)[:, :, :Kp - Lcb] = self.tb.view(B, C, Kp - Lcb)
                 h.crc_raw(self.info, B * C, Kp - Lcb, K, capi.CRC24B, parity=self.info.data_ptr() + Kp - Lcb,
                           parity_stride=K, stream=st)
         else:
-            self.info[:, :Kp] = torch.randint(0, 2, (B * C, Kp), dtype=torch.uint8, device="cuda", generator=self.gen)
+            h.random_bits_raw(self.info, B * C, Kp, K, D.rank_seed(self.seed, self.rank), (1 << 62) | self.n_batches, stream=st)
         h.encode_raw(self.info, B * C, self.cw, mem=capi.MEM_DEVICE, stream=st)
         if self.harq is not None:
             self.harq.zero_()                            # reset(hDec), plot_BLER_vs_SNR.m:122

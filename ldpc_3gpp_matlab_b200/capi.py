@@ -41,7 +41,7 @@ SYMBOLS = (
     "nrldpc_rate_match", "nrldpc_rate_recover", "nrldpc_qpsk_awgn_llr", "nrldpc_host_alloc",
     "nrldpc_host_free", "nrldpc_launch_count", "nrldpc_version",
     "nrldpc_modulate", "nrldpc_awgn", "nrldpc_demodulate", "nrldpc_mod_awgn_llr", "nrldpc_crc", "nrldpc_decode16", "nrldpc_decode64",
-    "nrldpc_qpsk_awgn_rate_recover", "nrldpc_bler_count",
+    "nrldpc_qpsk_awgn_rate_recover", "nrldpc_bler_count", "nrldpc_random_bits",
 )
 
 
@@ -104,6 +104,7 @@ def load():
     lib.nrldpc_rate_recover.argtypes = [vp, vp, i64, C.POINTER(Rm), vp, vp, i32, vp]
     lib.nrldpc_qpsk_awgn_llr.argtypes = [vp, vp, i64, i32, C.c_float, u64, u64, vp, vp]
     lib.nrldpc_qpsk_awgn_rate_recover.argtypes = [vp, vp, i64, C.POINTER(Rm), C.c_float, u64, u64, vp, vp, vp]
+    lib.nrldpc_random_bits.argtypes = [vp, vp, i64, i32, i64, u64, u64, vp]
     lib.nrldpc_bler_count.argtypes = [vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, i64, i32, i32, i32, vp, vp, i32, i32, vp]
     lib.nrldpc_modulate.argtypes = [vp, vp, i64, i32, vp, vp]
     lib.nrldpc_awgn.argtypes = [vp, vp, i64, C.c_float, u64, u64, vp]
@@ -259,6 +260,11 @@ class Handle:
     def mod_awgn_llr_raw(self, bits, n_bits, Q_m, variance, method, seed, stream_id, llr, stream=None):
         self._check(self._lib.nrldpc_mod_awgn_llr(self._h, _ptr(bits), int(n_bits), int(Q_m), float(variance), int(method),
                                                   int(seed), int(stream_id), _ptr(llr), stream))
+
+    def random_bits_raw(self, bits, rows, n_bits, stride, seed, stream_id, stream=None):
+        """Uniform random bits (device memory), rows of n_bits at `stride`: round(rand(A,1)) of plot_BLER_vs_SNR.m:112."""
+        self._check(self._lib.nrldpc_random_bits(self._h, _ptr(bits), int(rows), int(n_bits), int(stride), int(seed) & (2 ** 64 - 1),
+                                                 int(stream_id) & (2 ** 64 - 1), stream))
 
     def crc_raw(self, bits, batch, n_bits, stride, kind, parity=None, parity_stride=0, ok=None, stream=None):
         self._check(self._lib.nrldpc_crc(self._h, _ptr(bits), int(batch), int(n_bits), int(stride), int(kind), _ptr(parity),

@@ -1309,6 +1309,21 @@ NRLDPC_EXPORT int nrldpc_bler_count(nrldpc_t *h, const uint8_t *hard, const uint
     return 0;
 }
 
+NRLDPC_EXPORT int nrldpc_random_bits(nrldpc_t *h, uint8_t *bits, int64_t rows, int32_t n_bits, int64_t stride, uint64_t seed,
+                                     uint64_t stream_id, void *stream) {
+    if (!h) return NRLDPC_ESHAPE;
+    if (rows < 0 || n_bits < 0 || stride < n_bits) return fail(h, NRLDPC_ESHAPE, "rows, n_bits >= 0 and stride >= n_bits required");
+    if (n_bits >= (1 << 27) || rows >= ((int64_t)1 << 43)) return fail(h, NRLDPC_ESHAPE, "n_bits < 2^27 and rows < 2^43 required");
+    if (rows == 0 || n_bits == 0) return 0;
+    if (!bits) return fail(h, NRLDPC_ESHAPE, "bits must not be NULL");
+    ENTER_DEVICE(h);
+    const long long total = rows * (((long long)n_bits + 15) >> 4);
+    nrldpc::random_bits_kernel<<<grid_for(h, total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(bits, rows, n_bits, stride, seed, stream_id);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Modulation / channel / demodulation for every NRModulator / NRDemodulator setting (device memory only)
 namespace {

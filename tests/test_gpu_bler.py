@@ -87,8 +87,8 @@ def test_device_crc_matches_oracle_and_bler_criterion(O):
     h = capi.Handle(2, 2, 1)
     st = torch.cuda.current_stream().cuda_stream
     for name, kind, L in (("CRC16", capi.CRC16, 16), ("CRC24A", capi.CRC24A, 24), ("CRC24B", capi.CRC24B, 24)):
-        for n in (1, 7, 20, 333, 8424):
-            B, stride = 37, n + L + 5
+        for n, pad in ((1, 5), (7, 5), (20, 5), (333, 5), (8424, 5), (8424, 0), (4000, 8), (264, 16 - L % 16)):
+            B, stride = 37, n + L + pad          # odd strides: rows at every alignment; pad 0 / 8: word-aligned rows (table path)
             bits = rng.integers(0, 2, (B, stride), dtype=np.uint8)
             d = torch.from_numpy(bits).cuda()
             ok = torch.zeros(B, dtype=torch.uint8, device="cuda")
@@ -241,3 +241,43 @@ def test_bler_counters_fused_path_equals_stagewise_path(monkeypatch):
         assert res[0][0][0] == 2 * kw["batch"]
         if len(kw.get("rv_id_sequence", (0,))) == 1:
             assert 0 < res[0][0][1] < res[0][0][0]      # the point sits in the waterfall: both outcomes occur
+
+
+def test_random_bits_kernel():
+    """nrldpc_random_bits (the information blocks of the Monte-Carlo loop, plot_BLER_vs_SNR.m:112): only [0, n_bits) of each row
+    is written, the bits depend on (seed, stream id, row, position) and not on alignment or launch geometry, different keys give
+    different blocks, and the bits are uniform and independent enough for a Monte-Carlo source (mean, row/column balance,
+    lag correlations within a few standard deviations)."""
+    import torch
+    from ldpc_3gpp_matlab_b200 import capi
+    h = capi.Handle(2, 2, 1)
+    st = torch.cuda.current_stream().cuda_stream
+    ref = None
+    for off, stride in ((0, 8448), (3, 8453), (16, 8432)):
+        buf = torch.full((64 * stride + 64,), 7, dtype=torch.uint8, device="cuda")
+        view = buf[off:off + 64 * stride]
+        h.random_bits_raw(view, 64, 8424, stride, 1234, 5, stream=st)
+        got = view.cpu().numpy().reshape(64, stride)
+        assert set(np.unique(got[:, :8424])) == {0, 1}
+        assert (got[:, 8424:] == 7).all() and (buf[:off].cpu().numpy() == 7).all() and (buf[off + 64 * stride:].cpu().numpy() == 7).all()
+        if ref is None:
+            ref = got[:, :8424].copy()
+        assert (got[:, :8424] == ref).all(), (off, stride)
+    small = torch.zeros((5, 40), dtype=torch.uint8, device="cuda")
+    h.random_bits_raw(small, 5, 33, 40, 1234, 5, stream=st)
+    assert (small.cpu().numpy()[:, :33] == ref[:5, :33]).all() and not small.cpu().numpy()[:, 33:].any()    # prefix property of a row
+    other = torch.zeros((64, 8448), dtype=torch.uint8, device="cuda")
+    h.random_bits_raw(other, 64, 8424, 8448, 1234, 6, stream=st)
+    x = other.cpu().numpy()[:, :8424]
+    assert 0.45 < (x != ref).mean() < 0.55
+    big = torch.zeros((4096, 8448), dtype=torch.uint8, device="cuda")
+    h.random_bits_raw(big, 4096, 8424, 8448, 99, 1, stream=st)
+    b = big.cpu().numpy()[:, :8424].astype(np.float64)
+    n = b.size
+    assert abs(b.mean() - 0.5) < 5 * 0.5 / np.sqrt(n)
+    assert np.abs(b.mean(axis=0) - 0.5).max() < 6 * 0.5 / np.sqrt(4096) and np.abs(b.mean(axis=1) - 0.5).max() < 6 * 0.5 / np.sqrt(8424)
+    c = 2 * b - 1
+    for lag in (1, 2, 16, 32, 128):
+        assert abs((c[:, :-lag] * c[:, lag:]).mean()) < 5 / np.sqrt(c[:, lag:].size), lag
+    assert abs((c[:-1] * c[1:]).mean()) < 5 / np.sqrt(c[1:].size)
+    h.close()
