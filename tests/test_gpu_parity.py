@@ -875,3 +875,50 @@ def test_warp_shuffle_mapping_bit_exact_small_Z(capi, O, bg, monkeypatch):
     h.close()
     assert (out["hard"] == ref["hard"]).all() and _same_bits(out["app"], ref["app"])
     assert (out["iters"] == ref["iters"]).all() and (out["parity_ok"] == ref["parity_ok"]).all()
+
+
+def test_handle_lifetime_and_concurrent_host_threads(capi, O):
+    """release(obj) gives everything back (NRLDPCDecoder.m releaseImpl -> nrldpc_destroy: 80 create / decode / destroy cycles of
+    mixed sizes and arithmetics leave the device's free memory where it was), and distinct handles really are independent:
+    two host threads, each with its own handle (different base graph, lifting size and termination rule), decode concurrently
+    through the host-memory call and every result equals the oracle."""
+    import threading
+    import torch
+    rng = np.random.default_rng(77)
+    cases = []
+    for bg, Z, et in ((1, 96, True), (2, 52, False)):
+        d = O.dims(bg, Z)
+        info, llr = make_llr(O, bg, Z, 300, d["N"], 1.0, rng)
+        cases.append((bg, Z, et, llr, O.decode_nms(bg, Z, llr, 6, early_term=et)))
+    h = capi.Handle(1, 384, 8, False); h.decode(np.zeros((2, 68 * 384), np.float32)); h.close()     # warm the context / module
+    torch.cuda.synchronize()
+    free0 = torch.cuda.mem_get_info()[0]
+    for i in range(80):
+        bg, Z, et, llr, ref = cases[i % 2]
+        h = capi.Handle(bg, Z, 6, et, llr_dtype=capi.F16X2 if i % 4 == 3 else capi.F32, algorithm=capi.ALG_BP if i % 8 == 5 else capi.ALG_NMS)
+        out = h.decode(llr[:64 + i])
+        if i % 4 != 3 and i % 8 != 5:
+            assert (out["hard"] == ref["hard"][:64 + i]).all(), i
+        h.close()
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < (32 << 20), (free0, free1)
+    errors = []
+
+    def worker(case):
+        try:
+            bg, Z, et, llr, ref = case
+            hh = capi.Handle(bg, Z, 6, et)
+            for _ in range(25):
+                out = hh.decode(llr, want_soft=True)
+                assert (out["hard"] == ref["hard"]).all() and _same_bits(out["app"], ref["app"])
+                assert (out["iters"] == ref["iters"]).all() and (out["parity_ok"] == ref["parity_ok"]).all()
+            hh.close()
+        except Exception as e:      # noqa: BLE001 - reported below
+            errors.append(repr(e))
+    ts = [threading.Thread(target=worker, args=(c,)) for c in cases]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
