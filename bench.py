@@ -579,6 +579,11 @@ def main():
         cpu = {"value": bits / dt / 1e9, "unit": "Gb/s", "cores": threads, "kind": "port",
                "sample": f"first {CPU_BASELINE_CW} codewords of the batch, oracle B = flooding sum-product f64 with parity-check "
                          f"stop (comm.LDPCDecoder's algorithm), OpenMP over codewords, {dt:.2f} s"}
+        rb_all = cpu_reference_time.last
+        # the same on ONE host thread (SURVEY 8d asks for both): the first 48 codewords of the sample
+        dt1, bits1 = cpu_reference_time(w, sample[:48], 1)
+        cpu["one_thread"] = {"value": bits1 / dt1 / 1e9, "unit": "Gb/s", "cores": 1, "sample": f"first 48 codewords, {dt1:.2f} s"}
+        cpu_reference_time.last = rb_all
         from oracle import oracle as O
         t0 = time.perf_counter()
         ref = O.decode_nms(w["bg"], w["Z"], sample, w["iters"], early_term=bool(w["early_term"]), n_rows=w["n_rows"],
