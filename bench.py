@@ -527,6 +527,26 @@ def main():
                                 "d2h_bytes_per_step": B * K, "ms_per_step": dt16 * 1e3,
                                 "bler_at_esn0": float((hard_h.cuda() != info).any(dim=1).float().mean())}
         del llr_h16
+        # and as 8-bit integers (nrldpc_decode8, llr = q / 8): a quarter of the float32 bytes -- the transfer then hides behind the
+        # kernel.  Quantisation is the caller's choice and costs BLER (reported); the float32 figure above stays the e2e headline.
+        i8_scale = 0.125
+        llr_h8 = torch.empty((B, h.n_cw), dtype=torch.int8, pin_memory=True)
+        llr_h8.copy_((llr / i8_scale).round().clamp(-127, 126).to(torch.int8))
+        torch.cuda.synchronize()
+        for _ in range(2):
+            h.decode8_raw(llr_h8, i8_scale, B, hard_h, n_rows=w["n_rows"], mem=capi.MEM_HOST)
+        D.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            h.decode8_raw(llr_h8, i8_scale, B, hard_h, n_rows=w["n_rows"], mem=capi.MEM_HOST)
+        torch.cuda.synchronize()
+        dt8 = D.max_over_ranks((time.perf_counter() - t0) / n_e2e)
+        e2e["i8_transport"] = {"value": world * B * K / dt8 / 1e9, "unit": "Gb/s", "h2d_bytes_per_step": B * h.n_cw,
+                               "d2h_bytes_per_step": B * K, "ms_per_step": dt8 * 1e3, "scale": i8_scale,
+                               "bler_at_esn0": float((hard_h.cuda() != info).any(dim=1).float().mean()),
+                               "note": "LLRs quantised to int8 by the caller (q = round(8 * llr), |q| <= 127); decoded in float32"}
+        del llr_h8
         # what the MEX gateway really calls (matlab/nrldpc_mex.cpp): nrldpc_decode64 on ORDINARY pageable float64 memory,
         # decisions into pageable memory.  Host threads narrow to float32 into a pinned ring, so PCIe still carries 4 B / LLR.
         llr64 = llr_h.numpy().astype(np.float64)

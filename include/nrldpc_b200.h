@@ -122,6 +122,16 @@ int nrldpc_decode16(nrldpc_t *h, const uint16_t *llr_f16, int64_t batch, int32_t
                     uint8_t *info_hard, float *app_soft, int32_t *iters, uint8_t *parity_ok,
                     int32_t mem, void *stream);
 
+/* Same call with the LLRs transported as 8-bit integers (a quarter of the host<->device bytes of float32; what the
+ * host-memory call is bound by is PCIe): llr = scale * q for q in [-128, 126], q = 127 marks a filler / known-zero
+ * position (+inf, NRLDPCDecoder.m:264), q = 0 a punctured / unsent one.  The values are widened to float32 on the device
+ * (one rounded multiplication) and decoded as by nrldpc_decode: the result is bit-identical to nrldpc_decode on the
+ * float32 values scale * q.  Quantising the LLRs is the CALLER's decision and costs BLER (receivers use 6-8 bits);
+ * nrldpc_decode on float32 stays the reference-facing call. */
+int nrldpc_decode8(nrldpc_t *h, const int8_t *llr_q, float scale, int64_t batch, int32_t n_rows,
+                   uint8_t *info_hard, float *app_soft, int32_t *iters, uint8_t *parity_ok,
+                   int32_t mem, void *stream);
+
 /* Same call on float64 buffers, the type the reference hands to step() (cw_tilde is double, NRLDPCDecoder.m:262).
  * With NRLDPC_ALG_BP the doubles are decoded as they are (float64 arithmetic, app_soft in float64); with the
  * default algorithm they are rounded to float32 on the device and app_soft must be NULL. */

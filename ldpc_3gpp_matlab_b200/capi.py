@@ -40,7 +40,7 @@ SYMBOLS = (
     "nrldpc_set_index", "nrldpc_lifting_size", "nrldpc_base_graph", "nrldpc_decode", "nrldpc_encode",
     "nrldpc_rate_match", "nrldpc_rate_recover", "nrldpc_qpsk_awgn_llr", "nrldpc_host_alloc",
     "nrldpc_host_free", "nrldpc_launch_count", "nrldpc_version",
-    "nrldpc_modulate", "nrldpc_awgn", "nrldpc_demodulate", "nrldpc_mod_awgn_llr", "nrldpc_crc", "nrldpc_decode16", "nrldpc_decode64",
+    "nrldpc_modulate", "nrldpc_awgn", "nrldpc_demodulate", "nrldpc_mod_awgn_llr", "nrldpc_crc", "nrldpc_decode16", "nrldpc_decode64", "nrldpc_decode8",
     "nrldpc_qpsk_awgn_rate_recover", "nrldpc_bler_count", "nrldpc_random_bits",
 )
 
@@ -98,6 +98,7 @@ def load():
     lib.nrldpc_base_graph.argtypes = [i32, i32, vp, vp, vp]
     lib.nrldpc_decode.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, i32, vp]
     lib.nrldpc_decode16.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, i32, vp]
+    lib.nrldpc_decode8.argtypes = [vp, vp, C.c_float, i64, i32, vp, vp, vp, vp, i32, vp]
     lib.nrldpc_decode64.argtypes = [vp, vp, i64, i32, vp, vp, vp, vp, i32, vp]
     lib.nrldpc_encode.argtypes = [vp, vp, i64, vp, i32, vp]
     lib.nrldpc_rate_match.argtypes = [vp, vp, i64, C.POINTER(Rm), vp, i32, vp]
@@ -212,6 +213,11 @@ class Handle:
     def decode_raw(self, llr, batch, hard, soft=None, iters=None, ok=None, n_rows=0, mem=MEM_HOST, stream=None):
         self._check(self._lib.nrldpc_decode(self._h, _ptr(llr), int(batch), int(n_rows), _ptr(hard), _ptr(soft),
                                             _ptr(iters), _ptr(ok), int(mem), stream))
+
+    def decode8_raw(self, llr_q, scale, batch, hard, soft=None, iters=None, ok=None, n_rows=0, mem=MEM_HOST, stream=None):
+        """nrldpc_decode8: LLRs as int8 (llr = scale * q, q = 127 = filler)."""
+        self._check(self._lib.nrldpc_decode8(self._h, _ptr(llr_q), float(scale), int(batch), int(n_rows), _ptr(hard), _ptr(soft),
+                                             _ptr(iters), _ptr(ok), mem, stream))
 
     def decode16_raw(self, llr_f16, batch, hard, soft=None, iters=None, ok=None, n_rows=0, mem=MEM_HOST, stream=None):
         """nrldpc_decode16: LLRs as IEEE binary16 (numpy float16 / torch.float16)."""

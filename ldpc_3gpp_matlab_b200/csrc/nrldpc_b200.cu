@@ -37,6 +37,20 @@ __global__ void __launch_bounds__(256) widen_f16_kernel(const uint2 *__restrict_
     }
 }
 
+// 8-bit LLR transport (nrldpc_decode8): llr = scale * q, q = 127 marks a filler / known-zero position (+inf)
+__global__ void __launch_bounds__(256) widen_i8_kernel(const uint32_t *__restrict__ in, float4 *__restrict__ out, long long n4, float scale) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t v = __ldcs(in + i);
+        float f[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int q = (int)(signed char)((v >> (8 * k)) & 0xffu);
+            f[k] = q == 127 ? __int_as_float(0x7f800000) : __fmul_rn(scale, (float)q);
+        }
+        out[i] = make_float4(f[0], f[1], f[2], f[3]);
+    }
+}
+
 // Shared-window address at which a kernel without static shared memory sees its dynamic shared memory.
 __global__ void smem_base_probe(uint32_t *out) {
     extern __shared__ __align__(16) unsigned char probe_smem[];
@@ -47,7 +61,7 @@ __global__ void smem_base_probe(uint32_t *out) {
 namespace {
 
 constexpr int kNumPipe = 3;  // streams / staging sets for NRLDPC_MEM_HOST calls
-enum { kInF32 = 0, kInF16 = 1, kInF64 = 2 };   // element type of the LLR buffer handed to decode_impl
+enum { kInF32 = 0, kInF16 = 1, kInF64 = 2, kInI8 = 3 };   // element type of the LLR buffer handed to decode_impl
 
 thread_local char g_create_error[256] = "";
 
@@ -130,6 +144,7 @@ struct nrldpc_handle {
     int zero_copy_max = 2;                   // host-memory decodes of up to this many codewords read / write pinned host memory directly (NRLDPC_ZERO_COPY_MAX, 0 = off)
     int refill = 1;                          // NRLDPC_REFILL: 0 = never refill slots, 1 = where measured to pay (default), 2 = refill kernel whenever possible,
                                              // 3 = prefetched refill (decode_kernel_refill.cuh) whenever possible
+    float i8_scale = 1.0f;                   // scale of the current nrldpc_decode8 call
     int refill_spares = 2;                   // NRLDPC_REFILL_SPARES: mailboxes per CTA of the prefetched-refill kernel
     int no_staging = 0;                      // NRLDPC_NO_STAGING=1: hand pageable buffers to cudaMemcpyAsync as they are (A/B)
     int bp_threads = 1024;           // CTA width of the sum-product kernel (NRLDPC_BP_THREADS=512 selects the 128-register build)
@@ -531,7 +546,7 @@ int ensure_decode_staging(nrldpc_handle *h, PipeSlot &s, size_t cw, bool soft, i
         s.cap_cw = cw;
     }
     if (soft && in_kind != kInF64 && !s.soft) CUDA_TRY(h, cudaMalloc(&s.soft, s.cap_cw * h->d.n_cw * sizeof(float)));
-    if (in_kind == kInF16 && !s.llr16) CUDA_TRY(h, cudaMalloc(&s.llr16, s.cap_cw * h->d.n_cw * sizeof(uint16_t)));
+    if ((in_kind == kInF16 || in_kind == kInI8) && !s.llr16) CUDA_TRY(h, cudaMalloc(&s.llr16, s.cap_cw * h->d.n_cw * sizeof(uint16_t)));
     if (in_kind == kInF64 && !s.llr64) CUDA_TRY(h, cudaMalloc(&s.llr64, s.cap_cw * h->d.n_cw * sizeof(double)));
     if (in_kind == kInF64 && soft && !s.soft64) CUDA_TRY(h, cudaMalloc(&s.soft64, s.cap_cw * h->d.n_cw * sizeof(double)));
     return 0;
@@ -916,6 +931,14 @@ int widen(nrldpc_handle *h, cudaStream_t st, const uint16_t *in, float *out, int
     return 0;
 }
 
+int widen8(nrldpc_handle *h, cudaStream_t st, const int8_t *in, float *out, int64_t n_cw_total) {
+    const long long n4 = (long long)n_cw_total * h->d.n_cw / 4;   // n_cw is a multiple of 4
+    nrldpc::widen_i8_kernel<<<grid_for(h, n4, 256), 256, 0, st>>>(reinterpret_cast<const uint32_t *>(in), reinterpret_cast<float4 *>(out), n4, h->i8_scale);
+    CUDA_TRY(h, cudaGetLastError());
+    h->launches += 1;
+    return 0;
+}
+
 int narrow(nrldpc_handle *h, cudaStream_t st, const double *in, float *out, int64_t n_cw_total) {
     const long long n = (long long)n_cw_total * h->d.n_cw;
     nrldpc::narrow_f64_kernel<<<grid_for(h, n, 256), 256, 0, st>>>(in, out, n);
@@ -936,6 +959,9 @@ int launch_any(nrldpc_handle *h, PipeSlot &s, cudaStream_t st, const void *llr, 
     const float *src = static_cast<const float *>(llr);
     if (in_kind == kInF16) {
         if (int rc = widen(h, st, static_cast<const uint16_t *>(llr), f32_tmp, batch)) return rc;
+        src = f32_tmp;
+    } else if (in_kind == kInI8) {
+        if (int rc = widen8(h, st, static_cast<const int8_t *>(llr), f32_tmp, batch)) return rc;
         src = f32_tmp;
     } else if (in_kind == kInF64) {
         if (int rc = narrow(h, st, static_cast<const double *>(llr), f32_tmp, batch)) return rc;
@@ -958,9 +984,9 @@ int decode_impl(nrldpc_t *h, const void *llr, int in_kind, int64_t batch, int32_
     if (in_kind == kInF64 && !bp && app_soft)
         return fail(h, NRLDPC_EUNSUPPORTED, "nrldpc_decode64 returns app_soft only with NRLDPC_ALG_BP (the min-sum kernels compute in float32)");
     ENTER_DEVICE(h);
-    const size_t in_elt = in_kind == kInF16 ? sizeof(uint16_t) : in_kind == kInF64 ? sizeof(double) : sizeof(float);
+    const size_t in_elt = in_kind == kInF16 ? sizeof(uint16_t) : in_kind == kInF64 ? sizeof(double) : in_kind == kInI8 ? sizeof(int8_t) : sizeof(float);
     const size_t soft_elt = in_kind == kInF64 ? sizeof(double) : sizeof(float);
-    const bool convert = in_kind == kInF16 || (in_kind == kInF64 && !bp);
+    const bool convert = in_kind == kInF16 || in_kind == kInI8 || (in_kind == kInF64 && !bp);
     if (mem == NRLDPC_MEM_DEVICE) {
         cudaStream_t st = static_cast<cudaStream_t>(stream);
         if ((reinterpret_cast<uintptr_t>(llr) & 15) || (app_soft && (reinterpret_cast<uintptr_t>(app_soft) & 15)))
@@ -1003,7 +1029,7 @@ int decode_impl(nrldpc_t *h, const void *llr, int in_kind, int64_t batch, int32_
     // The kernel reads the LLRs straight from pinned host memory (its bulk copy crosses PCIe itself) and writes the
     // decisions straight back -- one launch and one synchronisation instead of H2D + launch + D2H + synchronisation.
     // Caller buffers that are pageable, float64 or misaligned pass through the pinned ring on the caller's thread.
-    if (batch <= h->zero_copy_max && !bp && in_kind != kInF16 && !app_soft) {
+    if (batch <= h->zero_copy_max && !bp && in_kind != kInF16 && in_kind != kInI8 && !app_soft) {
         PipeSlot &s = h->pipe[0];
         if (int rc = ensure_host_ring(h, s, (size_t)batch * h->d.n_cw * sizeof(float), (size_t)batch, true, true)) return rc;
         const float *src = static_cast<const float *>(llr);
@@ -1079,7 +1105,7 @@ int decode_impl(nrldpc_t *h, const void *llr, int in_kind, int64_t batch, int32_
     for (int64_t off = 0; off < batch; off += chunk, k = (k + 1) % kNumPipe) {
         PipeSlot &s = h->pipe[k];
         const int64_t n = std::min<int64_t>(chunk, batch - off);
-        void *d_in = kind_dev == kInF16 ? static_cast<void *>(s.llr16) : kind_dev == kInF64 ? static_cast<void *>(s.llr64)
+        void *d_in = (kind_dev == kInF16 || kind_dev == kInI8) ? static_cast<void *>(s.llr16) : kind_dev == kInF64 ? static_cast<void *>(s.llr64)
                                                                                            : static_cast<void *>(s.llr);
         void *d_soft = !app_soft ? nullptr : in_kind == kInF64 ? static_cast<void *>(s.soft64) : static_cast<void *>(s.soft);
         const unsigned char *src = llr_b + (size_t)off * h->d.n_cw * in_elt;
@@ -1129,6 +1155,14 @@ NRLDPC_EXPORT int nrldpc_decode(nrldpc_t *h, const float *llr, int64_t batch, in
 NRLDPC_EXPORT int nrldpc_decode16(nrldpc_t *h, const uint16_t *llr_f16, int64_t batch, int32_t n_rows, uint8_t *info_hard,
                                   float *app_soft, int32_t *iters, uint8_t *parity_ok, int32_t mem, void *stream) {
     return decode_impl(h, llr_f16, kInF16, batch, n_rows, info_hard, app_soft, iters, parity_ok, mem, stream);
+}
+
+NRLDPC_EXPORT int nrldpc_decode8(nrldpc_t *h, const int8_t *llr_q, float scale, int64_t batch, int32_t n_rows, uint8_t *info_hard,
+                                 float *app_soft, int32_t *iters, uint8_t *parity_ok, int32_t mem, void *stream) {
+    if (!h) return NRLDPC_ESHAPE;
+    if (!(scale > 0.0f) || !(scale < 1e30f)) return fail(h, NRLDPC_ESHAPE, "scale must be a positive finite number");
+    h->i8_scale = scale;
+    return decode_impl(h, llr_q, kInI8, batch, n_rows, info_hard, app_soft, iters, parity_ok, mem, stream);
 }
 
 NRLDPC_EXPORT int nrldpc_decode64(nrldpc_t *h, const double *llr_f64, int64_t batch, int32_t n_rows, uint8_t *info_hard,

@@ -512,6 +512,43 @@ def test_decode16_half_transport(capi, O):
             h.close()
 
 
+def test_decode8_int8_transport(capi, O):
+    """nrldpc_decode8 (LLRs transported as int8, llr = scale * q, q = 127 = filler): bit-identical to nrldpc_decode / the oracle on
+    the float32 values scale * q -- host path (pinned and pageable), device path, both arithmetics, early stop, soft output,
+    trimmed rows, extreme codes (-128, 126, 127, 0)."""
+    import torch
+    rng = np.random.default_rng(88)
+    for bg, Z, B, E, scale in ((1, 384, 9, 25272, 0.125), (2, 52, 600, 2000, 0.25), (2, 6, 300, 100, 0.5), (1, 22, 41, 1200, 0.1)):
+        info, llr = make_llr(O, bg, Z, B, E, 0.5, rng)
+        q = np.clip(np.rint(llr / scale), -127, 126).astype(np.int8)
+        q[0, 5 * Z:5 * Z + 3] = 127                      # filler marks
+        q[1, 7 * Z] = -128
+        q[1, 7 * Z + 1] = 126
+        deq = (np.float32(scale) * q.astype(np.float32)).astype(np.float32)
+        deq[q == 127] = np.inf
+        rows = 0 if bg == 2 else max(4, -(-(E + 2 * Z) // Z) - 22)
+        for dt, f16 in ((capi.F32, False), (capi.F16X2, True)):
+            h = capi.Handle(bg, Z, 6, True, llr_dtype=dt)
+            ref = O.decode_nms(bg, Z, deq, 6, early_term=True, f16=f16, n_rows=rows if rows else None)
+            hard = np.zeros((B, h.K), np.uint8); soft = np.zeros((B, h.n_cw), np.float32)
+            it = np.zeros(B, np.int32); ok = np.zeros(B, np.uint8)
+            h.decode8_raw(q, scale, B, hard, soft, it, ok, n_rows=rows)            # pageable host memory
+            assert (hard == ref["hard"]).all() and _same_bits(soft, ref["app"]), (bg, Z, f16)
+            assert (it == ref["iters"]).all() and (ok == ref["parity_ok"]).all(), (bg, Z, f16)
+            qp = torch.from_numpy(q).pin_memory()
+            hp = torch.zeros((B, h.K), dtype=torch.uint8).pin_memory()
+            h.decode8_raw(qp, scale, B, hp, n_rows=rows)                           # pinned host memory
+            assert (hp.numpy() == ref["hard"]).all()
+            dq = torch.from_numpy(q).cuda()
+            dh = torch.zeros((B, h.K), dtype=torch.uint8, device="cuda")
+            h.decode8_raw(dq, scale, B, dh, n_rows=rows, mem=capi.MEM_DEVICE, stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert (dh.cpu().numpy() == ref["hard"]).all()
+            with pytest.raises(capi.NRLDPCError):
+                h.decode8_raw(q, 0.0, B, hard)
+            h.close()
+
+
 # ---- NRLDPC_ALG_BP: the reference's own algorithm (flooding sum-product, float64) on the device -------------
 # Checker: oracle B (oracle/nrldpc_oracle.c, decode_bp_one), the restatement of MathWorks' documented comm.LDPCDecoder
 # algorithm as configured at NRLDPCDecoder.m:120.  Kernel and oracle perform every +, -, * in the same order; they
