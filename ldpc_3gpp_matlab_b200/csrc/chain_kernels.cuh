@@ -320,10 +320,91 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------
+// Gather table of rate recovery (round 2).  The map "entry c of the decoder's input layout <- received LLR(s)" depends only on
+// the rate-matching geometry, not on the code block, so it is evaluated ONCE per geometry into a table in global memory (it stays
+// in L2; every CTA reads it with 16-byte loads) instead of once per code block and entry (~120 instructions each):
+//     code >= 0   the entry has exactly one source: f[code] (bit de-interleaver already folded in)
+//     kRrZero     punctured prefix, or beyond the circular buffer: 0, no HARQ state
+//     kRrFiller   filler: +inf (NRLDPCDecoder.m:264)
+//     kRrEmpty    inside the circular buffer but not transmitted this time: 0 + the HARQ buffer
+//     kRrMulti    wrapped repetitions (several sources, soft-combined in increasing k): the general loop below
+// Same additions in the same order as before (0 + x, then + HARQ), hence bit-identical outputs.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRrZero = -1, kRrFiller = -2, kRrEmpty = -3, kRrMulti = -4;
+
+__global__ void __launch_bounds__(256) rr_table_kernel(int *__restrict__ table, RmGeom g, int QM, uint32_t magic_eq) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < g.ncw; c += gridDim.x * blockDim.x) {
+        const int n = c - g.Z2;
+        int code = kRrZero;
+        if (n >= 0) {
+            if (n >= g.F0u && n < g.F1u) {
+                code = kRrFiller;
+            } else if (n < g.Ncb) {
+                int first = rm_rank(g, n) - g.rank_k0;
+                if (first < 0) first += g.Nnf;
+                if (first >= g.E) {
+                    code = kRrEmpty;
+                } else if (first + g.Nnf < g.E) {
+                    code = kRrMulti;
+                } else {
+                    int i = (int)__umulhi((uint32_t)first, magic_eq);      // first / EQ, one below at most
+                    int j = first - i * g.EQ;
+                    if (j >= g.EQ) { j -= g.EQ; ++i; }
+                    code = i + j * QM;
+                }
+            }
+        }
+        table[c] = code;
+    }
+}
+
+// soft-combined repetitions of entry n (n in the circular buffer, not filler), e_f = the block's received LLRs in f order
+__device__ __noinline__ float rr_multi(const RmGeom &g, const int n, const float *e_f, const uint32_t magic_eq, const int QM) {
+    int first = rm_rank(g, n) - g.rank_k0;
+    if (first < 0) first += g.Nnf;
+    float acc = 0.0f;
+    for (int k = first; k < g.E; k += g.Nnf) {
+        int i = (int)__umulhi((uint32_t)k, magic_eq);
+        int j = k - i * g.EQ;
+        if (j >= g.EQ) { j -= g.EQ; ++i; }
+        acc = __fadd_rn(acc, e_f[i + j * QM]);                             // same addition order as NRLDPCDecoder.m:230
+    }
+    return acc;
+}
+
+// one float4 of the decoder's input layout from the table (q = index of the float4 in the row)
+__device__ __forceinline__ float4 rr_gather4(const RmGeom &g, const int *__restrict__ table, const int q, const float *e_f,
+                                             float *__restrict__ harq_row, const uint32_t magic_eq, const int QM) {
+    const int4 c4 = __ldg(reinterpret_cast<const int4 *>(table) + q);
+    const int code[4] = {c4.x, c4.y, c4.z, c4.w};
+    float v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int cd = code[u];
+        float r = 0.0f;
+        if (cd == kRrFiller) {
+            r = __int_as_float(0x7f800000);
+        } else if (cd != kRrZero) {
+            float acc = 0.0f;
+            if (cd >= 0) acc = __fadd_rn(acc, e_f[cd]);
+            else if (cd == kRrMulti) acc = rr_multi(g, 4 * q + u - g.Z2, e_f, magic_eq, QM);
+            if (harq_row) {
+                float *hb = harq_row + (4 * q + u - g.Z2);
+                acc = __fadd_rn(acc, *hb);
+                *hb = acc;
+            }
+            r = acc;
+        }
+        v[u] = r;
+    }
+    return make_float4(v[0], v[1], v[2], v[3]);
+}
+
 template <int QM>
 __global__ void __launch_bounds__(512) rate_recover_tma_kernel(const float *__restrict__ f, float *__restrict__ harq,
                                                                float *__restrict__ out, long long batch, RmGeom g,
-                                                               int n_buf, uint32_t magic_eq) {
+                                                               int n_buf, uint32_t magic_eq, const int *__restrict__ table) {
     extern __shared__ __align__(128) unsigned char rr_tma_smem[];
     __shared__ __align__(8) uint64_t bar[2];
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -352,6 +433,10 @@ __global__ void __launch_bounds__(512) rate_recover_tma_kernel(const float *__re
         phase[cur] ^= 1u;
         const float *e_f = buf[cur];
         float4 *ob = reinterpret_cast<float4 *>(out + b * g.ncw);
+        if (table != nullptr) {
+            float *hrow = harq ? harq + b * g.N : nullptr;
+            for (int q = tid; q < (g.ncw >> 2); q += nt) __stcs(ob + q, rr_gather4(g, table, q, e_f, hrow, magic_eq, QM));
+        } else
         for (int q = tid; q < (g.ncw >> 2); q += nt) {
             float v[4];
 #pragma unroll
@@ -734,7 +819,8 @@ __global__ void __launch_bounds__(256) random_bits_kernel(uint8_t *__restrict__ 
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(512) qpsk_awgn_rate_recover_kernel(const uint8_t *__restrict__ f_bits, float *__restrict__ harq,
                                                                      float *__restrict__ out, long long batch, RmGeom g, uint32_t magic_eq,
-                                                                     float sigma, float gain, uint64_t seed, uint64_t stream_id) {
+                                                                     float sigma, float gain, uint64_t seed, uint64_t stream_id,
+                                                                     const int *__restrict__ table) {
     extern __shared__ __align__(16) unsigned char qrr_smem[];
     float *e_f = reinterpret_cast<float *>(qrr_smem);
     const int tid = threadIdx.x, nt = blockDim.x;
@@ -760,6 +846,10 @@ __global__ void __launch_bounds__(512) qpsk_awgn_rate_recover_kernel(const uint8
         }
         __syncthreads();
         float4 *ob = reinterpret_cast<float4 *>(out + b * g.ncw);
+        if (table != nullptr) {
+            float *hrow = harq ? harq + b * g.N : nullptr;
+            for (int q = tid; q < (g.ncw >> 2); q += nt) __stcs(ob + q, rr_gather4(g, table, q, e_f, hrow, magic_eq, 2));
+        } else
         for (int q = tid; q < (g.ncw >> 2); q += nt) {
             float v[4];
 #pragma unroll

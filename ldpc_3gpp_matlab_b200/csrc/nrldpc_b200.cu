@@ -144,6 +144,9 @@ struct nrldpc_handle {
     int zero_copy_max = 2;                   // host-memory decodes of up to this many codewords read / write pinned host memory directly (NRLDPC_ZERO_COPY_MAX, 0 = off)
     int refill = 1;                          // NRLDPC_REFILL: 0 = never refill slots, 1 = where measured to pay (default), 2 = refill kernel whenever possible,
                                              // 3 = prefetched refill (decode_kernel_refill.cuh) whenever possible
+    struct RrTable { nrldpc::RmGeom g; int *d; };
+    std::vector<RrTable> rr_tables;          // gather tables of rate recovery, one per geometry seen (chain_kernels.cuh)
+    int rr_table_on = 1;                     // NRLDPC_RR_TABLE=0: evaluate the gather map per code block (the round-1 kernels)
     float i8_scale = 1.0f;                   // scale of the current nrldpc_decode8 call
     int refill_spares = 2;                   // NRLDPC_REFILL_SPARES: mailboxes per CTA of the prefetched-refill kernel
     int no_staging = 0;                      // NRLDPC_NO_STAGING=1: hand pageable buffers to cudaMemcpyAsync as they are (A/B)
@@ -633,6 +636,28 @@ int launch_rr_staged(nrldpc_handle *h, cudaStream_t st, const float *f, float *h
     return 0;
 }
 
+// Gather table of this geometry (built once on an internal stream and finished before it is handed out, so that consumers on
+// any stream may read it); nullptr when tables are switched off or too many geometries are alive: the kernels then evaluate
+// the map themselves.
+const int *rr_table_for(nrldpc_handle *h, const nrldpc::RmGeom &g, uint32_t magic) {
+    if (!h->rr_table_on) return nullptr;
+    for (const auto &t : h->rr_tables)
+        if (memcmp(&t.g, &g, sizeof(g)) == 0) return t.d;
+    if (h->rr_tables.size() >= 64) return nullptr;
+    if (ensure_pipe(h)) return nullptr;
+    int *d = nullptr;
+    if (cudaMalloc(&d, (size_t)g.ncw * sizeof(int)) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    cudaStream_t st = h->pipe[0].stream;
+    nrldpc::rr_table_kernel<<<grid_for(h, g.ncw, 256), 256, 0, st>>>(d, g, g.Qm, magic);
+    if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); cudaFree(d); return nullptr; }
+    h->launches += 1;
+    nrldpc_handle::RrTable t;
+    memcpy(&t.g, &g, sizeof(g));
+    t.d = d;
+    h->rr_tables.push_back(t);
+    return d;
+}
+
 template <int QM>
 int launch_rr_tma(nrldpc_handle *h, cudaStream_t st, const float *f, float *harq, float *out, int64_t n, const nrldpc::RmGeom &g) {
     const size_t row = (size_t)g.E * sizeof(float);
@@ -643,8 +668,8 @@ int launch_rr_tma(nrldpc_handle *h, cudaStream_t st, const float *f, float *harq
     int occ = 1;
     if (int rc = cached_occupancy(h, reinterpret_cast<const void *>(nrldpc::rate_recover_tma_kernel<QM>), 512, smem, &occ)) return rc;
     const int grid = (int)std::min<int64_t>(n, (int64_t)h->num_sms * std::max(1, occ));
-    const uint32_t magic = (uint32_t)((1ull << 32) / (uint64_t)g.EQ);   // floor: quotient estimate is exact or one low
-    nrldpc::rate_recover_tma_kernel<QM><<<grid, 512, smem, st>>>(f, harq, out, n, g, n_buf, g.EQ == 1 ? 0xffffffffu : magic);
+    const uint32_t magic = g.EQ == 1 ? 0xffffffffu : (uint32_t)((1ull << 32) / (uint64_t)g.EQ);   // floor: quotient estimate is exact or one low
+    nrldpc::rate_recover_tma_kernel<QM><<<grid, 512, smem, st>>>(f, harq, out, n, g, n_buf, magic, rr_table_for(h, g, magic));
     return 0;
 }
 
@@ -786,6 +811,7 @@ NRLDPC_EXPORT int nrldpc_create(nrldpc_t **out, const nrldpc_cfg *cfg) {
     if (getenv("NRLDPC_NO_STAGING")) h->no_staging = 1;
     if (const char *v = getenv("NRLDPC_ZERO_COPY_MAX")) h->zero_copy_max = std::max(0, std::min(64, atoi(v)));
     if (const char *v = getenv("NRLDPC_REFILL")) h->refill = std::max(0, std::min(3, atoi(v)));
+    if (const char *v = getenv("NRLDPC_RR_TABLE")) h->rr_table_on = atoi(v) ? 1 : 0;
     if (const char *v = getenv("NRLDPC_REFILL_SPARES")) h->refill_spares = std::max(1, std::min(8, atoi(v)));
     if (const char *v = getenv("NRLDPC_CWPC")) h->cwpc_override = std::max(0, atoi(v));
     if (const char *v = getenv("NRLDPC_OCC_CAP")) { h->occ_cap = std::max(1, std::min(32, atoi(v))); h->occ_cap_forced = 1; }
@@ -902,6 +928,7 @@ NRLDPC_EXPORT void nrldpc_destroy(nrldpc_t *h) {
     delete h->pool;
     if (h->dev_done) cudaEventDestroy(h->dev_done);
     cudaFree(h->dev_widen);
+    for (auto &t : h->rr_tables) cudaFree(t.d);
     cudaFree(h->edesc);
     cudaFree(h->row_start);
     cudaFree(h->bp_shift); cudaFree(h->bp_colz); cudaFree(h->bp_col_start); cudaFree(h->bp_col_edge);
@@ -1319,7 +1346,8 @@ NRLDPC_EXPORT int nrldpc_qpsk_awgn_rate_recover(nrldpc_t *h, const uint8_t *f_bi
     const int grid = (int)std::min<int64_t>(batch, (int64_t)h->num_sms * occ);
     const uint32_t magic = g.EQ == 1 ? 0xffffffffu : (uint32_t)((1ull << 32) / (uint64_t)g.EQ);
     nrldpc::qpsk_awgn_rate_recover_kernel<<<grid, 512, smem, static_cast<cudaStream_t>(stream)>>>(
-        f_bits, harq, llr_cw, batch, g, magic, sqrtf(0.5f * variance), 2.8284271247461900976f / variance, seed, stream_id);
+        f_bits, harq, llr_cw, batch, g, magic, sqrtf(0.5f * variance), 2.8284271247461900976f / variance, seed, stream_id,
+        rr_table_for(h, g, magic));
     CUDA_TRY(h, cudaGetLastError());
     h->launches += 1;
     return 0;
