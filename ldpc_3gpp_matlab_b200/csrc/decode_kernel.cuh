@@ -510,6 +510,47 @@ __device__ __forceinline__ void store_outputs(const DecArgs &a, const float *app
     }
 }
 
+// One codeword per CTA (FULL kernels): the per-codeword load / store run OUT of line.  They execute once per codeword, and
+// inlined into the kernel they weigh on the layer loop's register allocation.  Measured on one box, two rounds each
+// (profiles/r02_v9_ool_helpers_ab.txt; inline -> out of line, ms per headline launch): float32 2.900 -> 2.890 fixed, 3.086 -> 3.074
+// with the stop, config 4 1.136 -> 1.130; packed half 1.716 -> 1.675, 2.038 -> 2.012, 1.002 -> 0.99.  Everything they need is passed
+// by value: with a reference to the kernel parameters every field access out of line is a generic load, and config 4 (short
+// codewords) lost 1.3 %.  The multi-codeword kernels keep the inline versions: out of line BASELINE config 3 lost 9 %.
+__device__ __noinline__ uint32_t load_one_ool(const float *src, float *app, const int ncw, uint64_t *bar, uint32_t parity) {
+    const uint32_t bytes = (uint32_t)ncw * 4u;                 // ncw*4 is a multiple of 16 for every (BG, Z)
+    if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // earlier generic-proxy accesses to app vs the async write
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s_stream(app, src, bytes, bar);                 // evict_first: must not displace the pinned c2v scratch
+    }
+    mbar_wait(bar, parity);
+    float4 *dst = reinterpret_cast<float4 *>(app);
+    for (int i = threadIdx.x; i < (ncw >> 2); i += blockDim.x) {
+        float4 v = dst[i];
+        v.x = clamp_llr(v.x); v.y = clamp_llr(v.y); v.z = clamp_llr(v.z); v.w = clamp_llr(v.w);
+        dst[i] = v;
+    }
+    return parity ^ 1u;
+}
+__device__ __noinline__ void store_one_ool(const float *app, uint8_t *hard, float *soft, const int ncw, const int K) {
+    if ((K & 3) == 0) {       // four hard decisions per 32-bit store (K = kcols*Z is a multiple of 4 for every even Z)
+        const float4 *src = reinterpret_cast<const float4 *>(app);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(hard);
+        for (int k = threadIdx.x; k < (K >> 2); k += blockDim.x) {
+            const float4 v = src[k];
+            dst[k] = (__float_as_uint(v.x) >> 31) | ((__float_as_uint(v.y) >> 31) << 8) |
+                     ((__float_as_uint(v.z) >> 31) << 16) | ((__float_as_uint(v.w) >> 31) << 24);
+        }
+    } else {
+        for (int k = threadIdx.x; k < K; k += blockDim.x) hard[k] = app[k] < 0.0f ? 1 : 0;
+    }
+    if (soft) {
+        float4 *dst = reinterpret_cast<float4 *>(soft);
+        const float4 *src = reinterpret_cast<const float4 *>(app);
+        for (int i = threadIdx.x; i < (ncw >> 2); i += blockDim.x) __stcs(dst + i, src[i]);
+    }
+}
+
 // The same syndrome with the base graph's shape known at compile time: edge operands come from the parameter bank
 // as in the layer code (no descriptor loads, no loop control) -- about 5 instructions per edge instead of 12.  With
 // 'Parity check satisfied' (the reference's only setting, NRLDPCDecoder.m:120) this runs after EVERY iteration.
@@ -826,7 +867,8 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
         const long long cw0 = group * a.cwpc;
         const int n_here = (int)min((long long)a.cwpc, a.batch - cw0);
 
-        load_group(a, app, cw0, n_here, ncw, bar, bar_parity);
+        if (FULL) bar_parity = load_one_ool(a.llr + cw0 * ncw, app, ncw, bar, bar_parity);
+        else load_group(a, app, cw0, n_here, ncw, bar, bar_parity);
         if (tid < 2 * a.cwpc) s_flag[tid] = 0;
         __syncthreads();
 
@@ -915,7 +957,8 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_kernel(
             }
             __syncthreads();
         }
-        store_outputs(a, app, cw0, n_here, ncw, K);
+        if (FULL) store_one_ool(app, a.hard + cw0 * K, a.soft ? a.soft + cw0 * ncw : nullptr, ncw, K);
+        else store_outputs(a, app, cw0, n_here, ncw, K);
         if (active && z == 0) {
             if (a.iters) a.iters[cw0 + slot] = my_iters;
             if (a.ok) a.ok[cw0 + slot] = (uint8_t)my_ok;

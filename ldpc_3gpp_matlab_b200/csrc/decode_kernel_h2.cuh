@@ -339,10 +339,11 @@ __device__ __forceinline__ void load_pair(const float *__restrict__ rowA, const 
 // Outputs of ONE codeword (half 0 = A, 1 = B) of a pair, written by the pair's own lanes.
 // Soft output: lane z handles position z of every block column (nlanes = Z), so for the degree-1 parity columns of the
 // active extension rows it owns the row's record and rebuilds the a-posteriori value on the fly (ext_app_h2).
-__device__ __forceinline__ void store_half(const DecArgs &a, const uint32_t *app, long long cw, int half, int ncw, int K,
+__device__ __forceinline__ void store_half(uint8_t *hard_base, float *soft_base, const int kcols, const int n_rows, const uint32_t *app,
+                                           long long cw, int half, int ncw, int K,
                                            int lane, int nlanes, const uint32_t *my_rec, const uint64_t pol) {
     const int sh = half ? 31 : 15;
-    uint8_t *hard = a.hard + cw * K;
+    uint8_t *hard = hard_base + cw * K;
     if ((K & 3) == 0 && (reinterpret_cast<uintptr_t>(app) & 15) == 0) {
         const uint4 *src = reinterpret_cast<const uint4 *>(app);
         uint32_t *dst = reinterpret_cast<uint32_t *>(hard);
@@ -353,12 +354,12 @@ __device__ __forceinline__ void store_half(const DecArgs &a, const uint32_t *app
     } else {
         for (int k = lane; k < K; k += nlanes) hard[k] = (uint8_t)((app[k] >> sh) & 1u);
     }
-    if (a.soft) {
-        float *dst = a.soft + cw * ncw;
-        const int ext0 = a.kcols + 4, ext1 = a.kcols + a.n_rows;
+    if (soft_base) {
+        float *dst = soft_base + cw * ncw;
+        const int ext0 = kcols + 4, ext1 = kcols + n_rows;
         for (int i = lane, col = 0; i < ncw; i += nlanes, ++col) {
             uint32_t w = app[i];
-            if (col >= ext0 && col < ext1) w = ext_app_h2(my_rec, col - a.kcols, pol, w);
+            if (col >= ext0 && col < ext1) w = ext_app_h2(my_rec, col - kcols, pol, w);
             const float2 f = __half22float2(as_h2(w));
             __stcs(dst + i, half ? f.y : f.x);
         }
@@ -458,6 +459,21 @@ struct UnrolledRowsH2<BG, BgShape<BG>::kRows, FULL, MASKED> {
 
 // shared-window address of the packed hard decisions of both codewords (FULL kernels): behind the flags, the work slot
 // and the (unused here) barrier slot
+// one pair per CTA (FULL kernels): per-codeword load / store out of line, see load_group_ool in decode_kernel.cuh
+__device__ __noinline__ void load_pair_ool(const float *__restrict__ rowA, const float *__restrict__ rowB, uint32_t *app, int ncw, int lane, int nlanes) {
+    load_pair(rowA, rowB, app, ncw, lane, nlanes);
+}
+__device__ __noinline__ void store_half_ool(uint8_t *hard_base, float *soft_base, const int kcols, const int n_rows, const uint32_t *app, long long cw,
+                                            int half, int ncw, int K, int lane, int nlanes, const uint32_t *my_rec, const uint64_t pol) {
+    store_half(hard_base, soft_base, kcols, n_rows, app, cw, half, ncw, K, lane, nlanes, my_rec, pol);
+}
+template <bool FULL>
+__device__ __forceinline__ void store_half_sel(const DecArgs &a, const uint32_t *app, long long cw, int half, int ncw, int K, int lane, int nlanes,
+                                               const uint32_t *my_rec, const uint64_t pol) {
+    if (FULL) store_half_ool(a.hard, a.soft, a.kcols, a.n_rows, app, cw, half, ncw, K, lane, nlanes, my_rec, pol);   // by value: no generic loads of the parameters out of line
+    else store_half(a.hard, a.soft, a.kcols, a.n_rows, app, cw, half, ncw, K, lane, nlanes, my_rec, pol);
+}
+
 __device__ __forceinline__ uint32_t h2_hard_bits(int *s_flag, int cwpc) {
     return (((uint32_t)__cvta_generic_to_shared(s_flag + 4 * cwpc + 1) + 7u) & ~7u) + 8u;
 }
@@ -510,7 +526,10 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
         const long long cwA = cw0 + 2 * slot, cwB = cwA + 1;
         const bool active = lane_ok && 2 * slot < n_here;
         const bool has_b = lane_ok && 2 * slot + 1 < n_here;
-        if (active) load_pair(a.llr + cwA * ncw, has_b ? a.llr + cwB * ncw : nullptr, my_app, ncw, z, Z);
+        if (active) {
+            if (FULL) load_pair_ool(a.llr + cwA * ncw, has_b ? a.llr + cwB * ncw : nullptr, my_app, ncw, z, Z);
+            else load_pair(a.llr + cwA * ncw, has_b ? a.llr + cwB * ncw : nullptr, my_app, ncw, z, Z);
+        }
         for (int i = tid; i < 2 * per_group; i += blockDim.x) s_flag[i] = 0;
         __syncthreads();
 
@@ -567,14 +586,14 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
                 if (!fin_a) {
                     ok_a = (fu & 0x00008000u) ? 0 : 1;
                     if (ok_a && a.early_term) {   // converged: freeze this codeword's outputs now
-                        store_half(a, my_app, cwA, 0, ncw, K, z, Z, c.my_rec, c.pol);
+                        store_half_sel<FULL>(a, my_app, cwA, 0, ncw, K, z, Z, c.my_rec, c.pol);
                         fin_a = true;
                     }
                 }
                 if (!fin_b) {
                     ok_b = (fu & 0x80000000u) ? 0 : 1;
                     if (ok_b && a.early_term) {
-                        store_half(a, my_app, cwB, 1, ncw, K, z, Z, c.my_rec, c.pol);
+                        store_half_sel<FULL>(a, my_app, cwB, 1, ncw, K, z, Z, c.my_rec, c.pol);
                         fin_b = true;
                     }
                 }
@@ -586,8 +605,8 @@ __global__ void __launch_bounds__(kDecThreads, kDecCtasPerSm) decode_nms_h2_kern
         }
         __syncthreads();
 
-        if (active && !fin_a) store_half(a, my_app, cwA, 0, ncw, K, z, Z, c.my_rec, c.pol);
-        if (has_b && !fin_b) store_half(a, my_app, cwB, 1, ncw, K, z, Z, c.my_rec, c.pol);
+        if (active && !fin_a) store_half_sel<FULL>(a, my_app, cwA, 0, ncw, K, z, Z, c.my_rec, c.pol);
+        if (has_b && !fin_b) store_half_sel<FULL>(a, my_app, cwB, 1, ncw, K, z, Z, c.my_rec, c.pol);
         if (active && z == 0) {
             if (a.iters) a.iters[cwA] = it_a;
             if (a.ok) a.ok[cwA] = (uint8_t)ok_a;

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 b() {  # label, workload, dtype, env...
   local label=$1 wl=$2 dt=$3; shift 3
-  env "$@" python bench.py --workload $wl --steps 50 --warmup 3 --no-cpu-baseline --no-e2e --no-alt --llr-dtype $dt 2>&1 | tail -1 |
+  env "$@" python bench.py --workload $wl --steps 50 --warmup 3 --no-cpu-baseline --no-e2e --no-alt --no-side --llr-dtype $dt 2>&1 | tail -1 |
     python -c "import json,sys;d=json.loads(sys.stdin.read());print('$label $wl $dt',round(d['value'],3),'Gb/s',round(d['ms_per_step'],4),'ms iters',d['config']['mean_iters'],flush=True)"
 }
 for lib in ldpc_3gpp_matlab_b200/libnrldpc_b200.so build_variants/*.so; do
