@@ -271,6 +271,47 @@ def test_rate_match_and_recover_against_reference_loops(capi, O, A, BG, R, Qm, r
     h.close()
 
 
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_rate_recover_random_geometries(capi, O, seed, monkeypatch):
+    """Rate recovery over random rate-matching geometries (any E, k_0, N_cb, K', Q_m the C ABI accepts, including several laps of
+    the circular buffer = wrapped repetitions, limited buffers, filler, rows that do and do not qualify for the TMA kernel), two
+    transmissions with HARQ accumulation: the table-driven gather (default), the per-block closed form (NRLDPC_RR_TABLE=0) and the
+    oracle's literal restatement of the reference's while-loop (NRLDPCDecoder.m:172-242,262-264) agree bit for bit."""
+    rng = np.random.default_rng(9000 + seed)
+    for case in range(14):
+        bg = int(rng.integers(1, 3))
+        Z = int(rng.choice([2, 6, 13, 22, 36, 52, 80, 120]))
+        d = O.dims(bg, Z)
+        K, N = d["K"], d["N"]
+        Kp = int(rng.integers(max(1, K - 3 * Z), K + 1))
+        N_cb = N if rng.random() < 0.5 else int(rng.integers(max(K - 2 * Z + Z, N // 3), N + 1))
+        Qm = int(rng.choice([1, 2, 4, 6, 8]))
+        E = int(rng.integers(1, max(2, int(2.7 * N_cb)) // Qm + 1)) * Qm
+        k_0 = int(rng.integers(0, N_cb))
+        B = 3
+        outs = {}
+        for mode in ("1", "0"):
+            monkeypatch.setenv("NRLDPC_RR_TABLE", mode)
+            h = capi.Handle(bg, Z, 1)
+            harq = np.zeros((B, N), np.float32)
+            r2 = np.random.default_rng(case)
+            got = []
+            for tx in range(2):
+                llr_f = r2.normal(0, 3, (B, E)).astype(np.float32)
+                got.append((llr_f, h.rate_recover(llr_f, E, k_0, N_cb, Kp, Qm, harq=harq).copy()))
+            outs[mode] = got
+            h.close()
+        harq_ref = [np.zeros(N_cb, np.float32) for _ in range(B)]
+        for tx in range(2):
+            llr_f, g1 = outs["1"][tx]
+            g0 = outs["0"][tx][1]
+            assert (g1.view(np.uint32) == g0.view(np.uint32)).all(), (bg, Z, E, k_0, N_cb, Kp, Qm, tx)
+            for b in range(B):
+                d_t = O.bit_selection_rx(O.deinterleave_rx(llr_f[b], Qm), N, N_cb, k_0, Z, K, Kp, harq_buf=harq_ref[b])
+                want = O.d_to_cw_llr(d_t, Z)
+                assert (g1[b].view(np.uint32) == want.view(np.uint32)).all(), (bg, Z, E, k_0, N_cb, Kp, Qm, tx, b)
+
+
 def test_full_chain_system_objects(capi, O):
     """encode -> QPSK -> AWGN -> exact LLR -> decode through the NRLDPCEncoder/NRLDPCDecoder mirrors
     (plot_BLER_vs_SNR.m:118-146 for one frame per configuration), incl. C=2 segmentation and a_hat=[]."""
