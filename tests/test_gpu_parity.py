@@ -289,6 +289,16 @@ def test_rate_recover_random_geometries(capi, O, seed, monkeypatch):
         E = int(rng.integers(1, max(2, int(2.7 * N_cb)) // Qm + 1)) * Qm
         k_0 = int(rng.integers(0, N_cb))
         B = 3
+        # TX side of the same geometry: bit selection + interleaving against the literal loops (NRLDPCEncoder.m:168-225)
+        info = rng.integers(0, 2, (B, K), dtype=np.uint8)
+        info[:, Kp:] = 0
+        h = capi.Handle(bg, Z, 1)
+        cw = h.encode(info)
+        f_tx = h.rate_match(cw, E, k_0, N_cb, Kp, Qm)
+        h.close()
+        for b in range(B):
+            d_tx = O.cw_to_d(Z, K, Kp, N, cw[b])
+            assert (f_tx[b] == O.interleave_tx(O.bit_selection_tx(d_tx, N_cb, k_0, E), Qm)).all(), ("tx", bg, Z, E, k_0, N_cb, Kp, Qm, b)
         outs = {}
         for mode in ("1", "0"):
             monkeypatch.setenv("NRLDPC_RR_TABLE", mode)
