@@ -11,6 +11,9 @@
 //     h     = nrldpc_mex('create', BG, Z, max_iters, early_term, alpha, llr_dtype, algorithm);
 //             algorithm: 0 = layered normalized min-sum (default), 1 = the reference's flooding sum-product in float64
 //     c_hat = nrldpc_mex('decode', h, cw_tilde, n_rows);   % cw_tilde: (68Z or 52Z) x batch double, +inf = filler
+//             cw_tilde may also be SINGLE (half the host bytes; min-sum modes) or INT8 with a scale as fifth argument:
+//             c_hat = nrldpc_mex('decode', h, int8(q), n_rows, scale)  % llr = scale*q, q = 127 marks filler (a quarter of
+//             the PCIe bytes of float32: nrldpc_decode8)
 //     [c_hat, num_iters, parity_ok] = nrldpc_mex('decode', ...)   % as comm.LDPCDecoder's NumIterationsOutputPort /
 //                                                                 % FinalParityChecksOutputPort (1 x batch each)
 //     cw    = nrldpc_mex('encode', h, c);                  % c: K x batch, values 0/1
@@ -79,8 +82,8 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         // MATLAB passes a column-major (n_cw x batch) double matrix: each column is one cw_tilde
         // (NRLDPCDecoder.m:262-264), i.e. exactly the row-major [batch][n_cw] layout of the C ABI.
         const mxArray *in = prhs[2];
-        if (!mxIsDouble(in) || (int)mxGetM(in) != d.n_cw)
-            mexErrMsgIdAndTxt("ldpc_3gpp_matlab:Error", "cw_tilde should have %d rows.", d.n_cw);
+        if (!(mxIsDouble(in) || mxIsSingle(in) || mxIsInt8(in)) || (int)mxGetM(in) != d.n_cw)
+            mexErrMsgIdAndTxt("ldpc_3gpp_matlab:Error", "cw_tilde should be a double, single or int8 matrix with %d rows.", d.n_cw);
         const int64_t batch = (int64_t)mxGetN(in);
         const int n_rows = nrhs > 3 ? (int)mxGetScalar(prhs[3]) : 0;
         // the doubles go to the library as they are (nrldpc_decode64, ordinary pageable MATLAB memory): the sum-product
@@ -93,8 +96,17 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         uint8_t *hard = reinterpret_cast<uint8_t *>(mxGetLogicals(plhs[0]));
         std::vector<int32_t> iters(nlhs > 1 ? (size_t)batch : 0);
         std::vector<uint8_t> ok(nlhs > 2 ? (size_t)batch : 0);
-        check(nrldpc_decode64(h, mxGetPr(in), batch, n_rows, hard, nullptr, nlhs > 1 ? iters.data() : nullptr,
-                              nlhs > 2 ? ok.data() : nullptr, NRLDPC_MEM_HOST, nullptr), h);
+        int32_t *it_p = nlhs > 1 ? iters.data() : nullptr;
+        uint8_t *ok_p = nlhs > 2 ? ok.data() : nullptr;
+        if (mxIsDouble(in)) {
+            check(nrldpc_decode64(h, mxGetPr(in), batch, n_rows, hard, nullptr, it_p, ok_p, NRLDPC_MEM_HOST, nullptr), h);
+        } else if (mxIsSingle(in)) {       // single(cw_tilde): the C ABI's own type, copied into the pinned ring by host threads
+            check(nrldpc_decode(h, static_cast<const float *>(mxGetData(in)), batch, n_rows, hard, nullptr, it_p, ok_p, NRLDPC_MEM_HOST, nullptr), h);
+        } else {                           // int8 codes with a scale: llr = scale * q, 127 = filler
+            if (nrhs < 5) mexErrMsgIdAndTxt("ldpc_3gpp_matlab:Error", "usage: nrldpc_mex('decode', h, int8(q), n_rows, scale)");
+            check(nrldpc_decode8(h, static_cast<const int8_t *>(mxGetData(in)), (float)mxGetScalar(prhs[4]), batch, n_rows, hard, nullptr,
+                                 it_p, ok_p, NRLDPC_MEM_HOST, nullptr), h);
+        }
         if (nlhs > 1) {
             plhs[1] = mxCreateDoubleMatrix(1, batch, mxREAL);
             for (int64_t i = 0; i < batch; ++i) mxGetPr(plhs[1])[i] = iters[i];

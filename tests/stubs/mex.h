@@ -19,12 +19,15 @@ extern "C" {
 typedef struct mxArray_tag mxArray;
 typedef bool mxLogical;
 typedef size_t mwSize;
-typedef enum { mxUNKNOWN_CLASS = 0, mxLOGICAL_CLASS = 3, mxCHAR_CLASS = 4, mxDOUBLE_CLASS = 6, mxUINT8_CLASS = 9, mxUINT64_CLASS = 15 } mxClassID;
+typedef enum { mxUNKNOWN_CLASS = 0, mxLOGICAL_CLASS = 3, mxCHAR_CLASS = 4, mxDOUBLE_CLASS = 6, mxSINGLE_CLASS = 7, mxINT8_CLASS = 8,
+               mxUINT8_CLASS = 9, mxUINT64_CLASS = 15 } mxClassID;
 typedef enum { mxREAL = 0, mxCOMPLEX = 1 } mxComplexity;
 
 bool mxIsChar(const mxArray *a);
 bool mxIsDouble(const mxArray *a);
 bool mxIsLogical(const mxArray *a);
+bool mxIsSingle(const mxArray *a);
+bool mxIsInt8(const mxArray *a);
 bool mxIsUint64(const mxArray *a);
 size_t mxGetM(const mxArray *a);
 size_t mxGetN(const mxArray *a);

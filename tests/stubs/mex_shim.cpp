@@ -33,6 +33,8 @@ bool mxIsChar(const mxArray *a) { return a && a->cls == mxCHAR_CLASS; }
 bool mxIsDouble(const mxArray *a) { return a && a->cls == mxDOUBLE_CLASS; }
 bool mxIsLogical(const mxArray *a) { return a && a->cls == mxLOGICAL_CLASS; }
 bool mxIsUint64(const mxArray *a) { return a && a->cls == mxUINT64_CLASS; }
+bool mxIsSingle(const mxArray *a) { return a && a->cls == mxSINGLE_CLASS; }
+bool mxIsInt8(const mxArray *a) { return a && a->cls == mxINT8_CLASS; }
 size_t mxGetM(const mxArray *a) { return a->m; }
 size_t mxGetN(const mxArray *a) { return a->n; }
 size_t mxGetNumberOfElements(const mxArray *a) { return a->m * a->n; }
@@ -45,6 +47,8 @@ double mxGetScalar(const mxArray *a) {
         case mxLOGICAL_CLASS: return *static_cast<mxLogical *>(a->data) ? 1.0 : 0.0;
         case mxUINT64_CLASS: return (double)*static_cast<uint64_t *>(a->data);
         case mxUINT8_CLASS: return (double)*static_cast<uint8_t *>(a->data);
+        case mxSINGLE_CLASS: return (double)*static_cast<float *>(a->data);
+        case mxINT8_CLASS: return (double)*static_cast<int8_t *>(a->data);
         default: return 0.0;
     }
 }
@@ -57,7 +61,7 @@ int mxGetString(const mxArray *a, char *buf, mwSize buflen) {
     return n >= buflen;
 }
 mxArray *mxCreateNumericMatrix(mwSize m, mwSize n, mxClassID cls, mxComplexity) {
-    const size_t elt = cls == mxDOUBLE_CLASS || cls == mxUINT64_CLASS ? 8 : 1;
+    const size_t elt = cls == mxDOUBLE_CLASS || cls == mxUINT64_CLASS ? 8 : cls == mxSINGLE_CLASS ? 4 : 1;
     return make(m, n, cls, elt);
 }
 mxArray *mxCreateDoubleMatrix(mwSize m, mwSize n, mxComplexity) { return make(m, n, mxDOUBLE_CLASS, 8); }
@@ -94,6 +98,16 @@ mxArray *shim_logical(const uint8_t *colmajor, size_t m, size_t n) {
 }
 mxArray *shim_uint8(const uint8_t *colmajor, size_t m, size_t n) {
     mxArray *a = make(m, n, mxUINT8_CLASS, 1);
+    memcpy(a->data, colmajor, m * n);
+    return a;
+}
+mxArray *shim_single(const float *colmajor, size_t m, size_t n) {
+    mxArray *a = make(m, n, mxSINGLE_CLASS, 4);
+    memcpy(a->data, colmajor, m * n * 4);
+    return a;
+}
+mxArray *shim_int8(const int8_t *colmajor, size_t m, size_t n) {
+    mxArray *a = make(m, n, mxINT8_CLASS, 1);
     memcpy(a->data, colmajor, m * n);
     return a;
 }

@@ -33,6 +33,7 @@ class Mex:
         vp = C.c_void_p
         for name, res, args in (("shim_string", vp, [C.c_char_p]), ("shim_double", vp, [vp, C.c_size_t, C.c_size_t]),
                                 ("shim_logical", vp, [vp, C.c_size_t, C.c_size_t]), ("shim_uint8", vp, [vp, C.c_size_t, C.c_size_t]),
+                                ("shim_single", vp, [vp, C.c_size_t, C.c_size_t]), ("shim_int8", vp, [vp, C.c_size_t, C.c_size_t]),
                                 ("shim_class", C.c_int, [vp]), ("mxGetM", C.c_size_t, [vp]), ("mxGetN", C.c_size_t, [vp]),
                                 ("mxGetData", vp, [vp]), ("mxDestroyArray", None, [vp]),
                                 ("shim_mex", C.c_int, [C.c_int, C.POINTER(vp), C.c_int, C.POINTER(vp), C.c_char_p, C.c_char_p, C.c_size_t])):
@@ -58,6 +59,10 @@ class Mex:
             return L.shim_logical(f.ctypes.data, m, n)
         if a.dtype == np.uint8:
             return L.shim_uint8(f.ctypes.data, m, n)
+        if a.dtype == np.float32:
+            return L.shim_single(f.ctypes.data, m, n)
+        if a.dtype == np.int8:
+            return L.shim_int8(f.ctypes.data, m, n)
         f = np.asfortranarray(a.astype(np.float64))
         return L.shim_double(f.ctypes.data, m, n)
 
@@ -158,6 +163,21 @@ def test_gateway_decode_matches_oracle(mex, O, bg, Z, E, esn0):
     with pytest.raises(MexError) as e:
         mex("decode", h, cw_tilde, 2.0)                                   # n_rows out of range
     assert e.value.identifier == ID_UNSUPPORTED
+    # single(cw_tilde): same decisions (the min-sum kernels compute in float32 anyway); int8 codes with a scale: equal to the oracle
+    # on the de-quantised values
+    c32 = mex("decode", h, cw_tilde.astype(np.float32), 0.0)
+    assert (c32.T.astype(np.uint8) == ref["hard"]).all()
+    scale = 0.25
+    q = np.clip(np.rint(np.nan_to_num(llr, posinf=0.0) / scale), -127, 126).astype(np.int8)
+    q[np.isposinf(llr)] = 127
+    deq = (np.float32(scale) * q.astype(np.float32)).astype(np.float32)
+    deq[q == 127] = np.inf
+    c8, it8 = mex("decode", h, np.ascontiguousarray(q.T), 0.0, scale, nlhs=2)
+    ref8 = O.decode_nms(bg, Z, deq, 8, early_term=True)
+    assert (c8.T.astype(np.uint8) == ref8["hard"]).all() and (it8.ravel() == ref8["iters"]).all()
+    with pytest.raises(MexError) as e:
+        mex("decode", h, np.ascontiguousarray(q.T), 0.0)                  # int8 without a scale
+    assert e.value.identifier == ID_ERROR
     mex("destroy", h, nlhs=0)
     # the reference's own algorithm on the reference's own doubles
     h = mex("create", float(bg), float(Z), 8.0, 1.0, 0.75, 0.0, 1.0)
